@@ -1,0 +1,556 @@
+// C ABI (include/b200ba.h): handle, workspace, LM loop orchestration, CUDA-graph capture,
+// host-pointer variants, NCCL plumbing for the shard-by-point multi-GPU path.
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/b200ba.h"
+#include "ba_kernels.cuh"
+
+using namespace ba;
+
+// ------------------------------------------------------------------------------------------
+// NCCL through dlopen: the single-GPU path must not depend on libnccl being present
+// ------------------------------------------------------------------------------------------
+namespace {
+typedef struct { char internal[128]; } nccl_uid;
+typedef void* nccl_comm;
+typedef int (*fn_get_uid)(nccl_uid*);
+typedef int (*fn_init_rank)(nccl_comm*, int, nccl_uid, int);
+typedef int (*fn_destroy)(nccl_comm);
+typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t);
+typedef const char* (*fn_errstr)(int);
+struct NcclApi {
+  void* lib = nullptr;
+  fn_get_uid get_uid = nullptr;
+  fn_init_rank init_rank = nullptr;
+  fn_destroy destroy = nullptr;
+  fn_allreduce allreduce = nullptr;
+  fn_errstr errstr = nullptr;
+};
+NcclApi g_nccl;
+bool load_nccl() {
+  if (g_nccl.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    void* h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) continue;
+    g_nccl.get_uid = (fn_get_uid)dlsym(h, "ncclGetUniqueId");
+    g_nccl.init_rank = (fn_init_rank)dlsym(h, "ncclCommInitRank");
+    g_nccl.destroy = (fn_destroy)dlsym(h, "ncclCommDestroy");
+    g_nccl.allreduce = (fn_allreduce)dlsym(h, "ncclAllReduce");
+    g_nccl.errstr = (fn_errstr)dlsym(h, "ncclGetErrorString");
+    if (g_nccl.get_uid && g_nccl.init_rank && g_nccl.destroy && g_nccl.allreduce) {
+      g_nccl.lib = h;
+      return true;
+    }
+    dlclose(h);
+  }
+  return false;
+}
+constexpr int kNcclDouble = 8, kNcclSum = 0;
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct ba_handle {
+  int device = 0;
+  int sm_count = 148;
+  ba_params prm;
+  std::string err;
+  // workspace
+  DevBuf pose0, pose1, X0, X1, red, dp, ctl, cand;
+  // staging for the host-pointer API
+  DevBuf d_R, d_t, d_fixed, d_X, d_ocam, d_opt, d_ouv, d_off, d_flags, d_hist, d_acc, d_foff;
+  LmCtl* h_ctl = nullptr;         // pinned
+  cudaStream_t stream = nullptr;  // used by the host API
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // CUDA graph cache of the LM loop
+  cudaGraphExec_t graph = nullptr;
+  struct GraphKey {
+    int n_cam = -1, n_pt = -1, n_obs = -1, max_iter = -1, schur = -1, world = -1;
+    const void* ptrs[10] = {0};
+    double scal[12] = {0};
+    bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
+  } graph_key;
+  int graph_launches = 0;
+  // multi-GPU
+  nccl_comm comm = nullptr;
+  int rank = 0, world = 1;
+};
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                        \
+      return BA_ERR_CUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+static int ensure(ba_handle* h, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return BA_OK;
+  if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+  size_t cap = bytes + bytes / 4 + 256;
+  CK(cudaMalloc(&b.p, cap));
+  b.cap = cap;
+  if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; h->graph_key = ba_handle::GraphKey(); }
+  return BA_OK;
+}
+
+extern "C" int ba_version(void) { return 100; }
+
+extern "C" const char* ba_error_string(int code) {
+  switch (code) {
+    case BA_OK: return "ok";
+    case BA_ERR_INVALID: return "invalid argument";
+    case BA_ERR_CUDA: return "CUDA error";
+    case BA_ERR_TOO_LARGE: return "problem too large for the selected solver";
+    case BA_ERR_NCCL: return "NCCL error";
+    case BA_ERR_NO_DEVICE: return "no CUDA device (this solver has no CPU fallback)";
+    default: return "unknown error";
+  }
+}
+
+extern "C" const char* ba_last_error(const ba_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+extern "C" void ba_default_params(ba_params* p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->huber_delta = 5.0;
+  p->chi2_thr = 5.991;
+  p->lambda0 = 1e-4;
+  p->lambda_up = 10.0;
+  p->lambda_down = 0.1;
+  p->lambda_min = 1e-9;
+  p->lambda_max = 1e8;
+  p->max_iter = 10;
+  p->solver_kind = BA_SOLVER_AUTO;
+  p->schur_kind = BA_SCHUR_AUTO;
+  p->pcg_max_iter = 200;
+  p->pcg_tol = 1e-10;
+  p->use_graph = 1;
+}
+
+static int check_params(const ba_params* p) {
+  if (!p) return BA_ERR_INVALID;
+  if (p->max_iter < 0 || p->max_iter > BA_MAX_ITER) return BA_ERR_INVALID;
+  if (!(p->huber_delta > 0) || !(p->lambda0 > 0) || !(p->lambda_up >= 1) || !(p->lambda_down > 0))
+    return BA_ERR_INVALID;
+  return BA_OK;
+}
+
+extern "C" int ba_create(const ba_params* params, int device, ba_handle** out) {
+  if (!out) return BA_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return BA_ERR_NO_DEVICE;
+  if (device < 0 || device >= ndev) return BA_ERR_INVALID;
+  ba_params p;
+  if (params) p = *params; else ba_default_params(&p);
+  if (check_params(&p) != BA_OK) return BA_ERR_INVALID;
+  ba_handle* h = new ba_handle();
+  h->device = device;
+  h->prm = p;
+  if (cudaSetDevice(device) != cudaSuccess) { delete h; return BA_ERR_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+  if (configure_kernels() != 0) { delete h; return BA_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+      cudaMallocHost((void**)&h->h_ctl, sizeof(LmCtl)) != cudaSuccess) {
+    delete h;
+    return BA_ERR_CUDA;
+  }
+  *out = h;
+  return BA_OK;
+}
+
+extern "C" int ba_set_params(ba_handle* h, const ba_params* params) {
+  if (!h || check_params(params) != BA_OK) return BA_ERR_INVALID;
+  h->prm = *params;
+  return BA_OK;
+}
+
+extern "C" int ba_destroy(ba_handle* h) {
+  if (!h) return BA_OK;
+  cudaSetDevice(h->device);
+  if (h->graph) cudaGraphExecDestroy(h->graph);
+  DevBuf* bufs[] = {&h->pose0, &h->pose1, &h->X0, &h->X1, &h->red, &h->dp, &h->ctl, &h->cand,
+                    &h->d_R, &h->d_t, &h->d_fixed, &h->d_X, &h->d_ocam, &h->d_opt, &h->d_ouv,
+                    &h->d_off, &h->d_flags, &h->d_hist, &h->d_acc, &h->d_foff};
+  for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+  if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
+  if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return BA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// local BA
+// ------------------------------------------------------------------------------------------
+static int make_work(ba_handle* h, int n_cam, int n_pt, int n_obs, const double intr[4],
+                     const uint8_t* fixed, const int32_t* obs_cam, const int32_t* obs_pt,
+                     const float* obs_uv, const int32_t* pt_off, Work& w) {
+  const int n = 6 * n_cam;
+  int rc;
+  if ((rc = ensure(h, h->pose0, sizeof(double) * 12 * (size_t)n_cam))) return rc;
+  if ((rc = ensure(h, h->pose1, sizeof(double) * 12 * (size_t)n_cam))) return rc;
+  if ((rc = ensure(h, h->X0, sizeof(float) * 3 * (size_t)(n_pt + 1)))) return rc;
+  if ((rc = ensure(h, h->X1, sizeof(float) * 3 * (size_t)(n_pt + 1)))) return rc;
+  if ((rc = ensure(h, h->red, sizeof(double) * ((size_t)n * n + 2 * (size_t)n + 1)))) return rc;
+  if ((rc = ensure(h, h->dp, sizeof(double) * (size_t)(n + 1)))) return rc;
+  if ((rc = ensure(h, h->ctl, sizeof(LmCtl)))) return rc;
+  if ((rc = ensure(h, h->cand, sizeof(double) * 2))) return rc;
+  w.n_cam = n_cam; w.n_pt = n_pt; w.n_obs = n_obs; w.n = n;
+  w.K = Intr{intr[0], intr[1], intr[2], intr[3]};
+  w.obs_cam = obs_cam; w.obs_pt = obs_pt; w.obs_uv = obs_uv; w.pt_off = pt_off; w.fixed = fixed;
+  w.pose[0] = (double*)h->pose0.p; w.pose[1] = (double*)h->pose1.p;
+  w.X[0] = (float*)h->X0.p; w.X[1] = (float*)h->X1.p;
+  w.S = (double*)h->red.p;
+  w.b = w.S + (size_t)n * n;
+  w.diagU = w.b + n;
+  w.cost_lin = w.diagU + n;
+  w.cost_cand = (double*)h->cand.p;
+  w.dp = (double*)h->dp.p;
+  w.ctl = (LmCtl*)h->ctl.p;
+  w.world = h->world;
+  return BA_OK;
+}
+
+static int pick_schur(const ba_handle* h, const Work& w) {
+  int kind = h->prm.schur_kind;
+  if (kind == BA_SCHUR_AUTO) kind = tiled_supported(w.n_cam) ? BA_SCHUR_TILED : BA_SCHUR_SCATTER;
+  if (kind == BA_SCHUR_TILED && !tiled_supported(w.n_cam)) kind = BA_SCHUR_SCATTER;
+  return kind;
+}
+
+// enqueue the LM iterations (no init / finalize); returns kernels launched or < 0
+static int enqueue_lm_loop(ba_handle* h, const Work& w, int schur, cudaStream_t s) {
+  int launches = 0;
+  const size_t nred = (size_t)w.n * w.n + 2 * (size_t)w.n + 1;
+  for (int it = 0; it < h->prm.max_iter; ++it) {
+    launches += (schur == BA_SCHUR_TILED) ? launch_linearize_tiled(w, h->sm_count, s)
+                                          : launch_linearize_scatter(w, h->sm_count, s);
+    if (h->world > 1) {
+      int r = g_nccl.allreduce(w.S, w.S, nred, kNcclDouble, kNcclSum, h->comm, s);
+      if (r != 0) { h->err = std::string("ncclAllReduce(S): ") + (g_nccl.errstr ? g_nccl.errstr(r) : "?"); return BA_ERR_NCCL; }
+    }
+    launches += launch_rcs_cholesky(w, s);
+    launches += launch_backsub(w, h->sm_count, s);
+    if (h->world > 1) {
+      int r = g_nccl.allreduce(w.cost_cand, w.cost_cand, 1, kNcclDouble, kNcclSum, h->comm, s);
+      if (r != 0) { h->err = std::string("ncclAllReduce(cost): ") + (g_nccl.errstr ? g_nccl.errstr(r) : "?"); return BA_ERR_NCCL; }
+      launches += launch_accept(w, s);
+    }
+  }
+  return launches;
+}
+
+static void fill_report(const ba_handle* h, const LmCtl* c, ba_report* rep, int status, float ms,
+                        int launches) {
+  memset(rep, 0, sizeof(*rep));
+  rep->status = status;
+  rep->n_iter = c->iter;
+  rep->n_accepted = c->n_accepted;
+  rep->solver_used = BA_SOLVER_CHOLESKY;
+  for (int i = 0; i <= BA_MAX_ITER; ++i) rep->cost_hist[i] = c->cost_hist[i];
+  for (int i = 0; i < BA_MAX_ITER; ++i) {
+    rep->cand_cost_hist[i] = c->cand_hist[i];
+    rep->lambda_hist[i] = c->lambda_hist[i];
+    rep->accepted[i] = c->accepted[i];
+    rep->solve_fail[i] = c->solve_fail_hist[i];
+    rep->pcg_iters[i] = c->pcg_iters_hist[i];
+  }
+  rep->gpu_ms = ms;
+  rep->n_launches = launches;
+  (void)h;
+}
+
+extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t n_obs,
+                              const double intr[4], double* cam_R, double* cam_t,
+                              const uint8_t* cam_fixed, float* X, const int32_t* obs_cam,
+                              const int32_t* obs_pt, const float* obs_uv, const int32_t* pt_offsets,
+                              uint8_t* flags, void* stream, ba_report* report) {
+  if (!h) return BA_ERR_INVALID;
+  if (n_cam <= 0 || n_pt < 0 || n_obs < 0 || !intr || !cam_R || !cam_t || !cam_fixed ||
+      (n_pt > 0 && (!X || !pt_offsets)) || (n_obs > 0 && (!obs_cam || !obs_pt || !obs_uv)))
+    return BA_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (6 * n_cam > rcs_cholesky_max_n() || h->prm.solver_kind == BA_SOLVER_PCG) {
+    h->err = "reduced camera system larger than the in-shared-memory Cholesky (PCG path not built yet)";
+    return BA_ERR_TOO_LARGE;
+  }
+  Work w;
+  int rc = make_work(h, n_cam, n_pt, n_obs, intr, cam_fixed, obs_cam, obs_pt, obs_uv, pt_offsets, w);
+  if (rc) return rc;
+  const int schur = pick_schur(h, w);
+  LmInit li{h->prm.lambda0, h->prm.huber_delta, h->prm.chi2_thr, h->prm.lambda_up,
+            h->prm.lambda_down, h->prm.lambda_min, h->prm.lambda_max};
+
+  int launches = 0;
+  CK(cudaEventRecord(h->ev0, s));
+  launches += launch_init(w, cam_R, cam_t, X, li, s);
+
+  bool use_graph = h->prm.use_graph != 0 && h->prm.max_iter > 0;
+  if (use_graph) {
+    ba_handle::GraphKey key;
+    key.n_cam = n_cam; key.n_pt = n_pt; key.n_obs = n_obs; key.max_iter = h->prm.max_iter;
+    key.schur = schur; key.world = h->world;
+    const void* ptrs[10] = {cam_fixed, obs_cam, obs_pt, obs_uv, pt_offsets, w.S, w.pose[0], w.X[0], w.ctl, w.dp};
+    memcpy(key.ptrs, ptrs, sizeof(ptrs));
+    key.scal[0] = intr[0]; key.scal[1] = intr[1]; key.scal[2] = intr[2]; key.scal[3] = intr[3];
+    if (!(h->graph && key == h->graph_key)) {
+      if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+      cudaGraph_t g = nullptr;
+      cudaStream_t cs = h->stream;
+      CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      int n = enqueue_lm_loop(h, w, schur, cs);
+      cudaError_t ce = cudaStreamEndCapture(cs, &g);
+      if (n < 0) { if (g) cudaGraphDestroy(g); return n; }
+      if (ce != cudaSuccess) { h->err = std::string("graph capture: ") + cudaGetErrorString(ce); return BA_ERR_CUDA; }
+      ce = cudaGraphInstantiate(&h->graph, g, 0);
+      cudaGraphDestroy(g);
+      if (ce != cudaSuccess) { h->graph = nullptr; h->err = std::string("graph instantiate: ") + cudaGetErrorString(ce); return BA_ERR_CUDA; }
+      h->graph_key = key;
+      h->graph_launches = n;
+    }
+    CK(cudaGraphLaunch(h->graph, s));
+    launches += h->graph_launches;
+  } else {
+    int n = enqueue_lm_loop(h, w, schur, s);
+    if (n < 0) return n;
+    launches += n;
+  }
+  launches += launch_finalize(w, cam_R, cam_t, X, flags, s);
+  CK(cudaEventRecord(h->ev1, s));
+  CK(cudaGetLastError());
+  if (report) {
+    CK(cudaMemcpyAsync(h->h_ctl, w.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    fill_report(h, h->h_ctl, report, BA_OK, ms, launches);
+  }
+  return BA_OK;
+}
+
+extern "C" int ba_solve_local_host(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t n_obs,
+                                   const double intr[4], double* cam_R, double* cam_t,
+                                   const uint8_t* cam_fixed, float* X, const int32_t* obs_cam,
+                                   const int32_t* obs_pt, const float* obs_uv,
+                                   const int32_t* pt_offsets, uint8_t* flags, ba_report* report) {
+  if (!h) return BA_ERR_INVALID;
+  if (n_cam <= 0 || n_pt < 0 || n_obs < 0 || !intr || !cam_R || !cam_t || !cam_fixed ||
+      (n_pt > 0 && (!X || !pt_offsets)) || (n_obs > 0 && (!obs_cam || !obs_pt || !obs_uv)))
+    return BA_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  int rc;
+  if ((rc = ensure(h, h->d_R, sizeof(double) * 9 * (size_t)n_cam))) return rc;
+  if ((rc = ensure(h, h->d_t, sizeof(double) * 3 * (size_t)n_cam))) return rc;
+  if ((rc = ensure(h, h->d_fixed, (size_t)n_cam))) return rc;
+  if ((rc = ensure(h, h->d_X, sizeof(float) * 3 * (size_t)(n_pt + 1)))) return rc;
+  if ((rc = ensure(h, h->d_ocam, sizeof(int32_t) * (size_t)(n_obs + 1)))) return rc;
+  if ((rc = ensure(h, h->d_opt, sizeof(int32_t) * (size_t)(n_obs + 1)))) return rc;
+  if ((rc = ensure(h, h->d_ouv, sizeof(float) * 2 * (size_t)(n_obs + 1)))) return rc;
+  if ((rc = ensure(h, h->d_off, sizeof(int32_t) * (size_t)(n_pt + 1)))) return rc;
+  if ((rc = ensure(h, h->d_flags, (size_t)(n_obs + 1)))) return rc;
+  CK(cudaMemcpyAsync(h->d_R.p, cam_R, sizeof(double) * 9 * (size_t)n_cam, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->d_t.p, cam_t, sizeof(double) * 3 * (size_t)n_cam, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->d_fixed.p, cam_fixed, (size_t)n_cam, cudaMemcpyHostToDevice, s));
+  if (n_pt > 0) {
+    CK(cudaMemcpyAsync(h->d_X.p, X, sizeof(float) * 3 * (size_t)n_pt, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_off.p, pt_offsets, sizeof(int32_t) * (size_t)(n_pt + 1), cudaMemcpyHostToDevice, s));
+  }
+  if (n_obs > 0) {
+    CK(cudaMemcpyAsync(h->d_ocam.p, obs_cam, sizeof(int32_t) * (size_t)n_obs, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_opt.p, obs_pt, sizeof(int32_t) * (size_t)n_obs, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_ouv.p, obs_uv, sizeof(float) * 2 * (size_t)n_obs, cudaMemcpyHostToDevice, s));
+  }
+  rc = ba_solve_local(h, n_cam, n_pt, n_obs, intr, (double*)h->d_R.p, (double*)h->d_t.p,
+                      (const uint8_t*)h->d_fixed.p, (float*)h->d_X.p, (const int32_t*)h->d_ocam.p,
+                      (const int32_t*)h->d_opt.p, (const float*)h->d_ouv.p,
+                      (const int32_t*)h->d_off.p, flags ? (uint8_t*)h->d_flags.p : nullptr, s, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(cam_R, h->d_R.p, sizeof(double) * 9 * (size_t)n_cam, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(cam_t, h->d_t.p, sizeof(double) * 3 * (size_t)n_cam, cudaMemcpyDeviceToHost, s));
+  if (n_pt > 0) CK(cudaMemcpyAsync(X, h->d_X.p, sizeof(float) * 3 * (size_t)n_pt, cudaMemcpyDeviceToHost, s));
+  if (flags && n_obs > 0) CK(cudaMemcpyAsync(flags, h->d_flags.p, (size_t)n_obs, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h->h_ctl, h->ctl.p, sizeof(LmCtl), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (report) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    int launches = 2 + (h->prm.use_graph ? h->graph_launches
+                                         : h->prm.max_iter * (h->world > 1 ? 4 : 3));
+    fill_report(h, h->h_ctl, report, BA_OK, ms, launches);
+  }
+  return BA_OK;
+}
+
+extern "C" int ba_eval_cost(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t n_obs,
+                            const double intr[4], const double* cam_R, const double* cam_t,
+                            const float* X, const int32_t* obs_cam, const int32_t* obs_pt,
+                            const float* obs_uv, void* stream, double* cost_out) {
+  if (!h || !cost_out || n_cam <= 0) return BA_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  Work w;
+  int rc = make_work(h, n_cam, n_pt, n_obs, intr, nullptr, obs_cam, obs_pt, obs_uv, nullptr, w);
+  if (rc) return rc;
+  LmInit li{h->prm.lambda0, h->prm.huber_delta, h->prm.chi2_thr, h->prm.lambda_up,
+            h->prm.lambda_down, h->prm.lambda_min, h->prm.lambda_max};
+  launch_init(w, cam_R, cam_t, X, li, s);
+  launch_eval_cost(w, w.pose[0], w.X[0], w.cost_cand, h->prm.huber_delta, s);
+  CK(cudaMemcpyAsync(cost_out, w.cost_cand, sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaMemsetAsync(w.cost_cand, 0, sizeof(double), s));
+  return BA_OK;
+}
+
+extern "C" int ba_debug_linearize(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t n_obs,
+                                  const double intr[4], const double* cam_R, const double* cam_t,
+                                  const uint8_t* cam_fixed, const float* X, const int32_t* obs_cam,
+                                  const int32_t* obs_pt, const float* obs_uv,
+                                  const int32_t* pt_offsets, double lambda, void* stream,
+                                  double* S_host, double* b_host, double* diagU_host,
+                                  double* cost_host) {
+  if (!h || n_cam <= 0) return BA_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  Work w;
+  int rc = make_work(h, n_cam, n_pt, n_obs, intr, cam_fixed, obs_cam, obs_pt, obs_uv, pt_offsets, w);
+  if (rc) return rc;
+  LmInit li{lambda, h->prm.huber_delta, h->prm.chi2_thr, h->prm.lambda_up,
+            h->prm.lambda_down, h->prm.lambda_min, h->prm.lambda_max};
+  launch_init(w, cam_R, cam_t, X, li, s);
+  if (pick_schur(h, w) == BA_SCHUR_TILED) launch_linearize_tiled(w, h->sm_count, s);
+  else launch_linearize_scatter(w, h->sm_count, s);
+  const size_t n = (size_t)w.n;
+  if (S_host) CK(cudaMemcpyAsync(S_host, w.S, sizeof(double) * n * n, cudaMemcpyDeviceToHost, s));
+  if (b_host) CK(cudaMemcpyAsync(b_host, w.b, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  if (diagU_host) CK(cudaMemcpyAsync(diagU_host, w.diagU, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  if (cost_host) CK(cudaMemcpyAsync(cost_host, w.cost_lin, sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  return BA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// pose-only
+// ------------------------------------------------------------------------------------------
+extern "C" int ba_solve_pose_only(ba_handle* h, int32_t n_frames, int32_t n_match,
+                                  const double intr[4], double* R, double* t, const float* X,
+                                  const float* uv, const int32_t* frame_offsets, uint8_t* flags,
+                                  double* cost_hist, uint8_t* accepted, void* stream) {
+  if (!h || n_frames < 0 || n_match < 0 || !intr) return BA_ERR_INVALID;
+  if (n_frames == 0) return BA_OK;
+  if (!R || !t || !frame_offsets || (n_match > 0 && (!X || !uv))) return BA_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  PoseWork w;
+  w.n_frames = n_frames;
+  w.K = Intr{intr[0], intr[1], intr[2], intr[3]};
+  w.R = R; w.t = t; w.X = X; w.uv = uv; w.frame_off = frame_offsets;
+  w.flags = flags; w.cost_hist = cost_hist; w.accepted = accepted;
+  w.max_iter = h->prm.max_iter;
+  w.huber_delta = h->prm.huber_delta; w.chi2_thr = h->prm.chi2_thr; w.lambda0 = h->prm.lambda0;
+  w.lambda_up = h->prm.lambda_up; w.lambda_down = h->prm.lambda_down;
+  w.lambda_min = h->prm.lambda_min; w.lambda_max = h->prm.lambda_max;
+  launch_pose_only(w, (cudaStream_t)stream);
+  CK(cudaGetLastError());
+  return BA_OK;
+}
+
+extern "C" int ba_solve_pose_only_host(ba_handle* h, int32_t n_frames, int32_t n_match,
+                                       const double intr[4], double* R, double* t, const float* X,
+                                       const float* uv, const int32_t* frame_offsets,
+                                       uint8_t* flags, double* cost_hist, uint8_t* accepted,
+                                       float* gpu_ms) {
+  if (!h || n_frames < 0 || n_match < 0 || !intr) return BA_ERR_INVALID;
+  if (n_frames == 0) return BA_OK;
+  if (!R || !t || !frame_offsets || (n_match > 0 && (!X || !uv))) return BA_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int mi = h->prm.max_iter;
+  int rc;
+  if ((rc = ensure(h, h->d_R, sizeof(double) * 9 * (size_t)n_frames))) return rc;
+  if ((rc = ensure(h, h->d_t, sizeof(double) * 3 * (size_t)n_frames))) return rc;
+  if ((rc = ensure(h, h->d_X, sizeof(float) * 3 * (size_t)(n_match + 1)))) return rc;
+  if ((rc = ensure(h, h->d_ouv, sizeof(float) * 2 * (size_t)(n_match + 1)))) return rc;
+  if ((rc = ensure(h, h->d_foff, sizeof(int32_t) * (size_t)(n_frames + 1)))) return rc;
+  if ((rc = ensure(h, h->d_flags, (size_t)(n_match + 1)))) return rc;
+  if ((rc = ensure(h, h->d_hist, sizeof(double) * (size_t)n_frames * (mi + 1)))) return rc;
+  if ((rc = ensure(h, h->d_acc, (size_t)n_frames * (mi + 1)))) return rc;
+  CK(cudaMemcpyAsync(h->d_R.p, R, sizeof(double) * 9 * (size_t)n_frames, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->d_t.p, t, sizeof(double) * 3 * (size_t)n_frames, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->d_foff.p, frame_offsets, sizeof(int32_t) * (size_t)(n_frames + 1), cudaMemcpyHostToDevice, s));
+  if (n_match > 0) {
+    CK(cudaMemcpyAsync(h->d_X.p, X, sizeof(float) * 3 * (size_t)n_match, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_ouv.p, uv, sizeof(float) * 2 * (size_t)n_match, cudaMemcpyHostToDevice, s));
+  }
+  CK(cudaEventRecord(h->ev0, s));
+  rc = ba_solve_pose_only(h, n_frames, n_match, intr, (double*)h->d_R.p, (double*)h->d_t.p,
+                          (const float*)h->d_X.p, (const float*)h->d_ouv.p,
+                          (const int32_t*)h->d_foff.p, flags ? (uint8_t*)h->d_flags.p : nullptr,
+                          cost_hist ? (double*)h->d_hist.p : nullptr,
+                          accepted ? (uint8_t*)h->d_acc.p : nullptr, s);
+  if (rc) return rc;
+  CK(cudaEventRecord(h->ev1, s));
+  CK(cudaMemcpyAsync(R, h->d_R.p, sizeof(double) * 9 * (size_t)n_frames, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(t, h->d_t.p, sizeof(double) * 3 * (size_t)n_frames, cudaMemcpyDeviceToHost, s));
+  if (flags && n_match > 0) CK(cudaMemcpyAsync(flags, h->d_flags.p, (size_t)n_match, cudaMemcpyDeviceToHost, s));
+  if (cost_hist) CK(cudaMemcpyAsync(cost_hist, h->d_hist.p, sizeof(double) * (size_t)n_frames * (mi + 1), cudaMemcpyDeviceToHost, s));
+  if (accepted && mi > 0) CK(cudaMemcpyAsync(accepted, h->d_acc.p, (size_t)n_frames * mi, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (gpu_ms) cudaEventElapsedTime(gpu_ms, h->ev0, h->ev1);
+  return BA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU plumbing
+// ------------------------------------------------------------------------------------------
+extern "C" int ba_nccl_unique_id(void* out_id) {
+  if (!out_id) return BA_ERR_INVALID;
+  if (!load_nccl()) return BA_ERR_NCCL;
+  nccl_uid id;
+  if (g_nccl.get_uid(&id) != 0) return BA_ERR_NCCL;
+  memcpy(out_id, &id, sizeof(id));
+  return BA_OK;
+}
+
+extern "C" int ba_dist_init(ba_handle* h, const void* id, int32_t rank, int32_t world) {
+  if (!h || !id || world < 1 || rank < 0 || rank >= world) return BA_ERR_INVALID;
+  if (world == 1) { h->rank = 0; h->world = 1; return BA_OK; }
+  if (!load_nccl()) { h->err = "libnccl.so.2 not found"; return BA_ERR_NCCL; }
+  CK(cudaSetDevice(h->device));
+  nccl_uid uid;
+  memcpy(&uid, id, sizeof(uid));
+  int r = g_nccl.init_rank(&h->comm, world, uid, rank);
+  if (r != 0) { h->err = std::string("ncclCommInitRank: ") + (g_nccl.errstr ? g_nccl.errstr(r) : "?"); return BA_ERR_NCCL; }
+  h->rank = rank;
+  h->world = world;
+  if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+  return BA_OK;
+}
+
+extern "C" int ba_dist_shutdown(ba_handle* h) {
+  if (!h) return BA_ERR_INVALID;
+  if (h->comm && g_nccl.destroy) { g_nccl.destroy(h->comm); h->comm = nullptr; }
+  h->world = 1; h->rank = 0;
+  if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+  return BA_OK;
+}

@@ -1,0 +1,65 @@
+// Kernel-facing view of one local-BA solve and the launch wrappers (defined in ba_local.cu,
+// ba_pose.cu) used by the C ABI in ba_api.cu.
+#pragma once
+#include "ba_device.cuh"
+
+namespace ba {
+
+// Plain-old-data view handed to every kernel by value.
+struct Work {
+  int n_cam, n_pt, n_obs, n;          // n = 6 * n_cam (dense reduced camera system order)
+  Intr K;
+  const int* obs_cam;                 // [n_obs]
+  const int* obs_pt;                  // [n_obs] non-decreasing
+  const float* obs_uv;                // [2 n_obs]
+  const int* pt_off;                  // [n_pt + 1]
+  const unsigned char* fixed;         // [n_cam]
+  double* pose[2];                    // [12 n_cam] each: R row-major (9) then t (3); double-buffered
+  float* X[2];                        // [3 n_pt] each; double-buffered
+  double* S;                          // [n*n] row-major, lower triangle valid (reduction buffer)
+  double* b;                          // [n]
+  double* diagU;                      // [n]   diag of the un-damped pose blocks
+  double* cost_lin;                   // [1]   cost at the linearisation point (same buffer as S)
+  double* cost_cand;                  // [1]
+  double* dp;                         // [n]   camera step
+  LmCtl* ctl;
+  int world;                          // > 1: accept/reject runs as its own kernel after the all-reduce
+};
+
+// launch wrappers; every one returns the number of kernels it launched
+struct LmInit {
+  double lambda0, huber_delta, chi2_thr, lambda_up, lambda_down, lambda_min, lambda_max;
+};
+int launch_init(const Work& w, const double* R_in, const double* t_in, const float* X_in,
+                const LmInit& p, cudaStream_t s);
+int launch_linearize_scatter(const Work& w, int sm_count, cudaStream_t s);
+int launch_linearize_tiled(const Work& w, int sm_count, cudaStream_t s);
+int launch_rcs_cholesky(const Work& w, cudaStream_t s);
+int launch_backsub(const Work& w, int sm_count, cudaStream_t s);
+int launch_accept(const Work& w, cudaStream_t s);
+int launch_finalize(const Work& w, double* R_out, double* t_out, float* X_out,
+                    unsigned char* flags, cudaStream_t s);
+int launch_eval_cost(const Work& w, const double* pose, const float* X, double* out,
+                     double delta, cudaStream_t s);
+int configure_kernels();   // per-device function attributes; call once after cudaSetDevice
+size_t rcs_cholesky_smem_bytes(int n);
+int rcs_cholesky_max_n();
+bool tiled_supported(int n_cam);
+
+struct PoseWork {
+  int n_frames;
+  Intr K;
+  double* R;                 // [9 n_frames] in/out
+  double* t;                 // [3 n_frames] in/out
+  const float* X;            // [3 n_match]
+  const float* uv;           // [2 n_match]
+  const int* frame_off;      // [n_frames+1]
+  unsigned char* flags;      // [n_match] or null
+  double* cost_hist;         // [n_frames*(max_iter+1)] or null
+  unsigned char* accepted;   // [n_frames*max_iter] or null
+  int max_iter;
+  double huber_delta, chi2_thr, lambda0, lambda_up, lambda_down, lambda_min, lambda_max;
+};
+int launch_pose_only(const PoseWork& w, cudaStream_t s);
+
+}  // namespace ba

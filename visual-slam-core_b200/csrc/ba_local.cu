@@ -1,0 +1,579 @@
+// Local bundle adjustment: the Levenberg-Marquardt hot path on sm_100a.
+//
+// Replaces the Adam/autograd loop of the reference
+// (visual_slam/optimization/torch_optimizer.py:148-180) with, per LM iteration,
+//   k_linearize_*   residuals + Jacobians + Huber weights + U/V/W/g blocks + Schur complement
+//   k_rcs_cholesky  damped reduced camera system, in-shared-memory Cholesky, camera retraction
+//   k_backsub       point back-substitution, candidate state, candidate cost, accept/reject
+// All LM control state lives in device memory (LmCtl), so the loop never syncs with the host.
+#include "ba_kernels.cuh"
+
+namespace ba {
+
+static constexpr int kWarps = 8;             // warps per CTA in the per-point kernels
+static constexpr int kThreads = kWarps * 32;
+
+// ------------------------------------------------------------------------------------------
+// state initialisation
+// ------------------------------------------------------------------------------------------
+__global__ void k_init(Work w, const double* __restrict__ R_in, const double* __restrict__ t_in,
+                       const float* __restrict__ X_in, LmInit p) {
+  int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  int nth = gridDim.x * blockDim.x;
+  for (int i = tid; i < w.n_cam * 12; i += nth) {
+    int c = i / 12, k = i % 12;
+    double v = k < 9 ? R_in[9 * c + k] : t_in[3 * c + (k - 9)];
+    w.pose[0][i] = v;
+    w.pose[1][i] = v;
+  }
+  for (int i = tid; i < 3 * w.n_pt; i += nth) w.X[0][i] = X_in[i];
+  long long nred = (long long)w.n * w.n + 2 * w.n + 1;   // S | b | diagU | cost_lin contiguous
+  for (long long i = tid; i < nred; i += nth) w.S[i] = 0.0;
+  for (int i = tid; i < w.n; i += nth) w.dp[i] = 0.0;
+  if (tid == 0) {
+    LmCtl* c = w.ctl;
+    c->lambda = p.lambda0;
+    c->huber_delta = p.huber_delta;
+    c->chi2_thr = p.chi2_thr;
+    c->lambda_up = p.lambda_up;
+    c->lambda_down = p.lambda_down;
+    c->lambda_min = p.lambda_min;
+    c->lambda_max = p.lambda_max;
+    c->cost_cur = 0.0;
+    c->cost_cand = 0.0;
+    c->cost_lin = 0.0;
+    c->cur = 0;
+    c->iter = 0;
+    c->solve_fail = 0;
+    c->n_accepted = 0;
+    c->ticket = 0u;
+    c->pcg_iters_last = 0;
+    *w.cost_cand = 0.0;
+  }
+}
+
+int launch_init(const Work& w, const double* R_in, const double* t_in, const float* X_in,
+                const LmInit& p, cudaStream_t s) {
+  long long work = (long long)w.n * w.n + 3LL * w.n_pt;
+  int blocks = (int)((work + 255) / 256);
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_init<<<blocks, 256, 0, s>>>(w, R_in, t_in, X_in, p);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// linearise + Schur, general scatter variant (warp per point, global float64 RED atomics)
+//
+// Works for any window size and any per-point observation count; used directly for
+// windows the tiled kernel does not cover and as an independent cross-check of it.
+// ------------------------------------------------------------------------------------------
+struct ObsIn {
+  int cam;
+  double u, v;
+};
+
+__device__ __forceinline__ ObsIn load_obs(const Work& w, int o) {
+  ObsIn r;
+  r.cam = __ldg(w.obs_cam + o);
+  float2 uv = __ldg(reinterpret_cast<const float2*>(w.obs_uv) + o);
+  r.u = (double)uv.x;
+  r.v = (double)uv.y;
+  return r;
+}
+
+__device__ __forceinline__ void make_W(const ObsLin& o, double W[18]) {
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    double a = o.wu * o.pu[r], b = o.wv * o.pv[r];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) W[3 * r + q] = a * o.lu[q] + b * o.lv[q];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_linearize_scatter(Work w) {
+  __shared__ double sW[kWarps][32][19];   // per-warp staging of W_ij (6x3), padded
+  __shared__ int sCam[kWarps][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const LmCtl* ctl = w.ctl;
+  const int cur = ctl->cur;
+  const double lambda = ctl->lambda, delta = ctl->huber_delta;
+  const double* __restrict__ pose = w.pose[cur];
+  const float* __restrict__ X = w.X[cur];
+  const int n = w.n;
+  double cost = 0.0;
+
+  const int warp_global = blockIdx.x * kWarps + wid;
+  const int warp_total = gridDim.x * kWarps;
+  for (int j = warp_global; j < w.n_pt; j += warp_total) {
+    const int o0 = __ldg(w.pt_off + j);
+    const int k = __ldg(w.pt_off + j + 1) - o0;
+    if (k <= 0) continue;
+    const double X0 = X[3 * j], X1 = X[3 * j + 1], X2 = X[3 * j + 2];
+
+    // ---- pass 1: V_j, g_l,j, cost -------------------------------------------------------
+    double V[6] = {0, 0, 0, 0, 0, 0}, gl[3] = {0, 0, 0};
+    for (int base = 0; base < k; base += 32) {
+      int i = base + lane;
+      if (i < k) {
+        ObsIn in = load_obs(w, o0 + i);
+        ObsLin ol;
+        linearize_obs<false>(w.K, pose + 12 * in.cam, pose + 12 * in.cam + 9, X0, X1, X2, in.u,
+                             in.v, delta, ol);
+        V[0] += ol.wu * ol.lu[0] * ol.lu[0] + ol.wv * ol.lv[0] * ol.lv[0];
+        V[1] += ol.wu * ol.lu[0] * ol.lu[1] + ol.wv * ol.lv[0] * ol.lv[1];
+        V[2] += ol.wu * ol.lu[0] * ol.lu[2] + ol.wv * ol.lv[0] * ol.lv[2];
+        V[3] += ol.wu * ol.lu[1] * ol.lu[1] + ol.wv * ol.lv[1] * ol.lv[1];
+        V[4] += ol.wu * ol.lu[1] * ol.lu[2] + ol.wv * ol.lv[1] * ol.lv[2];
+        V[5] += ol.wu * ol.lu[2] * ol.lu[2] + ol.wv * ol.lv[2] * ol.lv[2];
+        double au = ol.wu * ol.ru, av = ol.wv * ol.rv;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) gl[q] += au * ol.lu[q] + av * ol.lv[q];
+        cost += huber_rho(ol.ru, delta) + huber_rho(ol.rv, delta);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) V[q] = warp_sum(V[q]);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) gl[q] = warp_sum(gl[q]);
+    V[0] += damp(V[0], lambda);
+    V[3] += damp(V[3], lambda);
+    V[5] += damp(V[5], lambda);
+    double Vi[6];
+    sym3_inverse(V, Vi);
+
+    // ---- pass 2: pose blocks, Schur complement ------------------------------------------
+    for (int baseA = 0; baseA < k; baseA += 32) {
+      const int iA = baseA + lane;
+      const bool validA = iA < k;
+      int camA = -1;
+      double WA[18], T[18];
+      bool activeA = false;
+      if (validA) {
+        ObsIn in = load_obs(w, o0 + iA);
+        camA = in.cam;
+        activeA = (w.fixed[camA] == 0);
+        ObsLin ol;
+        linearize_obs<true>(w.K, pose + 12 * camA, pose + 12 * camA + 9, X0, X1, X2, in.u, in.v,
+                            delta, ol);
+        make_W(ol, WA);
+        // T = W V^-1  (6x3)
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          double w0 = WA[3 * r], w1 = WA[3 * r + 1], w2 = WA[3 * r + 2];
+          T[3 * r + 0] = w0 * Vi[0] + w1 * Vi[1] + w2 * Vi[2];
+          T[3 * r + 1] = w0 * Vi[1] + w1 * Vi[3] + w2 * Vi[4];
+          T[3 * r + 2] = w0 * Vi[2] + w1 * Vi[4] + w2 * Vi[5];
+        }
+        if (activeA) {
+          double* Sd = w.S + (size_t)(6 * camA) * n + 6 * camA;
+          double au = ol.wu * ol.ru, av = ol.wv * ol.rv;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+            double pur = ol.wu * ol.pu[r], pvr = ol.wv * ol.pv[r];
+#pragma unroll
+            for (int c = 0; c <= r; ++c) {
+              double u_rc = pur * ol.pu[c] + pvr * ol.pv[c];
+              double s_rc = T[3 * r] * WA[3 * c] + T[3 * r + 1] * WA[3 * c + 1] +
+                            T[3 * r + 2] * WA[3 * c + 2];
+              atomicAdd(Sd + (size_t)r * n + c, u_rc - s_rc);
+            }
+            atomicAdd(w.diagU + 6 * camA + r, pur * ol.pu[r] + pvr * ol.pv[r]);
+            double br = -(au * ol.pu[r] + av * ol.pv[r]) + T[3 * r] * gl[0] +
+                        T[3 * r + 1] * gl[1] + T[3 * r + 2] * gl[2];
+            atomicAdd(w.b + 6 * camA + r, br);
+          }
+        }
+      }
+      for (int baseB = 0; baseB < k; baseB += 32) {
+        const int iB = baseB + lane;
+        // stage W of chunk B
+        if (baseB == baseA) {
+          sCam[wid][lane] = activeA ? camA : -1;
+          if (activeA) {
+#pragma unroll
+            for (int q = 0; q < 18; ++q) sW[wid][lane][q] = WA[q];
+          }
+        } else {
+          int camB = -1;
+          if (iB < k) {
+            ObsIn in = load_obs(w, o0 + iB);
+            if (w.fixed[in.cam] == 0) {
+              camB = in.cam;
+              ObsLin ol;
+              linearize_obs<true>(w.K, pose + 12 * camB, pose + 12 * camB + 9, X0, X1, X2, in.u,
+                                  in.v, delta, ol);
+              double WB[18];
+              make_W(ol, WB);
+#pragma unroll
+              for (int q = 0; q < 18; ++q) sW[wid][lane][q] = WB[q];
+            }
+          }
+          sCam[wid][lane] = camB;
+        }
+        __syncwarp();
+        const int mB = min(32, k - baseB);
+        if (activeA) {
+          for (int m = 0; m < mB; ++m) {
+            const int camB = sCam[wid][m];
+            if (camB < 0 || camB > camA || baseB + m == iA) continue;
+            const double* Wb = sW[wid][m];
+            double* Sd = w.S + (size_t)(6 * camA) * n + 6 * camB;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+              double b0 = Wb[3 * c], b1 = Wb[3 * c + 1], b2 = Wb[3 * c + 2];
+#pragma unroll
+              for (int r = 0; r < 6; ++r) {
+                double s_rc = T[3 * r] * b0 + T[3 * r + 1] * b1 + T[3 * r + 2] * b2;
+                atomicAdd(Sd + (size_t)r * n + c, -s_rc);
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  cost = warp_sum(cost);
+  if (lane == 0 && cost != 0.0) atomicAdd(w.cost_lin, cost);
+}
+
+int launch_linearize_scatter(const Work& w, int sm_count, cudaStream_t s) {
+  int blocks = (w.n_pt + kWarps - 1) / kWarps;
+  if (blocks > sm_count) blocks = sm_count;
+  if (blocks < 1) blocks = 1;
+  k_linearize_scatter<<<blocks, kThreads, 0, s>>>(w);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// reduced camera system: damping, Cholesky in shared memory, camera retraction
+// ------------------------------------------------------------------------------------------
+static constexpr int kSolveThreads = 512;
+
+__device__ __forceinline__ int tri(int r, int c) { return ((r * (r + 1)) >> 1) + c; }
+
+size_t rcs_cholesky_smem_bytes(int n) {
+  return sizeof(double) * ((size_t)(n + 1) * (n + 2) / 2 + n + 8);
+}
+int rcs_cholesky_max_n() {
+  int n = 6;
+  while (rcs_cholesky_smem_bytes(n + 6) <= 227 * 1024) n += 6;
+  return n;
+}
+
+__global__ void __launch_bounds__(kSolveThreads, 1)
+k_rcs_cholesky(Work w) {
+  extern __shared__ double sm[];
+  const int n = w.n;
+  double* A = sm;                                   // packed lower, rows 0..n (row n = rhs)
+  double* x = sm + (size_t)(n + 1) * (n + 2) / 2;   // solution
+  __shared__ int s_fail;
+  LmCtl* ctl = w.ctl;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  const double lambda = ctl->lambda;
+  const int cur = ctl->cur;
+
+  if (tid == 0) {
+    s_fail = 0;
+    if (ctl->iter == 0) {
+      double c0 = *w.cost_lin;
+      ctl->cost_cur = c0;
+      ctl->cost_hist[0] = c0;
+    }
+  }
+  // load lower triangle (row per warp: contiguous in global and in packed storage), zero global
+  for (int r = wid; r < n; r += nw) {
+    double* Srow = w.S + (size_t)r * n;
+    const bool fx = w.fixed[r / 6] != 0;
+    for (int c = lane; c <= r; c += 32) {
+      double v = Srow[c];
+      Srow[c] = 0.0;
+      if (c == r) v = fx ? 1.0 : v + damp(w.diagU[r], lambda);
+      else if (fx || w.fixed[c / 6] != 0) v = 0.0;
+      A[tri(r, c)] = v;
+    }
+  }
+  for (int c = tid; c < n; c += nt) {
+    double v = w.b[c];
+    w.b[c] = 0.0;
+    A[tri(n, c)] = (w.fixed[c / 6] != 0) ? 0.0 : v;
+  }
+  __syncthreads();
+  for (int c = tid; c < n; c += nt) w.diagU[c] = 0.0;
+  if (tid == 0) *w.cost_lin = 0.0;
+
+  // right-looking Cholesky on rows 0..n (the rhs row rides along: row n becomes y = L^-1 b)
+  for (int k = 0; k < n; ++k) {
+    const double akk = A[tri(k, k)];
+    if (!(akk > 0.0) || !isfinite(akk)) {
+      if (tid == 0) s_fail = 1;
+      break;                                   // uniform: every thread read the same value
+    }
+    const double inv = 1.0 / sqrt(akk);
+    __syncthreads();
+    for (int i = k + 1 + tid; i <= n; i += nt) A[tri(i, k)] *= inv;
+    if (tid == 0) A[tri(k, k)] = akk * inv;
+    __syncthreads();
+    for (int i = k + 1 + wid; i <= n; i += nw) {
+      const double lik = A[tri(i, k)];
+      const int jmax = (i < n) ? i : n - 1;
+      double* Ai = A + tri(i, 0);
+      for (int j = k + 1 + lane; j <= jmax; j += 32) Ai[j] -= lik * A[tri(j, k)];
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  const bool fail = s_fail != 0;
+  if (!fail) {
+    // back substitution L^T x = y, row-oriented: one barrier per unknown
+    double* y = A + tri(n, 0);
+    for (int k = n - 1; k >= 0; --k) {
+      const double xk = y[k] / A[tri(k, k)];
+      if (tid == 0) x[k] = xk;
+      const double* Lk = A + tri(k, 0);
+      for (int j = tid; j < k; j += nt) y[j] -= Lk[j] * xk;
+      __syncthreads();
+    }
+  } else {
+    for (int c = tid; c < n; c += nt) x[c] = 0.0;
+    __syncthreads();
+  }
+  bool bad = false;
+  for (int c = tid; c < n; c += nt) {
+    double v = x[c];
+    if (!isfinite(v)) { bad = true; v = 0.0; }
+    w.dp[c] = v;
+  }
+  if (bad) s_fail = 1;
+  __syncthreads();
+  if (tid == 0) ctl->solve_fail = s_fail;
+  // candidate camera poses: R <- exp(dw) R, t <- t + dt   (torch_optimizer.py:159, t additive)
+  const double* P = w.pose[cur];
+  double* Pn = w.pose[cur ^ 1];
+  for (int c = tid; c < w.n_cam; c += nt) {
+    double R[9], Rn[9], dw[3], dt[3];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) R[q] = P[12 * c + q];
+    bool upd = (w.fixed[c] == 0) && (s_fail == 0);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      double a = x[6 * c + q], b2 = x[6 * c + 3 + q];
+      dw[q] = (upd && isfinite(a)) ? a : 0.0;
+      dt[q] = (upd && isfinite(b2)) ? b2 : 0.0;
+    }
+    if (upd) so3_exp_mul(dw, R, Rn);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) Pn[12 * c + q] = upd ? Rn[q] : R[q];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) Pn[12 * c + 9 + q] = P[12 * c + 9 + q] + dt[q];
+  }
+}
+
+int configure_kernels() {
+  cudaError_t e = cudaFuncSetAttribute(k_rcs_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(227 * 1024));
+  return e == cudaSuccess ? 0 : -1;
+}
+
+int launch_rcs_cholesky(const Work& w, cudaStream_t s) {
+  size_t smem = rcs_cholesky_smem_bytes(w.n);
+  k_rcs_cholesky<<<1, kSolveThreads, smem, s>>>(w);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// back-substitution, candidate points, candidate cost, accept / reject
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_backsub(Work w) {
+  __shared__ double s_cost[kWarps];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  LmCtl* ctl = w.ctl;
+  const int cur = ctl->cur;
+  const double lambda = ctl->lambda, delta = ctl->huber_delta;
+  const double* __restrict__ pose = w.pose[cur];
+  const double* __restrict__ posen = w.pose[cur ^ 1];
+  const float* __restrict__ X = w.X[cur];
+  float* __restrict__ Xn = w.X[cur ^ 1];
+  const double* __restrict__ dp = w.dp;
+  double cost = 0.0;
+
+  const int warp_global = blockIdx.x * kWarps + wid;
+  const int warp_total = gridDim.x * kWarps;
+  for (int j = warp_global; j < w.n_pt; j += warp_total) {
+    const int o0 = __ldg(w.pt_off + j);
+    const int k = __ldg(w.pt_off + j + 1) - o0;
+    const float xf0 = X[3 * j], xf1 = X[3 * j + 1], xf2 = X[3 * j + 2];
+    if (k <= 0) {
+      if (lane == 0) { Xn[3 * j] = xf0; Xn[3 * j + 1] = xf1; Xn[3 * j + 2] = xf2; }
+      continue;
+    }
+    const double X0 = xf0, X1 = xf1, X2 = xf2;
+    double V[6] = {0, 0, 0, 0, 0, 0}, q[3] = {0, 0, 0};
+    for (int base = 0; base < k; base += 32) {
+      int i = base + lane;
+      if (i < k) {
+        ObsIn in = load_obs(w, o0 + i);
+        ObsLin ol;
+        linearize_obs<true>(w.K, pose + 12 * in.cam, pose + 12 * in.cam + 9, X0, X1, X2, in.u,
+                            in.v, delta, ol);
+        double eu = ol.ru, ev = ol.rv;
+        if (w.fixed[in.cam] == 0) {
+          const double* d = dp + 6 * in.cam;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) { eu += ol.pu[r] * d[r]; ev += ol.pv[r] * d[r]; }
+        }
+        V[0] += ol.wu * ol.lu[0] * ol.lu[0] + ol.wv * ol.lv[0] * ol.lv[0];
+        V[1] += ol.wu * ol.lu[0] * ol.lu[1] + ol.wv * ol.lv[0] * ol.lv[1];
+        V[2] += ol.wu * ol.lu[0] * ol.lu[2] + ol.wv * ol.lv[0] * ol.lv[2];
+        V[3] += ol.wu * ol.lu[1] * ol.lu[1] + ol.wv * ol.lv[1] * ol.lv[1];
+        V[4] += ol.wu * ol.lu[1] * ol.lu[2] + ol.wv * ol.lv[1] * ol.lv[2];
+        V[5] += ol.wu * ol.lu[2] * ol.lu[2] + ol.wv * ol.lv[2] * ol.lv[2];
+        double au = ol.wu * eu, av = ol.wv * ev;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) q[r] += au * ol.lu[r] + av * ol.lv[r];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) V[r] = warp_sum(V[r]);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) q[r] = warp_sum(q[r]);
+    V[0] += damp(V[0], lambda);
+    V[3] += damp(V[3], lambda);
+    V[5] += damp(V[5], lambda);
+    double Vi[6];
+    sym3_inverse(V, Vi);
+    const double d0 = -(Vi[0] * q[0] + Vi[1] * q[1] + Vi[2] * q[2]);
+    const double d1 = -(Vi[1] * q[0] + Vi[3] * q[1] + Vi[4] * q[2]);
+    const double d2 = -(Vi[2] * q[0] + Vi[4] * q[1] + Vi[5] * q[2]);
+    const float n0 = (float)(X0 + d0), n1 = (float)(X1 + d1), n2 = (float)(X2 + d2);
+    if (lane == 0) { Xn[3 * j] = n0; Xn[3 * j + 1] = n1; Xn[3 * j + 2] = n2; }
+    const double N0 = n0, N1 = n1, N2 = n2;
+    for (int base = 0; base < k; base += 32) {
+      int i = base + lane;
+      if (i < k) {
+        ObsIn in = load_obs(w, o0 + i);
+        double ru, rv;
+        residual_only(w.K, posen + 12 * in.cam, posen + 12 * in.cam + 9, N0, N1, N2, in.u, in.v,
+                      ru, rv);
+        cost += huber_rho(ru, delta) + huber_rho(rv, delta);
+      }
+    }
+  }
+  cost = warp_sum(cost);
+  if (lane == 0) s_cost[wid] = cost;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double c = 0.0;
+#pragma unroll
+    for (int i = 0; i < kWarps; ++i) c += s_cost[i];
+    atomicAdd(w.cost_cand, c);
+    __threadfence();
+    unsigned t = atomicAdd(&ctl->ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0 && w.world == 1) {
+    __threadfence();
+    ctl->cost_cand = *((volatile double*)w.cost_cand);
+    *w.cost_cand = 0.0;
+    lm_accept(ctl);
+  }
+}
+
+int launch_backsub(const Work& w, int sm_count, cudaStream_t s) {
+  int blocks = (w.n_pt + kWarps - 1) / kWarps;
+  int cap = sm_count * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_backsub<<<blocks, kThreads, 0, s>>>(w);
+  return 1;
+}
+
+// accept / reject as its own kernel (multi-GPU: runs after the candidate-cost all-reduce)
+__global__ void k_accept(Work w) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    w.ctl->cost_cand = *w.cost_cand;
+    *w.cost_cand = 0.0;
+    lm_accept(w.ctl);
+  }
+}
+int launch_accept(const Work& w, cudaStream_t s) {
+  k_accept<<<1, 32, 0, s>>>(w);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// outlier flags at the final accepted iterate + copy-out
+// ------------------------------------------------------------------------------------------
+__global__ void k_finalize(Work w, double* __restrict__ R_out, double* __restrict__ t_out,
+                           float* __restrict__ X_out, unsigned char* __restrict__ flags) {
+  const int cur = w.ctl->cur;
+  const double chi2 = w.ctl->chi2_thr;
+  const double* __restrict__ pose = w.pose[cur];
+  const float* __restrict__ X = w.X[cur];
+  int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  int nth = gridDim.x * blockDim.x;
+  if (flags) {
+    for (int o = tid; o < w.n_obs; o += nth) {
+      ObsIn in = load_obs(w, o);
+      int j = __ldg(w.obs_pt + o);
+      double ru, rv;
+      residual_only(w.K, pose + 12 * in.cam, pose + 12 * in.cam + 9, (double)X[3 * j],
+                    (double)X[3 * j + 1], (double)X[3 * j + 2], in.u, in.v, ru, rv);
+      flags[o] = (ru * ru + rv * rv) > chi2 ? 1 : 0;
+    }
+  }
+  for (int i = tid; i < 3 * w.n_pt; i += nth) X_out[i] = X[i];
+  for (int i = tid; i < 12 * w.n_cam; i += nth) {
+    int c = i / 12, k = i % 12;
+    if (k < 9) R_out[9 * c + k] = pose[i];
+    else t_out[3 * c + (k - 9)] = pose[i];
+  }
+}
+
+int launch_finalize(const Work& w, double* R_out, double* t_out, float* X_out,
+                    unsigned char* flags, cudaStream_t s) {
+  int work = w.n_obs > 3 * w.n_pt ? w.n_obs : 3 * w.n_pt;
+  int blocks = (work + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_finalize<<<blocks, 256, 0, s>>>(w, R_out, t_out, X_out, flags);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// objective only
+// ------------------------------------------------------------------------------------------
+__global__ void k_eval_cost(Work w, const double* __restrict__ pose, const float* __restrict__ X,
+                            double* out, double delta) {
+  double cost = 0.0;
+  int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  int nth = gridDim.x * blockDim.x;
+  for (int o = tid; o < w.n_obs; o += nth) {
+    ObsIn in = load_obs(w, o);
+    int j = __ldg(w.obs_pt + o);
+    double ru, rv;
+    residual_only(w.K, pose + 12 * in.cam, pose + 12 * in.cam + 9, (double)X[3 * j],
+                  (double)X[3 * j + 1], (double)X[3 * j + 2], in.u, in.v, ru, rv);
+    cost += huber_rho(ru, delta) + huber_rho(rv, delta);
+  }
+  cost = warp_sum(cost);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, cost);
+}
+
+int launch_eval_cost(const Work& w, const double* pose, const float* X, double* out,
+                     double delta, cudaStream_t s) {
+  int blocks = (w.n_obs + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  cudaMemsetAsync(out, 0, sizeof(double), s);
+  k_eval_cost<<<blocks, 256, 0, s>>>(w, pose, X, out, delta);
+  return 1;
+}
+
+}  // namespace ba

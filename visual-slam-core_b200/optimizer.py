@@ -1,0 +1,156 @@
+"""`B200Optimizer`: the drop-in for the reference's optimizer plugin.
+
+Mirrors `BaseOptimizer` (`visual_slam/optimization/base_optimizer.py:11-50`) with the signatures
+its callers actually use (`map/map.py:148,171,178`): `optimize_local(keyframes, map_points) -> bool`,
+`optimize_global(...)`, `optimize_initial(...)`; constructor `(config, logger, log_dir, device)` as
+`TorchOptimizer` (`torch_optimizer.py:18-26`).  Results are delivered by mutating the passed
+objects; nothing is raised to the caller: any failure is logged and reported as `False`.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import threading
+from abc import ABC, abstractmethod
+from typing import Any, List, Optional
+
+import numpy as np
+
+from . import packing
+from .solver import LMConfig, LocalBASolver, SolveResult
+
+
+class BaseOptimizer(ABC):
+    """Interface mirror of the reference ABC (base_optimizer.py:11-50)."""
+
+    def __init__(self, config: Optional[Any] = None, logger: Optional[Any] = None,
+                 log_dir: Optional[str] = "logs") -> None:
+        self.config = config
+        self.logger = logger or _make_logger(self.__class__.__name__, log_dir)
+        self.logger.info("*" * 80)
+
+    @abstractmethod
+    def optimize_local(self, keyframes: List[Any], map_points: List[Any]) -> bool: ...
+
+    @abstractmethod
+    def optimize_global(self, keyframes: List[Any], map_points: List[Any]) -> bool: ...
+
+    @abstractmethod
+    def optimize_initial(self, keyframes: List[Any], map_points: List[Any]) -> bool: ...
+
+
+def _make_logger(name: str, log_dir: Optional[str]) -> logging.Logger:
+    logger = logging.getLogger(f"b200ba.{name}")
+    logger.setLevel(logging.INFO)
+    if log_dir and not any(isinstance(h, logging.FileHandler) for h in logger.handlers):
+        try:
+            from logging.handlers import RotatingFileHandler
+            os.makedirs(log_dir, exist_ok=True)
+            fh = RotatingFileHandler(os.path.join(log_dir, f"{name.lower()}.log"),
+                                     maxBytes=5 * 1024 * 1024, backupCount=3)
+            fh.setFormatter(logging.Formatter("%(asctime)s - %(name)s - %(levelname)s - %(message)s"))
+            logger.addHandler(fh)
+        except OSError:
+            pass
+    return logger
+
+
+def lm_config_from(config: Optional[Any]) -> LMConfig:
+    """Read LM fields the way the reference reads its own (`getattr(config.optimization, ...)`,
+    torch_optimizer.py:106-108), so a stock `Config` works and extra fields are optional."""
+    opt = getattr(config, "optimization", None) if config is not None else None
+    g = (lambda k, d: getattr(opt, k, d)) if opt is not None else (lambda k, d: d)
+    return LMConfig(
+        huber_delta=float(g("huber_delta", 5.0)),
+        chi2_thr=float(g("chi2_threshold", 5.991)),
+        lambda0=float(g("lm_lambda0", 1e-4)),
+        lambda_up=float(g("lm_lambda_up", 10.0)),
+        lambda_down=float(g("lm_lambda_down", 0.1)),
+        lambda_min=float(g("lm_lambda_min", 1e-9)),
+        lambda_max=float(g("lm_lambda_max", 1e8)),
+        max_iter=int(g("lm_max_iter", 10)),
+        solver=str(g("solver", "auto")),
+        schur=str(g("schur", "auto")),
+    )
+
+
+class B200Optimizer(BaseOptimizer):
+    """Levenberg-Marquardt local BA on a B200 behind the reference's optimizer API."""
+
+    def __init__(self, config: Optional[Any] = None, logger: Optional[Any] = None,
+                 log_dir: Optional[str] = "logs", device: str = "cuda") -> None:
+        super().__init__(config, logger, log_dir=log_dir)
+        self.device = device
+        dev_index = 0
+        if isinstance(device, str) and ":" in device:
+            dev_index = int(device.split(":")[1])
+        self._lm = lm_config_from(config)
+        self._solver: Optional[LocalBASolver] = None
+        self._dev_index = dev_index
+        self._lock = threading.Lock()          # one shared instance, two caller threads (tracking.py:61)
+        self.last_result: Optional[SolveResult] = None
+        self.last_packed: Optional[packing.PackedWindow] = None
+        self.mark_bad_points = bool(getattr(getattr(config, "optimization", None), "mark_bad_points", False))
+
+    def _get_solver(self) -> LocalBASolver:
+        if self._solver is None:
+            self._solver = LocalBASolver(self._lm, device=self._dev_index)   # raises without a GPU
+        return self._solver
+
+    # ------------------------------------------------------------------------------ local BA
+    def optimize_local(self, keyframes: List[Any], map_points: List[Any]) -> bool:
+        try:
+            self.logger.info(f"[B200Optimizer] keyframes - {len(keyframes)}, points - {len(map_points)}.")
+            if not keyframes:
+                return False
+            pw = packing.pack_window(keyframes, map_points)      # snapshot up front, as :46-95
+            self.logger.info(f"[B200Optimizer] observations - {pw.n_obs}.")
+            if pw.n_obs < packing.MIN_OBSERVATIONS:              # :99-101: False, nothing mutated
+                self.logger.warning("[B200Optimizer] too few observations for local optimisation.")
+                return False
+            with self._lock:
+                res = self._get_solver().solve_local(pw.intr, pw.R, pw.t, pw.fixed, pw.X, pw.obs_cam,
+                                                     pw.obs_pt, pw.obs_uv, pw.pt_offsets)
+            for i in range(res.n_iter):
+                self.logger.info(
+                    f"[Local BA] iter={i}, loss={res.cost_hist[i + 1]:.3f}, lambda={res.lambda_hist[i]:.1e}, "
+                    f"accepted={int(res.accepted[i])}")
+            if not (np.isfinite(res.R).all() and np.isfinite(res.t).all() and np.isfinite(res.X).all()):
+                self.logger.error("[B200Optimizer] non-finite result; nothing written back.")
+                return False
+            packing.write_back(keyframes, map_points, res.R, res.t, res.X)
+            self.last_result, self.last_packed = res, pw
+            if self.mark_bad_points:
+                self._mark_bad(map_points, pw, res.flags)
+            self.logger.info("[Local BA] finished.")
+            return True
+        except Exception as e:  # the caller thread must survive (handlers/local_handler.py:28-48)
+            self.logger.error(f"[B200Optimizer] optimize_local failed: {e!r}")
+            return False
+
+    @staticmethod
+    def _mark_bad(map_points, pw, flags):
+        """A point whose in-window observations are all flagged is marked bad (map_point.py:75-78)."""
+        n_pt = len(map_points)
+        tot = np.diff(pw.pt_offsets)
+        bad = np.bincount(pw.obs_pt, weights=flags.astype(np.float64), minlength=n_pt)
+        for j in np.nonzero((tot > 0) & (bad == tot))[0]:
+            map_points[int(j)].mark_as_bad()
+
+    @property
+    def outlier_mask(self) -> Optional[np.ndarray]:
+        """uint8 per packed observation of the last successful `optimize_local`."""
+        return None if self.last_result is None else self.last_result.flags
+
+    # ------------------------------------------------------------------------------ global / initial
+    def optimize_global(self, keyframes: List[Any], map_points: List[Any]) -> bool:
+        """Same solver over every keyframe (the reference's is an empty stub, torch_optimizer.py:319-320)."""
+        return self.optimize_local(keyframes, map_points)
+
+    def optimize_initial(self, keyframes: List[Any], map_points: List[Any]) -> bool:
+        """Two-view refinement (reference: torch_optimizer.py:209-317) on the same LM solver:
+        first keyframe fixed, second free, points free, local-BA objective."""
+        if len(keyframes) < 2 or len(map_points) == 0:     # :215-217
+            self.logger.warning("[B200Optimizer] not enough data for optimize_initial")
+            return False
+        return self.optimize_local(list(keyframes[:2]), map_points)
