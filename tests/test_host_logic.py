@@ -31,7 +31,7 @@ def test_write_back_reaches_every_object():
     window = kfs[: int(g["n_kf"])]
     pts = window_points(window)
     R = np.stack([np.eye(3)] * len(window)); t = np.arange(3 * len(window), dtype=float).reshape(-1, 3)
-    X = np.arange(3 * len(pts), dtype=np.float32).reshape(-1, 3)
+    X = np.arange(3 * len(pts), dtype=np.float64).reshape(-1, 3)
     packing.write_back(window, pts, R, t, X)
     for i, kf in enumerate(window):
         np.testing.assert_array_equal(kf.R_w2c, np.eye(3))

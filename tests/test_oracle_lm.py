@@ -90,7 +90,7 @@ def test_lm_monotone_and_flags():
     assert res.cost_hist[-1] < 0.3 * res.cost_hist[0]
     np.testing.assert_array_equal(res.R[0], p.R[0])           # gauge camera untouched
     np.testing.assert_array_equal(res.t[0], p.t[0])
-    assert res.X.dtype == np.float32
+    assert res.X.dtype == np.float64
     flags = O.outlier_flags(p.intr, res.R, res.t, res.X, p.obs_cam, p.obs_pt, p.obs_uv)
     np.testing.assert_array_equal(flags, res.flags)
     # injected gross outliers are (almost all) flagged

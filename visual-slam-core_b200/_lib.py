@@ -19,7 +19,7 @@ class BAParams(C.Structure):
     _fields_ = [
         ("huber_delta", C.c_double), ("chi2_thr", C.c_double), ("lambda0", C.c_double),
         ("lambda_up", C.c_double), ("lambda_down", C.c_double), ("lambda_min", C.c_double),
-        ("lambda_max", C.c_double), ("max_iter", C.c_int32), ("solver_kind", C.c_int32),
+        ("lambda_max", C.c_double), ("accept_rtol", C.c_double), ("max_iter", C.c_int32), ("solver_kind", C.c_int32),
         ("schur_kind", C.c_int32), ("pcg_max_iter", C.c_int32), ("pcg_tol", C.c_double),
         ("use_graph", C.c_int32), ("reserved", C.c_int32),
     ]
@@ -103,5 +103,5 @@ def load(build_if_missing: bool = True) -> C.CDLL:
 def check(lib: C.CDLL, handle, code: int, what: str):
     if code != BA_OK:
         msg = lib.ba_error_string(code).decode()
-        detail = lib.ba_last_error(handle).decode() if handle else ""
+        detail = lib.ba_last_error(handle if handle else None).decode()
         raise B200BAError(f"{what}: {msg} ({code}) {detail}")

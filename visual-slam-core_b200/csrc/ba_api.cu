@@ -121,7 +121,8 @@ extern "C" const char* ba_error_string(int code) {
   }
 }
 
-extern "C" const char* ba_last_error(const ba_handle* h) { return h ? h->err.c_str() : "null handle"; }
+static std::string g_create_err;   // ba_create has no handle to hang its message on
+extern "C" const char* ba_last_error(const ba_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 
 extern "C" void ba_default_params(ba_params* p) {
   if (!p) return;
@@ -131,8 +132,9 @@ extern "C" void ba_default_params(ba_params* p) {
   p->lambda0 = 1e-4;
   p->lambda_up = 10.0;
   p->lambda_down = 0.1;
-  p->lambda_min = 1e-9;
+  p->lambda_min = 1e-6;
   p->lambda_max = 1e8;
+  p->accept_rtol = 1e-8;
   p->max_iter = 10;
   p->solver_kind = BA_SOLVER_AUTO;
   p->schur_kind = BA_SCHUR_AUTO;
@@ -161,13 +163,21 @@ extern "C" int ba_create(const ba_params* params, int device, ba_handle** out) {
   ba_handle* h = new ba_handle();
   h->device = device;
   h->prm = p;
-  if (cudaSetDevice(device) != cudaSuccess) { delete h; return BA_ERR_CUDA; }
+  cudaError_t ce = cudaSetDevice(device);
+  if (ce != cudaSuccess) { g_create_err = std::string("cudaSetDevice: ") + cudaGetErrorString(ce); delete h; return BA_ERR_CUDA; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
-  if (configure_kernels() != 0) { delete h; return BA_ERR_CUDA; }
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
-      cudaMallocHost((void**)&h->h_ctl, sizeof(LmCtl)) != cudaSuccess) {
+  int ke = configure_kernels();
+  if (ke != 0) {
+    g_create_err = std::string("kernel attributes: ") + cudaGetErrorString((cudaError_t)ke);
+    cudaGetLastError();
+    delete h;
+    return BA_ERR_CUDA;
+  }
+  if ((ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (ce = cudaEventCreate(&h->ev0)) != cudaSuccess || (ce = cudaEventCreate(&h->ev1)) != cudaSuccess ||
+      (ce = cudaMallocHost((void**)&h->h_ctl, sizeof(LmCtl))) != cudaSuccess) {
+    g_create_err = std::string("handle resources: ") + cudaGetErrorString(ce);
     delete h;
     return BA_ERR_CUDA;
   }
@@ -208,8 +218,8 @@ static int make_work(ba_handle* h, int n_cam, int n_pt, int n_obs, const double 
   int rc;
   if ((rc = ensure(h, h->pose0, sizeof(double) * 12 * (size_t)n_cam))) return rc;
   if ((rc = ensure(h, h->pose1, sizeof(double) * 12 * (size_t)n_cam))) return rc;
-  if ((rc = ensure(h, h->X0, sizeof(float) * 3 * (size_t)(n_pt + 1)))) return rc;
-  if ((rc = ensure(h, h->X1, sizeof(float) * 3 * (size_t)(n_pt + 1)))) return rc;
+  if ((rc = ensure(h, h->X0, sizeof(double) * 3 * (size_t)(n_pt + 1)))) return rc;
+  if ((rc = ensure(h, h->X1, sizeof(double) * 3 * (size_t)(n_pt + 1)))) return rc;
   if ((rc = ensure(h, h->red, sizeof(double) * ((size_t)n * n + 2 * (size_t)n + 1)))) return rc;
   if ((rc = ensure(h, h->dp, sizeof(double) * (size_t)(n + 1)))) return rc;
   if ((rc = ensure(h, h->ctl, sizeof(LmCtl)))) return rc;
@@ -218,7 +228,7 @@ static int make_work(ba_handle* h, int n_cam, int n_pt, int n_obs, const double 
   w.K = Intr{intr[0], intr[1], intr[2], intr[3]};
   w.obs_cam = obs_cam; w.obs_pt = obs_pt; w.obs_uv = obs_uv; w.pt_off = pt_off; w.fixed = fixed;
   w.pose[0] = (double*)h->pose0.p; w.pose[1] = (double*)h->pose1.p;
-  w.X[0] = (float*)h->X0.p; w.X[1] = (float*)h->X1.p;
+  w.X[0] = (double*)h->X0.p; w.X[1] = (double*)h->X1.p;
   w.S = (double*)h->red.p;
   w.b = w.S + (size_t)n * n;
   w.diagU = w.b + n;
@@ -281,7 +291,7 @@ static void fill_report(const ba_handle* h, const LmCtl* c, ba_report* rep, int 
 
 extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t n_obs,
                               const double intr[4], double* cam_R, double* cam_t,
-                              const uint8_t* cam_fixed, float* X, const int32_t* obs_cam,
+                              const uint8_t* cam_fixed, double* X, const int32_t* obs_cam,
                               const int32_t* obs_pt, const float* obs_uv, const int32_t* pt_offsets,
                               uint8_t* flags, void* stream, ba_report* report) {
   if (!h) return BA_ERR_INVALID;
@@ -299,7 +309,7 @@ extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t
   if (rc) return rc;
   const int schur = pick_schur(h, w);
   LmInit li{h->prm.lambda0, h->prm.huber_delta, h->prm.chi2_thr, h->prm.lambda_up,
-            h->prm.lambda_down, h->prm.lambda_min, h->prm.lambda_max};
+            h->prm.lambda_down, h->prm.lambda_min, h->prm.lambda_max, h->prm.accept_rtol};
 
   int launches = 0;
   CK(cudaEventRecord(h->ev0, s));
@@ -350,7 +360,7 @@ extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t
 
 extern "C" int ba_solve_local_host(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t n_obs,
                                    const double intr[4], double* cam_R, double* cam_t,
-                                   const uint8_t* cam_fixed, float* X, const int32_t* obs_cam,
+                                   const uint8_t* cam_fixed, double* X, const int32_t* obs_cam,
                                    const int32_t* obs_pt, const float* obs_uv,
                                    const int32_t* pt_offsets, uint8_t* flags, ba_report* report) {
   if (!h) return BA_ERR_INVALID;
@@ -363,7 +373,7 @@ extern "C" int ba_solve_local_host(ba_handle* h, int32_t n_cam, int32_t n_pt, in
   if ((rc = ensure(h, h->d_R, sizeof(double) * 9 * (size_t)n_cam))) return rc;
   if ((rc = ensure(h, h->d_t, sizeof(double) * 3 * (size_t)n_cam))) return rc;
   if ((rc = ensure(h, h->d_fixed, (size_t)n_cam))) return rc;
-  if ((rc = ensure(h, h->d_X, sizeof(float) * 3 * (size_t)(n_pt + 1)))) return rc;
+  if ((rc = ensure(h, h->d_X, sizeof(double) * 3 * (size_t)(n_pt + 1)))) return rc;
   if ((rc = ensure(h, h->d_ocam, sizeof(int32_t) * (size_t)(n_obs + 1)))) return rc;
   if ((rc = ensure(h, h->d_opt, sizeof(int32_t) * (size_t)(n_obs + 1)))) return rc;
   if ((rc = ensure(h, h->d_ouv, sizeof(float) * 2 * (size_t)(n_obs + 1)))) return rc;
@@ -373,7 +383,7 @@ extern "C" int ba_solve_local_host(ba_handle* h, int32_t n_cam, int32_t n_pt, in
   CK(cudaMemcpyAsync(h->d_t.p, cam_t, sizeof(double) * 3 * (size_t)n_cam, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(h->d_fixed.p, cam_fixed, (size_t)n_cam, cudaMemcpyHostToDevice, s));
   if (n_pt > 0) {
-    CK(cudaMemcpyAsync(h->d_X.p, X, sizeof(float) * 3 * (size_t)n_pt, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_X.p, X, sizeof(double) * 3 * (size_t)n_pt, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(h->d_off.p, pt_offsets, sizeof(int32_t) * (size_t)(n_pt + 1), cudaMemcpyHostToDevice, s));
   }
   if (n_obs > 0) {
@@ -382,13 +392,13 @@ extern "C" int ba_solve_local_host(ba_handle* h, int32_t n_cam, int32_t n_pt, in
     CK(cudaMemcpyAsync(h->d_ouv.p, obs_uv, sizeof(float) * 2 * (size_t)n_obs, cudaMemcpyHostToDevice, s));
   }
   rc = ba_solve_local(h, n_cam, n_pt, n_obs, intr, (double*)h->d_R.p, (double*)h->d_t.p,
-                      (const uint8_t*)h->d_fixed.p, (float*)h->d_X.p, (const int32_t*)h->d_ocam.p,
+                      (const uint8_t*)h->d_fixed.p, (double*)h->d_X.p, (const int32_t*)h->d_ocam.p,
                       (const int32_t*)h->d_opt.p, (const float*)h->d_ouv.p,
                       (const int32_t*)h->d_off.p, flags ? (uint8_t*)h->d_flags.p : nullptr, s, nullptr);
   if (rc) return rc;
   CK(cudaMemcpyAsync(cam_R, h->d_R.p, sizeof(double) * 9 * (size_t)n_cam, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(cam_t, h->d_t.p, sizeof(double) * 3 * (size_t)n_cam, cudaMemcpyDeviceToHost, s));
-  if (n_pt > 0) CK(cudaMemcpyAsync(X, h->d_X.p, sizeof(float) * 3 * (size_t)n_pt, cudaMemcpyDeviceToHost, s));
+  if (n_pt > 0) CK(cudaMemcpyAsync(X, h->d_X.p, sizeof(double) * 3 * (size_t)n_pt, cudaMemcpyDeviceToHost, s));
   if (flags && n_obs > 0) CK(cudaMemcpyAsync(flags, h->d_flags.p, (size_t)n_obs, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(h->h_ctl, h->ctl.p, sizeof(LmCtl), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -404,7 +414,7 @@ extern "C" int ba_solve_local_host(ba_handle* h, int32_t n_cam, int32_t n_pt, in
 
 extern "C" int ba_eval_cost(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t n_obs,
                             const double intr[4], const double* cam_R, const double* cam_t,
-                            const float* X, const int32_t* obs_cam, const int32_t* obs_pt,
+                            const double* X, const int32_t* obs_cam, const int32_t* obs_pt,
                             const float* obs_uv, void* stream, double* cost_out) {
   if (!h || !cost_out || n_cam <= 0) return BA_ERR_INVALID;
   CK(cudaSetDevice(h->device));
@@ -413,7 +423,7 @@ extern "C" int ba_eval_cost(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t n
   int rc = make_work(h, n_cam, n_pt, n_obs, intr, nullptr, obs_cam, obs_pt, obs_uv, nullptr, w);
   if (rc) return rc;
   LmInit li{h->prm.lambda0, h->prm.huber_delta, h->prm.chi2_thr, h->prm.lambda_up,
-            h->prm.lambda_down, h->prm.lambda_min, h->prm.lambda_max};
+            h->prm.lambda_down, h->prm.lambda_min, h->prm.lambda_max, h->prm.accept_rtol};
   launch_init(w, cam_R, cam_t, X, li, s);
   launch_eval_cost(w, w.pose[0], w.X[0], w.cost_cand, h->prm.huber_delta, s);
   CK(cudaMemcpyAsync(cost_out, w.cost_cand, sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -424,7 +434,7 @@ extern "C" int ba_eval_cost(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t n
 
 extern "C" int ba_debug_linearize(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t n_obs,
                                   const double intr[4], const double* cam_R, const double* cam_t,
-                                  const uint8_t* cam_fixed, const float* X, const int32_t* obs_cam,
+                                  const uint8_t* cam_fixed, const double* X, const int32_t* obs_cam,
                                   const int32_t* obs_pt, const float* obs_uv,
                                   const int32_t* pt_offsets, double lambda, void* stream,
                                   double* S_host, double* b_host, double* diagU_host,
@@ -436,7 +446,7 @@ extern "C" int ba_debug_linearize(ba_handle* h, int32_t n_cam, int32_t n_pt, int
   int rc = make_work(h, n_cam, n_pt, n_obs, intr, cam_fixed, obs_cam, obs_pt, obs_uv, pt_offsets, w);
   if (rc) return rc;
   LmInit li{lambda, h->prm.huber_delta, h->prm.chi2_thr, h->prm.lambda_up,
-            h->prm.lambda_down, h->prm.lambda_min, h->prm.lambda_max};
+            h->prm.lambda_down, h->prm.lambda_min, h->prm.lambda_max, h->prm.accept_rtol};
   launch_init(w, cam_R, cam_t, X, li, s);
   if (pick_schur(h, w) == BA_SCHUR_TILED) launch_linearize_tiled(w, h->sm_count, s);
   else launch_linearize_scatter(w, h->sm_count, s);
@@ -470,6 +480,7 @@ extern "C" int ba_solve_pose_only(ba_handle* h, int32_t n_frames, int32_t n_matc
   w.huber_delta = h->prm.huber_delta; w.chi2_thr = h->prm.chi2_thr; w.lambda0 = h->prm.lambda0;
   w.lambda_up = h->prm.lambda_up; w.lambda_down = h->prm.lambda_down;
   w.lambda_min = h->prm.lambda_min; w.lambda_max = h->prm.lambda_max;
+  w.accept_rtol = h->prm.accept_rtol;
   launch_pose_only(w, (cudaStream_t)stream);
   CK(cudaGetLastError());
   return BA_OK;

@@ -31,7 +31,7 @@ struct LmCtl {
   int pcg_iters_last;
   int pad0, pad1;
   // parameters
-  double huber_delta, chi2_thr, lambda_up, lambda_down, lambda_min, lambda_max;
+  double huber_delta, chi2_thr, lambda_up, lambda_down, lambda_min, lambda_max, accept_rtol;
   // history
   double cost_hist[65];
   double cand_hist[64];
@@ -174,7 +174,7 @@ __device__ __forceinline__ void linearize_obs(const Intr& K, const double* __res
 __device__ __forceinline__ void lm_accept(LmCtl* c) {
   int it = c->iter;
   double cand = c->cost_cand, cur = c->cost_cur;
-  bool ok = (c->solve_fail == 0) && isfinite(cand) && (cand < cur);
+  bool ok = (c->solve_fail == 0) && isfinite(cand) && (cand < cur * (1.0 - c->accept_rtol));
   if (it < 64) {
     c->lambda_hist[it] = c->lambda;
     c->cand_hist[it] = cand;

@@ -15,7 +15,7 @@ struct Work {
   const int* pt_off;                  // [n_pt + 1]
   const unsigned char* fixed;         // [n_cam]
   double* pose[2];                    // [12 n_cam] each: R row-major (9) then t (3); double-buffered
-  float* X[2];                        // [3 n_pt] each; double-buffered
+  double* X[2];                       // [3 n_pt] each; double-buffered
   double* S;                          // [n*n] row-major, lower triangle valid (reduction buffer)
   double* b;                          // [n]
   double* diagU;                      // [n]   diag of the un-damped pose blocks
@@ -28,18 +28,18 @@ struct Work {
 
 // launch wrappers; every one returns the number of kernels it launched
 struct LmInit {
-  double lambda0, huber_delta, chi2_thr, lambda_up, lambda_down, lambda_min, lambda_max;
+  double lambda0, huber_delta, chi2_thr, lambda_up, lambda_down, lambda_min, lambda_max, accept_rtol;
 };
-int launch_init(const Work& w, const double* R_in, const double* t_in, const float* X_in,
+int launch_init(const Work& w, const double* R_in, const double* t_in, const double* X_in,
                 const LmInit& p, cudaStream_t s);
 int launch_linearize_scatter(const Work& w, int sm_count, cudaStream_t s);
 int launch_linearize_tiled(const Work& w, int sm_count, cudaStream_t s);
 int launch_rcs_cholesky(const Work& w, cudaStream_t s);
 int launch_backsub(const Work& w, int sm_count, cudaStream_t s);
 int launch_accept(const Work& w, cudaStream_t s);
-int launch_finalize(const Work& w, double* R_out, double* t_out, float* X_out,
+int launch_finalize(const Work& w, double* R_out, double* t_out, double* X_out,
                     unsigned char* flags, cudaStream_t s);
-int launch_eval_cost(const Work& w, const double* pose, const float* X, double* out,
+int launch_eval_cost(const Work& w, const double* pose, const double* X, double* out,
                      double delta, cudaStream_t s);
 int configure_kernels();   // per-device function attributes; call once after cudaSetDevice
 size_t rcs_cholesky_smem_bytes(int n);
@@ -58,7 +58,7 @@ struct PoseWork {
   double* cost_hist;         // [n_frames*(max_iter+1)] or null
   unsigned char* accepted;   // [n_frames*max_iter] or null
   int max_iter;
-  double huber_delta, chi2_thr, lambda0, lambda_up, lambda_down, lambda_min, lambda_max;
+  double huber_delta, chi2_thr, lambda0, lambda_up, lambda_down, lambda_min, lambda_max, accept_rtol;
 };
 int launch_pose_only(const PoseWork& w, cudaStream_t s);
 

@@ -17,7 +17,7 @@ static constexpr int kThreads = kWarps * 32;
 // state initialisation
 // ------------------------------------------------------------------------------------------
 __global__ void k_init(Work w, const double* __restrict__ R_in, const double* __restrict__ t_in,
-                       const float* __restrict__ X_in, LmInit p) {
+                       const double* __restrict__ X_in, LmInit p) {
   int tid = blockIdx.x * blockDim.x + threadIdx.x;
   int nth = gridDim.x * blockDim.x;
   for (int i = tid; i < w.n_cam * 12; i += nth) {
@@ -39,6 +39,7 @@ __global__ void k_init(Work w, const double* __restrict__ R_in, const double* __
     c->lambda_down = p.lambda_down;
     c->lambda_min = p.lambda_min;
     c->lambda_max = p.lambda_max;
+    c->accept_rtol = p.accept_rtol;
     c->cost_cur = 0.0;
     c->cost_cand = 0.0;
     c->cost_lin = 0.0;
@@ -52,7 +53,7 @@ __global__ void k_init(Work w, const double* __restrict__ R_in, const double* __
   }
 }
 
-int launch_init(const Work& w, const double* R_in, const double* t_in, const float* X_in,
+int launch_init(const Work& w, const double* R_in, const double* t_in, const double* X_in,
                 const LmInit& p, cudaStream_t s) {
   long long work = (long long)w.n * w.n + 3LL * w.n_pt;
   int blocks = (int)((work + 255) / 256);
@@ -100,7 +101,7 @@ k_linearize_scatter(Work w) {
   const int cur = ctl->cur;
   const double lambda = ctl->lambda, delta = ctl->huber_delta;
   const double* __restrict__ pose = w.pose[cur];
-  const float* __restrict__ X = w.X[cur];
+  const double* __restrict__ X = w.X[cur];
   const int n = w.n;
   double cost = 0.0;
 
@@ -257,9 +258,10 @@ __device__ __forceinline__ int tri(int r, int c) { return ((r * (r + 1)) >> 1) +
 size_t rcs_cholesky_smem_bytes(int n) {
   return sizeof(double) * ((size_t)(n + 1) * (n + 2) / 2 + n + 8);
 }
+static constexpr size_t kSolveSmemMax = 227 * 1024 - 1024;   // opt-in limit minus static shared
 int rcs_cholesky_max_n() {
   int n = 6;
-  while (rcs_cholesky_smem_bytes(n + 6) <= 227 * 1024) n += 6;
+  while (rcs_cholesky_smem_bytes(n + 6) <= kSolveSmemMax) n += 6;
   return n;
 }
 
@@ -374,8 +376,8 @@ k_rcs_cholesky(Work w) {
 
 int configure_kernels() {
   cudaError_t e = cudaFuncSetAttribute(k_rcs_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(227 * 1024));
-  return e == cudaSuccess ? 0 : -1;
+                                       (int)kSolveSmemMax);
+  return e == cudaSuccess ? 0 : (int)e;
 }
 
 int launch_rcs_cholesky(const Work& w, cudaStream_t s) {
@@ -397,8 +399,8 @@ k_backsub(Work w) {
   const double lambda = ctl->lambda, delta = ctl->huber_delta;
   const double* __restrict__ pose = w.pose[cur];
   const double* __restrict__ posen = w.pose[cur ^ 1];
-  const float* __restrict__ X = w.X[cur];
-  float* __restrict__ Xn = w.X[cur ^ 1];
+  const double* __restrict__ X = w.X[cur];
+  double* __restrict__ Xn = w.X[cur ^ 1];
   const double* __restrict__ dp = w.dp;
   double cost = 0.0;
 
@@ -407,12 +409,11 @@ k_backsub(Work w) {
   for (int j = warp_global; j < w.n_pt; j += warp_total) {
     const int o0 = __ldg(w.pt_off + j);
     const int k = __ldg(w.pt_off + j + 1) - o0;
-    const float xf0 = X[3 * j], xf1 = X[3 * j + 1], xf2 = X[3 * j + 2];
+    const double X0 = X[3 * j], X1 = X[3 * j + 1], X2 = X[3 * j + 2];
     if (k <= 0) {
-      if (lane == 0) { Xn[3 * j] = xf0; Xn[3 * j + 1] = xf1; Xn[3 * j + 2] = xf2; }
+      if (lane == 0) { Xn[3 * j] = X0; Xn[3 * j + 1] = X1; Xn[3 * j + 2] = X2; }
       continue;
     }
-    const double X0 = xf0, X1 = xf1, X2 = xf2;
     double V[6] = {0, 0, 0, 0, 0, 0}, q[3] = {0, 0, 0};
     for (int base = 0; base < k; base += 32) {
       int i = base + lane;
@@ -450,9 +451,8 @@ k_backsub(Work w) {
     const double d0 = -(Vi[0] * q[0] + Vi[1] * q[1] + Vi[2] * q[2]);
     const double d1 = -(Vi[1] * q[0] + Vi[3] * q[1] + Vi[4] * q[2]);
     const double d2 = -(Vi[2] * q[0] + Vi[4] * q[1] + Vi[5] * q[2]);
-    const float n0 = (float)(X0 + d0), n1 = (float)(X1 + d1), n2 = (float)(X2 + d2);
-    if (lane == 0) { Xn[3 * j] = n0; Xn[3 * j + 1] = n1; Xn[3 * j + 2] = n2; }
-    const double N0 = n0, N1 = n1, N2 = n2;
+    const double N0 = X0 + d0, N1 = X1 + d1, N2 = X2 + d2;
+    if (lane == 0) { Xn[3 * j] = N0; Xn[3 * j + 1] = N1; Xn[3 * j + 2] = N2; }
     for (int base = 0; base < k; base += 32) {
       int i = base + lane;
       if (i < k) {
@@ -511,11 +511,11 @@ int launch_accept(const Work& w, cudaStream_t s) {
 // outlier flags at the final accepted iterate + copy-out
 // ------------------------------------------------------------------------------------------
 __global__ void k_finalize(Work w, double* __restrict__ R_out, double* __restrict__ t_out,
-                           float* __restrict__ X_out, unsigned char* __restrict__ flags) {
+                           double* __restrict__ X_out, unsigned char* __restrict__ flags) {
   const int cur = w.ctl->cur;
   const double chi2 = w.ctl->chi2_thr;
   const double* __restrict__ pose = w.pose[cur];
-  const float* __restrict__ X = w.X[cur];
+  const double* __restrict__ X = w.X[cur];
   int tid = blockIdx.x * blockDim.x + threadIdx.x;
   int nth = gridDim.x * blockDim.x;
   if (flags) {
@@ -523,8 +523,8 @@ __global__ void k_finalize(Work w, double* __restrict__ R_out, double* __restric
       ObsIn in = load_obs(w, o);
       int j = __ldg(w.obs_pt + o);
       double ru, rv;
-      residual_only(w.K, pose + 12 * in.cam, pose + 12 * in.cam + 9, (double)X[3 * j],
-                    (double)X[3 * j + 1], (double)X[3 * j + 2], in.u, in.v, ru, rv);
+      residual_only(w.K, pose + 12 * in.cam, pose + 12 * in.cam + 9, X[3 * j], X[3 * j + 1],
+                    X[3 * j + 2], in.u, in.v, ru, rv);
       flags[o] = (ru * ru + rv * rv) > chi2 ? 1 : 0;
     }
   }
@@ -536,7 +536,7 @@ __global__ void k_finalize(Work w, double* __restrict__ R_out, double* __restric
   }
 }
 
-int launch_finalize(const Work& w, double* R_out, double* t_out, float* X_out,
+int launch_finalize(const Work& w, double* R_out, double* t_out, double* X_out,
                     unsigned char* flags, cudaStream_t s) {
   int work = w.n_obs > 3 * w.n_pt ? w.n_obs : 3 * w.n_pt;
   int blocks = (work + 255) / 256;
@@ -549,7 +549,7 @@ int launch_finalize(const Work& w, double* R_out, double* t_out, float* X_out,
 // ------------------------------------------------------------------------------------------
 // objective only
 // ------------------------------------------------------------------------------------------
-__global__ void k_eval_cost(Work w, const double* __restrict__ pose, const float* __restrict__ X,
+__global__ void k_eval_cost(Work w, const double* __restrict__ pose, const double* __restrict__ X,
                             double* out, double delta) {
   double cost = 0.0;
   int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -566,7 +566,7 @@ __global__ void k_eval_cost(Work w, const double* __restrict__ pose, const float
   if ((threadIdx.x & 31) == 0) atomicAdd(out, cost);
 }
 
-int launch_eval_cost(const Work& w, const double* pose, const float* X, double* out,
+int launch_eval_cost(const Work& w, const double* pose, const double* X, double* out,
                      double delta, cudaStream_t s) {
   int blocks = (w.n_obs + 255) / 256;
   if (blocks < 1) blocks = 1;

@@ -152,7 +152,7 @@ k_pose_only(PoseWork w) {
     block_sum<1>(c, s_red, s_sum);
     if (tid == 0) {
       double cand = s_sum[0];
-      bool ok = (s_fail == 0) && isfinite(cand) && (cand < s_cost);
+      bool ok = (s_fail == 0) && isfinite(cand) && (cand < s_cost * (1.0 - w.accept_rtol));
       if (ok) {
         s_cur = cur ^ 1;
         s_cost = cand;

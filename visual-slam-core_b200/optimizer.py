@@ -66,8 +66,9 @@ def lm_config_from(config: Optional[Any]) -> LMConfig:
         lambda0=float(g("lm_lambda0", 1e-4)),
         lambda_up=float(g("lm_lambda_up", 10.0)),
         lambda_down=float(g("lm_lambda_down", 0.1)),
-        lambda_min=float(g("lm_lambda_min", 1e-9)),
+        lambda_min=float(g("lm_lambda_min", 1e-6)),
         lambda_max=float(g("lm_lambda_max", 1e8)),
+        accept_rtol=float(g("lm_accept_rtol", 1e-8)),
         max_iter=int(g("lm_max_iter", 10)),
         solver=str(g("solver", "auto")),
         schur=str(g("schur", "auto")),

@@ -29,7 +29,7 @@ class PackedWindow:
     R: np.ndarray           # (n_cam,3,3) f64 (float32-valued)
     t: np.ndarray           # (n_cam,3)
     fixed: np.ndarray       # (n_cam,) u8
-    X: np.ndarray           # (n_pt,3) f32
+    X: np.ndarray           # (n_pt,3) f64 (float32-valued)
     obs_cam: np.ndarray     # (n_obs,) i32  index into `keyframes`
     obs_pt: np.ndarray      # (n_obs,) i32
     obs_uv: np.ndarray      # (n_obs,2) f32
@@ -59,9 +59,9 @@ def pack_window(keyframes: List[Any], map_points: List[Any]) -> PackedWindow:
 
     n_pt = len(map_points)
     if n_pt:
-        X = np.array([mp.position for mp in map_points], dtype=np.float32).reshape(n_pt, 3)
+        X = np.array([mp.position for mp in map_points], dtype=np.float32).reshape(n_pt, 3).astype(np.float64)
     else:
-        X = np.zeros((0, 3), dtype=np.float32)
+        X = np.zeros((0, 3), dtype=np.float64)
 
     obs_cam: List[int] = []
     obs_pt: List[int] = []

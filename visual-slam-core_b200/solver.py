@@ -25,8 +25,9 @@ class LMConfig:
     lambda0: float = 1e-4
     lambda_up: float = 10.0
     lambda_down: float = 0.1
-    lambda_min: float = 1e-9
+    lambda_min: float = 1e-6
     lambda_max: float = 1e8
+    accept_rtol: float = 1e-8
     max_iter: int = 10
     solver: str = "auto"        # auto | cholesky | pcg
     schur: str = "auto"         # auto | scatter | tiled
@@ -39,6 +40,7 @@ class LMConfig:
         p.huber_delta, p.chi2_thr, p.lambda0 = self.huber_delta, self.chi2_thr, self.lambda0
         p.lambda_up, p.lambda_down = self.lambda_up, self.lambda_down
         p.lambda_min, p.lambda_max = self.lambda_min, self.lambda_max
+        p.accept_rtol = self.accept_rtol
         p.max_iter = int(self.max_iter)
         p.solver_kind = {"auto": 0, "cholesky": 1, "pcg": 2}[self.solver]
         p.schur_kind = {"auto": 0, "scatter": 1, "tiled": 2}[self.schur]
@@ -107,7 +109,7 @@ class LocalBASolver:
         intr = np.ascontiguousarray(intr, dtype=np.float64)
         R = np.array(R, dtype=np.float64, order="C").reshape(-1, 3, 3)
         t = np.array(t, dtype=np.float64, order="C").reshape(-1, 3)
-        X = np.array(X, dtype=np.float32, order="C").reshape(-1, 3)
+        X = np.array(X, dtype=np.float64, order="C").reshape(-1, 3)
         fixed = np.ascontiguousarray(fixed, dtype=np.uint8)
         obs_cam = np.ascontiguousarray(obs_cam, dtype=np.int32)
         obs_pt = np.ascontiguousarray(obs_pt, dtype=np.int32)
@@ -141,9 +143,9 @@ class LocalBASolver:
     # ------------------------------------------------------------------ local BA, torch CUDA tensors
     def solve_local_device(self, intr, R, t, fixed, X, obs_cam, obs_pt, obs_uv, pt_offsets,
                            flags=None, stream: Optional[int] = None, sync: bool = True):
-        """In-place refinement of torch CUDA tensors (float64 R,t; float32 X,uv; int32 indices)."""
+        """In-place refinement of torch CUDA tensors (float64 R,t,X; float32 uv; int32 indices)."""
         import torch
-        for name, ten, dt in (("R", R, torch.float64), ("t", t, torch.float64), ("X", X, torch.float32),
+        for name, ten, dt in (("R", R, torch.float64), ("t", t, torch.float64), ("X", X, torch.float64),
                               ("obs_uv", obs_uv, torch.float32), ("obs_cam", obs_cam, torch.int32),
                               ("obs_pt", obs_pt, torch.int32), ("pt_offsets", pt_offsets, torch.int32),
                               ("fixed", fixed, torch.uint8)):
@@ -198,7 +200,7 @@ class LocalBASolver:
             R=torch.as_tensor(np.ascontiguousarray(R, dtype=np.float64)).to(dev),
             t=torch.as_tensor(np.ascontiguousarray(t, dtype=np.float64)).to(dev),
             fixed=torch.as_tensor(np.ascontiguousarray(fixed, dtype=np.uint8)).to(dev),
-            X=torch.as_tensor(np.ascontiguousarray(X, dtype=np.float32)).to(dev),
+            X=torch.as_tensor(np.ascontiguousarray(X, dtype=np.float64)).to(dev),
             oc=torch.as_tensor(np.ascontiguousarray(obs_cam, dtype=np.int32)).to(dev),
             op=torch.as_tensor(np.ascontiguousarray(obs_pt, dtype=np.int32)).to(dev),
             uv=torch.as_tensor(np.ascontiguousarray(obs_uv, dtype=np.float32)).to(dev),

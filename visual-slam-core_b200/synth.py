@@ -45,7 +45,7 @@ class BAProblem:
     R: np.ndarray             # (n_cam,3,3) f64 world->camera
     t: np.ndarray             # (n_cam,3) f64
     fixed: np.ndarray         # (n_cam,) u8
-    X: np.ndarray             # (n_pt,3) f32
+    X: np.ndarray             # (n_pt,3) f64, float32-representable
     obs_cam: np.ndarray       # (n_obs,) i32
     obs_pt: np.ndarray        # (n_obs,) i32, non-decreasing
     obs_uv: np.ndarray        # (n_obs,2) f32
@@ -293,7 +293,7 @@ def make_problem(
         R=R0.astype(np.float32).astype(np.float64),
         t=t0.astype(np.float32).astype(np.float64),
         fixed=fixed,
-        X=X0.astype(np.float32),
+        X=X0.astype(np.float32).astype(np.float64),
         obs_cam=obs_cam, obs_pt=obs_pt, obs_uv=obs_uv,
         pt_offsets=pt_offsets.astype(np.int32),
         R_true=R_true, t_true=t_true, X_true=X_true, outlier=outlier,
