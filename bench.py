@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the local-BA hot path (BASELINE.json metric: LM iterations/s, obs/s through
+residual + Jacobian + Schur, against the HBM roofline, with the CPU path timed beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2] [--impl b200|reference]
+
+A *step* is one complete local-BA solve of the workload window: `max_iter` (10) LM iterations,
+each = linearise + Schur -> reduced-camera solve -> back-substitution + candidate cost ->
+accept/reject, plus state init and outlier flags.  Every step starts from the same initial state.
+
+  value  = LM iterations/s with inputs resident in HBM (CUDA events around each step, L2 flushed
+           between steps, max over ranks; N > 1 = one independent window per GPU, weak scaling).
+  e2e    = the same through the public host-buffer API (`LocalBASolver.solve_local_inplace`,
+           i.e. the C-ABI `ba_solve_local_host`): pinned host inputs -> H2D -> solve -> D2H of
+           poses, points, flags and the LM report, all inside the timed region.
+  roofline = dominant kernel (by summed device time, measured live with CUDA events in a
+           profile pass of the same workload): algorithmic bytes / launch duration vs measured HBM peak.
+  cpu_baseline = oracle/lm_oracle.py (same LM, numpy float64) on this box's host cores.
+
+`--impl reference` times the reference's own CPU algorithm (Adam over a Python per-observation
+autograd loop, restated in oracle/ref_adam.py and validated against the unmodified reference in
+tests/test_ref_adam.py) on a bounded sample of the same window.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "local_ba_lm_iterations_per_s"
+UNIT = "LM iter/s"
+
+
+# --------------------------------------------------------------------------------------------
+def algorithmic_bytes(n_cam, n_pt, n_obs):
+    """SURVEY.md 8d-D4 / BASELINE.md 3 (float32 values, int32 indices, dense |S|)."""
+    S = (6 * n_cam) ** 2 * 4
+    b_rjs = 17 * n_obs + 48 * n_pt + 72 * n_cam + S
+    b_iter = 33 * n_obs + 108 * n_pt + 72 * n_cam + 2 * S
+    return b_rjs, b_iter
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's CPU algorithm on a bounded sample of the workload window."""
+    if rank != 0:
+        return
+    import torch
+    import b200ba  # noqa: F401
+    from visual_slam_core_b200 import synth
+    from oracle import ref_adam
+    p = synth.make_problem(args.config, seed=0)
+    total = args.steps + args.warmup
+    # probe the per-observation cost, then size the sample so the whole run ends in ~2.5 minutes
+    probe_n = 60
+    sub = p.shard_by_point(0, max(1, p.n_obs // probe_n))
+    ref_adam.adam_local_ba(sub.intr, sub.R, sub.t, sub.fixed, sub.X, sub.obs_cam, sub.obs_pt, sub.obs_uv, 1, 1e-4)
+    t0 = time.perf_counter()   # the first call pays torch's lazy initialisation: time the second
+    ref_adam.adam_local_ba(sub.intr, sub.R, sub.t, sub.fixed, sub.X, sub.obs_cam, sub.obs_pt, sub.obs_uv, 1, 1e-4)
+    per_obs = (time.perf_counter() - t0) / max(sub.n_obs, 1)
+    budget = 150.0
+    n_sample = int(min(p.n_obs, max(200, budget / max(total, 1) / max(per_obs, 1e-6))))
+    sub = p.shard_by_point(0, max(1, round(p.n_obs / n_sample)))
+    out = ref_adam.adam_local_ba(sub.intr, sub.R, sub.t, sub.fixed, sub.X, sub.obs_cam, sub.obs_pt, sub.obs_uv,
+                                 n_iter=total, lr=1e-4, delta=5.0)
+    secs = out["secs"][args.warmup:]
+    t_step = sum(secs) / max(len(secs), 1)
+    # one reference iteration over the full window = t_step * n_obs / sample (linear in n_obs: SURVEY 6)
+    value = (sub.n_obs / p.n_obs) / t_step
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, p), "iteration": "one Adam iteration (the reference has no LM)",
+                   "extrapolation": "value = (sample_obs / window_obs) / seconds_per_iteration; time is linear in observations"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{sub.n_obs} of {p.n_obs} observations ({sub.n_pt} points), {len(secs)} timed Adam "
+                                   f"iterations, torch {torch.__version__} CPU, torch threads {torch.get_num_threads()} "
+                                   f"(the loop is a single Python thread), host cpus {os.cpu_count()}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(cfg, p):
+    return f"{cfg}: local BA window, {p.n_cam} keyframes, {p.n_pt} map points, {p.n_obs} observations, pinhole, Huber 5px"
+
+
+# --------------------------------------------------------------------------------------------
+def run_b200(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import b200ba  # noqa: F401
+    from visual_slam_core_b200 import LMConfig, LocalBASolver, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the solver has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    max_iter = args.lm_iters
+    p = synth.make_problem(args.config, seed=rank)          # one independent window per GPU
+    T = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(dev)
+    R0, t0, X0 = T(p.R), T(p.t), T(p.X)
+    R, t, X = R0.clone(), t0.clone(), X0.clone()
+    fixed, oc, op, uv, off = T(p.fixed), T(p.obs_cam), T(p.obs_pt), T(p.obs_uv), T(p.pt_offsets)
+    flags = torch.zeros(p.n_obs, dtype=torch.uint8, device=dev)
+    solver = LocalBASolver(LMConfig(max_iter=max_iter, schur=args.schur), device=local_rank)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(sync=False):
+        R.copy_(R0); t.copy_(t0); X.copy_(X0)
+        return solver.solve_local_device(p.intr, R, t, fixed, X, oc, op, uv, off, flags,
+                                         stream=stream.cuda_stream, sync=sync)
+
+    rep = None
+    for _ in range(max(args.warmup, 3)):
+        rep = step(sync=True)
+    launches_per_step = int(rep.n_launches)
+
+    sampler = ClockSampler(local_rank)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    sampler.start()
+    for a, b in evs:
+        flush.zero_()
+        a.record(stream)
+        step(sync=False)
+        b.record(stream)
+    barrier()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop()
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    value = world * args.steps * max_iter / (ms_max / 1e3)
+
+    # ---- end to end through the host-buffer API (pinned host memory, copies inside the timed region)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a).copy()).pin_memory().numpy()
+    hR, ht, hX = pin(p.R), pin(p.t), pin(p.X)
+    hfixed, hoc, hop, huv, hoff = pin(p.fixed), pin(p.obs_cam), pin(p.obs_pt), pin(p.obs_uv), pin(p.pt_offsets)
+    hflags = pin(np.zeros(p.n_obs, dtype=np.uint8))
+    e2e_solver = LocalBASolver(LMConfig(max_iter=max_iter, schur=args.schur), device=local_rank)
+
+    def e2e_step():
+        np.copyto(hR, p.R); np.copyto(ht, p.t); np.copyto(hX, p.X)
+        return e2e_solver.solve_local_inplace(p.intr, hR, ht, hfixed, hX, hoc, hop, huv, hoff, hflags)
+
+    for _ in range(max(args.warmup, 3)):
+        res = e2e_step()
+    barrier()
+    t_a = time.perf_counter()
+    for _ in range(args.steps):
+        res = e2e_step()
+    torch.cuda.synchronize(dev)
+    t_b = time.perf_counter()
+    te = torch.tensor([t_b - t_a], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps * max_iter / float(te.item())
+    import ctypes as C
+    from visual_slam_core_b200 import _lib
+    h2d = sum(a.nbytes for a in (hR, ht, hfixed, hX, hoc, hop, huv, hoff))
+    d2h = hR.nbytes + ht.nbytes + hX.nbytes + hflags.nbytes + 2240   # + LM control block (report)
+    final_cost = float(res.cost_hist[-1])
+
+    # ---- profile pass: CUDA events around every kernel (no graph), same workload
+    prof = LocalBASolver(LMConfig(max_iter=max_iter, schur=args.schur, profile=True), device=local_rank)
+    acc = np.zeros(4)
+    n_prof = 5
+    for i in range(n_prof + 2):
+        R.copy_(R0); t.copy_(t0); X.copy_(X0)
+        r = prof.solve_local_device(p.intr, R, t, fixed, X, oc, op, uv, off, flags, stream=stream.cuda_stream, sync=True)
+        if i >= 2:
+            acc += np.array([r.ms_linearize, r.ms_solve, r.ms_backsub, r.ms_other])
+    acc /= n_prof
+    k_ms = {"linearize_schur": acc[0] / max_iter, "rcs_solve": acc[1] / max_iter,
+            "backsub_cost": acc[2] / max_iter, "init_finalize_per_step": acc[3]}
+    b_rjs, b_iter = algorithmic_bytes(p.n_cam, p.n_pt, p.n_obs)
+    peak, peak_src = hbm_peak()
+    dom = max(("linearize_schur", "rcs_solve", "backsub_cost"), key=lambda k: k_ms[k])
+    lin_gbs = b_rjs / (k_ms["linearize_schur"] * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(args.config, {}).get("linearize_schur")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_linearize (residual+Jacobian+Schur)", "achieved": lin_gbs, "peak": peak,
+                "unit": "GB/s", "frac": lin_gbs / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": b_rjs, "launch_ms": k_ms["linearize_schur"],
+                "dominant_kernel_by_time": dom,
+                "whole_iteration": {"algorithmic_bytes": b_iter,
+                                    "achieved": b_iter / (ms_max / 1e3 / (args.steps * max_iter)) / 1e9,
+                                    "frac": b_iter / (ms_max / 1e3 / (args.steps * max_iter)) / 1e9 / peak},
+                "note": "window is L2-resident (working set << 126 MB L2): latency/atomics-bound, see DESIGN.md"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, p), "lm_iterations_per_step": max_iter,
+                   "parallelism": "single GPU" if world == 1 else f"{world} independent windows, one per GPU (replicas)",
+                   "l2": "flushed between steps (256 MiB write); inside a step the window stays L2-resident by construction",
+                   "schur": args.schur},
+        "obs_per_s_residual_jacobian_schur": p.n_obs / (k_ms["linearize_schur"] * 1e-3) * world,
+        "kernel_ms_per_lm_iteration": k_ms,
+        "final_cost": final_cost,
+        "roofline": roofline,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "api": "LocalBASolver.solve_local_inplace -> ba_solve_local_host (pinned host buffers)"},
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks,
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import lm_oracle as O
+        t_c = time.perf_counter()
+        ref = O.solve_local(p.intr, p.R, p.t, p.fixed, p.X, p.obs_cam, p.obs_pt, p.obs_uv,
+                            O.LMParams(max_iter=max_iter))
+        dt = time.perf_counter() - t_c
+        rel = float(np.max(np.abs(res.cost_hist - ref.cost_hist) / ref.cost_hist))
+        line["cpu_baseline"] = {"value": max_iter / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"the full window, one solve of {max_iter} LM iterations with "
+                                          f"oracle/lm_oracle.py (numpy float64, same algorithm) in {dt:.1f} s"}
+        line["parity_vs_oracle"] = {"max_rel_cost_diff": rel,
+                                    "accept_sequence_equal": bool(np.array_equal(res.accepted, ref.accepted)),
+                                    "flags_equal": bool(np.array_equal(res.flags, ref.flags))}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--lm-iters", type=int, default=10)
+    ap.add_argument("--schur", default="auto")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

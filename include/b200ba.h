@@ -69,7 +69,7 @@ typedef struct ba_params {
   int32_t pcg_max_iter; /* block-Jacobi PCG cap */
   double pcg_tol;       /* relative residual */
   int32_t use_graph;    /* capture the LM loop in a CUDA graph (1) */
-  int32_t reserved;
+  int32_t profile;      /* 1: no graph, CUDA events around every kernel -> ba_report.ms_* (0) */
 } ba_params;
 
 typedef struct ba_report {
@@ -83,8 +83,12 @@ typedef struct ba_report {
   uint8_t accepted[BA_MAX_ITER];        /* 1 = step accepted */
   int32_t solve_fail[BA_MAX_ITER];      /* 1 = reduced system not SPD / PCG breakdown */
   int32_t pcg_iters[BA_MAX_ITER];
-  float gpu_ms;                         /* device time of the LM loop (CUDA events) */
+  float gpu_ms;                         /* device time of the whole solve (CUDA events) */
   int32_t n_launches;                   /* kernels launched by this solve */
+  float ms_linearize;                   /* profile=1 only: summed device time per kernel class */
+  float ms_solve;
+  float ms_backsub;
+  float ms_other;                       /* init + finalize (+ collectives when sharded) */
 } ba_report;
 
 typedef struct ba_handle ba_handle;

@@ -34,7 +34,7 @@ def test_struct_layout_matches_header():
     lib.ba_default_params(C.byref(p))
     assert (p.huber_delta, p.chi2_thr, p.lambda0, p.max_iter) == (5.0, 5.991, 1e-4, 10)
     assert (p.lambda_up, p.lambda_down, p.lambda_min, p.lambda_max) == (10.0, 0.1, 1e-6, 1e8)
-    assert p.use_graph == 1 and p.pcg_tol == 1e-10
+    assert p.use_graph == 1 and p.profile == 0 and p.pcg_tol == 1e-10
     assert C.sizeof(_lib.BAParams) == 8 * 8 + 4 * 4 + 8 + 2 * 4
     assert p.accept_rtol == 1e-8
     assert lib.ba_version() >= 100

@@ -21,7 +21,7 @@ class BAParams(C.Structure):
         ("lambda_up", C.c_double), ("lambda_down", C.c_double), ("lambda_min", C.c_double),
         ("lambda_max", C.c_double), ("accept_rtol", C.c_double), ("max_iter", C.c_int32), ("solver_kind", C.c_int32),
         ("schur_kind", C.c_int32), ("pcg_max_iter", C.c_int32), ("pcg_tol", C.c_double),
-        ("use_graph", C.c_int32), ("reserved", C.c_int32),
+        ("use_graph", C.c_int32), ("profile", C.c_int32),
     ]
 
 
@@ -36,6 +36,8 @@ class BAReport(C.Structure):
         ("solve_fail", C.c_int32 * BA_MAX_ITER),
         ("pcg_iters", C.c_int32 * BA_MAX_ITER),
         ("gpu_ms", C.c_float), ("n_launches", C.c_int32),
+        ("ms_linearize", C.c_float), ("ms_solve", C.c_float), ("ms_backsub", C.c_float),
+        ("ms_other", C.c_float),
     ]
 
 

@@ -86,7 +86,36 @@ struct ba_handle {
   // multi-GPU
   nccl_comm comm = nullptr;
   int rank = 0, world = 1;
+  // profile mode: events between kernels, tag of the kernel that follows each event
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_tag;
+  int prof_n = 0;
+  float prof_ms[4] = {0, 0, 0, 0};
 };
+
+enum { TAG_LIN = 0, TAG_SOLVE = 1, TAG_BACK = 2, TAG_OTHER = 3 };
+
+static void prof_mark(ba_handle* h, int tag, cudaStream_t s) {
+  if (!h->prm.profile) return;
+  if (h->prof_n >= (int)h->prof_ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->prof_ev.push_back(e);
+    h->prof_tag.push_back(0);
+  }
+  h->prof_tag[h->prof_n] = tag;
+  cudaEventRecord(h->prof_ev[h->prof_n], s);
+  h->prof_n++;
+}
+
+static void prof_collect(ba_handle* h) {
+  for (int i = 0; i < 4; ++i) h->prof_ms[i] = 0.f;
+  for (int i = 0; i + 1 < h->prof_n; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]) == cudaSuccess)
+      h->prof_ms[h->prof_tag[i]] += ms;
+  }
+}
 
 #define CK(call)                                                                          \
   do {                                                                                    \
@@ -141,6 +170,7 @@ extern "C" void ba_default_params(ba_params* p) {
   p->pcg_max_iter = 200;
   p->pcg_tol = 1e-10;
   p->use_graph = 1;
+  p->profile = 0;
 }
 
 static int check_params(const ba_params* p) {
@@ -200,6 +230,7 @@ extern "C" int ba_destroy(ba_handle* h) {
                     &h->d_off, &h->d_flags, &h->d_hist, &h->d_acc, &h->d_foff};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -252,15 +283,20 @@ static int enqueue_lm_loop(ba_handle* h, const Work& w, int schur, cudaStream_t 
   int launches = 0;
   const size_t nred = (size_t)w.n * w.n + 2 * (size_t)w.n + 1;
   for (int it = 0; it < h->prm.max_iter; ++it) {
+    prof_mark(h, TAG_LIN, s);
     launches += (schur == BA_SCHUR_TILED) ? launch_linearize_tiled(w, h->sm_count, s)
                                           : launch_linearize_scatter(w, h->sm_count, s);
     if (h->world > 1) {
+      prof_mark(h, TAG_OTHER, s);
       int r = g_nccl.allreduce(w.S, w.S, nred, kNcclDouble, kNcclSum, h->comm, s);
       if (r != 0) { h->err = std::string("ncclAllReduce(S): ") + (g_nccl.errstr ? g_nccl.errstr(r) : "?"); return BA_ERR_NCCL; }
     }
+    prof_mark(h, TAG_SOLVE, s);
     launches += launch_rcs_cholesky(w, s);
+    prof_mark(h, TAG_BACK, s);
     launches += launch_backsub(w, h->sm_count, s);
     if (h->world > 1) {
+      prof_mark(h, TAG_OTHER, s);
       int r = g_nccl.allreduce(w.cost_cand, w.cost_cand, 1, kNcclDouble, kNcclSum, h->comm, s);
       if (r != 0) { h->err = std::string("ncclAllReduce(cost): ") + (g_nccl.errstr ? g_nccl.errstr(r) : "?"); return BA_ERR_NCCL; }
       launches += launch_accept(w, s);
@@ -286,7 +322,10 @@ static void fill_report(const ba_handle* h, const LmCtl* c, ba_report* rep, int 
   }
   rep->gpu_ms = ms;
   rep->n_launches = launches;
-  (void)h;
+  rep->ms_linearize = h->prof_ms[TAG_LIN];
+  rep->ms_solve = h->prof_ms[TAG_SOLVE];
+  rep->ms_backsub = h->prof_ms[TAG_BACK];
+  rep->ms_other = h->prof_ms[TAG_OTHER];
 }
 
 extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t n_obs,
@@ -312,10 +351,12 @@ extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t
             h->prm.lambda_down, h->prm.lambda_min, h->prm.lambda_max, h->prm.accept_rtol};
 
   int launches = 0;
+  h->prof_n = 0;
   CK(cudaEventRecord(h->ev0, s));
+  prof_mark(h, TAG_OTHER, s);
   launches += launch_init(w, cam_R, cam_t, X, li, s);
 
-  bool use_graph = h->prm.use_graph != 0 && h->prm.max_iter > 0;
+  bool use_graph = h->prm.use_graph != 0 && h->prm.max_iter > 0 && !h->prm.profile;
   if (use_graph) {
     ba_handle::GraphKey key;
     key.n_cam = n_cam; key.n_pt = n_pt; key.n_obs = n_obs; key.max_iter = h->prm.max_iter;
@@ -345,7 +386,9 @@ extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t
     if (n < 0) return n;
     launches += n;
   }
+  prof_mark(h, TAG_OTHER, s);
   launches += launch_finalize(w, cam_R, cam_t, X, flags, s);
+  prof_mark(h, TAG_OTHER, s);
   CK(cudaEventRecord(h->ev1, s));
   CK(cudaGetLastError());
   if (report) {
@@ -353,6 +396,7 @@ extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t
     CK(cudaStreamSynchronize(s));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    if (h->prm.profile) prof_collect(h);
     fill_report(h, h->h_ctl, report, BA_OK, ms, launches);
   }
   return BA_OK;
@@ -405,8 +449,8 @@ extern "C" int ba_solve_local_host(ba_handle* h, int32_t n_cam, int32_t n_pt, in
   if (report) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-    int launches = 2 + (h->prm.use_graph ? h->graph_launches
-                                         : h->prm.max_iter * (h->world > 1 ? 4 : 3));
+    int launches = 2 + h->prm.max_iter * (h->world > 1 ? 4 : 3);
+    if (h->prm.profile) prof_collect(h);
     fill_report(h, h->h_ctl, report, BA_OK, ms, launches);
   }
   return BA_OK;

@@ -34,6 +34,7 @@ class LMConfig:
     pcg_max_iter: int = 200
     pcg_tol: float = 1e-10
     use_graph: bool = True
+    profile: bool = False       # events around every kernel (disables the graph)
 
     def to_c(self) -> "_lib.BAParams":
         p = _lib.BAParams()
@@ -46,6 +47,7 @@ class LMConfig:
         p.schur_kind = {"auto": 0, "scatter": 1, "tiled": 2}[self.schur]
         p.pcg_max_iter, p.pcg_tol = int(self.pcg_max_iter), float(self.pcg_tol)
         p.use_graph = 1 if self.use_graph else 0
+        p.profile = 1 if self.profile else 0
         return p
 
 
@@ -129,6 +131,28 @@ class LocalBASolver:
             _lib.check(self.lib, self._h, rc, "ba_solve_local_host")
         return self._result(rep, R, t, X, flags)
 
+    def solve_local_inplace(self, intr, R, t, fixed, X, obs_cam, obs_pt, obs_uv, pt_offsets,
+                            flags=None) -> SolveResult:
+        """Same as `solve_local` but refines the given host arrays in place (no defensive copies):
+        R,t,X float64 C-contiguous, uv float32, indices int32, fixed/flags uint8.  Hand it pinned
+        buffers and the host<->device copies inside the call are DMA transfers."""
+        for name, a, dt in (("R", R, np.float64), ("t", t, np.float64), ("X", X, np.float64),
+                            ("obs_uv", obs_uv, np.float32), ("obs_cam", obs_cam, np.int32),
+                            ("obs_pt", obs_pt, np.int32), ("pt_offsets", pt_offsets, np.int32),
+                            ("fixed", fixed, np.uint8)):
+            if a.dtype != dt or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"{name} must be C-contiguous {dt}")
+        intr = np.ascontiguousarray(intr, dtype=np.float64)
+        n_cam, n_pt, n_obs = R.shape[0], X.shape[0], obs_cam.shape[0]
+        rep = _lib.BAReport()
+        with self._lock:
+            rc = self.lib.ba_solve_local_host(
+                self._h, n_cam, n_pt, n_obs, _dptr(intr), _ptr(R), _ptr(t), _ptr(fixed), _ptr(X),
+                _ptr(obs_cam), _ptr(obs_pt), _ptr(obs_uv), _ptr(pt_offsets), _ptr(flags),
+                C.byref(rep))
+            _lib.check(self.lib, self._h, rc, "ba_solve_local_host")
+        return self._result(rep, R, t, X, flags)
+
     def _result(self, rep, R, t, X, flags) -> SolveResult:
         k = int(rep.n_iter)
         return SolveResult(
@@ -138,7 +162,9 @@ class LocalBASolver:
             lambda_hist=np.array(rep.lambda_hist[:k]),
             accepted=np.array(rep.accepted[:k], dtype=np.uint8),
             solve_fail=np.array(rep.solve_fail[:k], dtype=np.int32),
-            n_iter=k, gpu_ms=float(rep.gpu_ms), n_launches=int(rep.n_launches))
+            n_iter=k, gpu_ms=float(rep.gpu_ms), n_launches=int(rep.n_launches),
+            extra=dict(ms_linearize=float(rep.ms_linearize), ms_solve=float(rep.ms_solve),
+                       ms_backsub=float(rep.ms_backsub), ms_other=float(rep.ms_other)))
 
     # ------------------------------------------------------------------ local BA, torch CUDA tensors
     def solve_local_device(self, intr, R, t, fixed, X, obs_cam, obs_pt, obs_uv, pt_offsets,
