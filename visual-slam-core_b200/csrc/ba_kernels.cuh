@@ -41,6 +41,7 @@ int launch_finalize(const Work& w, double* R_out, double* t_out, double* X_out,
                     unsigned char* flags, cudaStream_t s);
 int launch_eval_cost(const Work& w, const double* pose, const double* X, double* out,
                      double delta, cudaStream_t s);
+int configure_tiled();
 int configure_kernels();   // per-device function attributes; call once after cudaSetDevice
 size_t rcs_cholesky_smem_bytes(int n);
 int rcs_cholesky_max_n();

@@ -377,7 +377,8 @@ k_rcs_cholesky(Work w) {
 int configure_kernels() {
   cudaError_t e = cudaFuncSetAttribute(k_rcs_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kSolveSmemMax);
-  return e == cudaSuccess ? 0 : (int)e;
+  if (e != cudaSuccess) return (int)e;
+  return configure_tiled();
 }
 
 int launch_rcs_cholesky(const Work& w, cudaStream_t s) {
