@@ -149,7 +149,8 @@ int ba_dist_init(ba_handle* h, const void* id /* BA_NCCL_ID_BYTES */, int32_t ra
 int ba_dist_shutdown(ba_handle* h);
 
 /* Debug/inspection for tests: copy the reduced camera system of the LAST linearisation
- * (dense (6 n_cam)^2 row-major lower triangle valid, b, diagU) to host buffers. Any may be NULL. */
+ * to host buffers: S block-packed lower triangle (6x6 block (I,J), J <= I, at ((I(I+1)/2+J)*36,
+ * row-major inside; n_cam(n_cam+1)/2*36 doubles), b and diagU (6 n_cam each). Any may be NULL. */
 int ba_debug_linearize(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t n_obs,
                        const double intr[4], const double* cam_R, const double* cam_t,
                        const uint8_t* cam_fixed, const double* X,

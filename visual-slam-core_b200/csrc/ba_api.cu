@@ -2,6 +2,7 @@
 // host-pointer variants, NCCL plumbing for the shard-by-point multi-GPU path.
 #include <dlfcn.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -68,7 +69,7 @@ struct ba_handle {
   ba_params prm;
   std::string err;
   // workspace
-  DevBuf pose0, pose1, X0, X1, red, dp, ctl, cand;
+  DevBuf pose0, pose1, X0, X1, red, dp, ctl, cand, dbg;
   // staging for the host-pointer API
   DevBuf d_R, d_t, d_fixed, d_X, d_ocam, d_opt, d_ouv, d_off, d_flags, d_hist, d_acc, d_foff;
   LmCtl* h_ctl = nullptr;         // pinned
@@ -227,7 +228,7 @@ extern "C" int ba_destroy(ba_handle* h) {
   if (h->graph) cudaGraphExecDestroy(h->graph);
   DevBuf* bufs[] = {&h->pose0, &h->pose1, &h->X0, &h->X1, &h->red, &h->dp, &h->ctl, &h->cand,
                     &h->d_R, &h->d_t, &h->d_fixed, &h->d_X, &h->d_ocam, &h->d_opt, &h->d_ouv,
-                    &h->d_off, &h->d_flags, &h->d_hist, &h->d_acc, &h->d_foff};
+                    &h->d_off, &h->d_flags, &h->d_hist, &h->d_acc, &h->d_foff, &h->dbg};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
@@ -251,7 +252,7 @@ static int make_work(ba_handle* h, int n_cam, int n_pt, int n_obs, const double 
   if ((rc = ensure(h, h->pose1, sizeof(double) * 12 * (size_t)n_cam))) return rc;
   if ((rc = ensure(h, h->X0, sizeof(double) * 3 * (size_t)(n_pt + 1)))) return rc;
   if ((rc = ensure(h, h->X1, sizeof(double) * 3 * (size_t)(n_pt + 1)))) return rc;
-  if ((rc = ensure(h, h->red, sizeof(double) * ((size_t)n * n + 2 * (size_t)n + 1)))) return rc;
+  if ((rc = ensure(h, h->red, sizeof(double) * (s_doubles(n_cam) + 2 * (size_t)n + 1)))) return rc;
   if ((rc = ensure(h, h->dp, sizeof(double) * (size_t)(n + 1)))) return rc;
   if ((rc = ensure(h, h->ctl, sizeof(LmCtl)))) return rc;
   if ((rc = ensure(h, h->cand, sizeof(double) * 2))) return rc;
@@ -261,13 +262,20 @@ static int make_work(ba_handle* h, int n_cam, int n_pt, int n_obs, const double 
   w.pose[0] = (double*)h->pose0.p; w.pose[1] = (double*)h->pose1.p;
   w.X[0] = (double*)h->X0.p; w.X[1] = (double*)h->X1.p;
   w.S = (double*)h->red.p;
-  w.b = w.S + (size_t)n * n;
+  w.b = w.S + s_doubles(n_cam);
   w.diagU = w.b + n;
   w.cost_lin = w.diagU + n;
   w.cost_cand = (double*)h->cand.p;
   w.dp = (double*)h->dp.p;
   w.ctl = (LmCtl*)h->ctl.p;
   w.world = h->world;
+  w.dbg = nullptr;
+  static int want_dbg = -1;
+  if (want_dbg < 0) { const char* e = getenv("BA_DBG_TIMES"); want_dbg = (e && atoi(e)) ? 1 : 0; }
+  if (want_dbg) {
+    if ((rc = ensure(h, h->dbg, sizeof(long long) * 4096))) return rc;
+    w.dbg = (long long*)h->dbg.p;
+  }
   return BA_OK;
 }
 
@@ -281,7 +289,7 @@ static int pick_schur(const ba_handle* h, const Work& w) {
 // enqueue the LM iterations (no init / finalize); returns kernels launched or < 0
 static int enqueue_lm_loop(ba_handle* h, const Work& w, int schur, cudaStream_t s) {
   int launches = 0;
-  const size_t nred = (size_t)w.n * w.n + 2 * (size_t)w.n + 1;
+  const size_t nred = s_doubles(w.n_cam) + 2 * (size_t)w.n + 1;
   for (int it = 0; it < h->prm.max_iter; ++it) {
     prof_mark(h, TAG_LIN, s);
     launches += (schur == BA_SCHUR_TILED) ? launch_linearize_tiled(w, h->sm_count, s)
@@ -303,6 +311,20 @@ static int enqueue_lm_loop(ba_handle* h, const Work& w, int schur, cudaStream_t 
     }
   }
   return launches;
+}
+
+static void dump_dbg(ba_handle* h) {
+  if (!h->dbg.p) return;
+  std::vector<long long> hb(4096);
+  cudaMemcpy(hb.data(), h->dbg.p, sizeof(long long) * 4096, cudaMemcpyDeviceToHost);
+  fprintf(stderr, "[ba dbg]");
+  long long prev = 0;
+  for (int i = 0; i < 2000; ++i) {
+    if (hb[2 + 2 * i] == 0) continue;
+    fprintf(stderr, " %lld:%lld", hb[1 + 2 * i], prev ? hb[2 + 2 * i] - prev : 0LL);
+    prev = hb[2 + 2 * i];
+  }
+  fprintf(stderr, "\n");
 }
 
 static void fill_report(const ba_handle* h, const LmCtl* c, ba_report* rep, int status, float ms,
@@ -352,6 +374,7 @@ extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t
 
   int launches = 0;
   h->prof_n = 0;
+  if (w.dbg) cudaMemsetAsync(w.dbg, 0, sizeof(long long) * 4096, s);
   CK(cudaEventRecord(h->ev0, s));
   prof_mark(h, TAG_OTHER, s);
   launches += launch_init(w, cam_R, cam_t, X, li, s);
@@ -398,6 +421,7 @@ extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     if (h->prm.profile) prof_collect(h);
     fill_report(h, h->h_ctl, report, BA_OK, ms, launches);
+    dump_dbg(h);
   }
   return BA_OK;
 }
@@ -446,6 +470,7 @@ extern "C" int ba_solve_local_host(ba_handle* h, int32_t n_cam, int32_t n_pt, in
   if (flags && n_obs > 0) CK(cudaMemcpyAsync(flags, h->d_flags.p, (size_t)n_obs, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(h->h_ctl, h->ctl.p, sizeof(LmCtl), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  dump_dbg(h);
   if (report) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
@@ -495,7 +520,7 @@ extern "C" int ba_debug_linearize(ba_handle* h, int32_t n_cam, int32_t n_pt, int
   if (pick_schur(h, w) == BA_SCHUR_TILED) launch_linearize_tiled(w, h->sm_count, s);
   else launch_linearize_scatter(w, h->sm_count, s);
   const size_t n = (size_t)w.n;
-  if (S_host) CK(cudaMemcpyAsync(S_host, w.S, sizeof(double) * n * n, cudaMemcpyDeviceToHost, s));
+  if (S_host) CK(cudaMemcpyAsync(S_host, w.S, sizeof(double) * s_doubles(w.n_cam), cudaMemcpyDeviceToHost, s));
   if (b_host) CK(cudaMemcpyAsync(b_host, w.b, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
   if (diagU_host) CK(cudaMemcpyAsync(diagU_host, w.diagU, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
   if (cost_host) CK(cudaMemcpyAsync(cost_host, w.cost_lin, sizeof(double), cudaMemcpyDeviceToHost, s));

@@ -16,7 +16,8 @@ struct Work {
   const unsigned char* fixed;         // [n_cam]
   double* pose[2];                    // [12 n_cam] each: R row-major (9) then t (3); double-buffered
   double* X[2];                       // [3 n_pt] each; double-buffered
-  double* S;                          // [n*n] row-major, lower triangle valid (reduction buffer)
+  double* S;                          // reduced camera matrix, block-packed lower triangle: 6x6 block
+                                      // (I,J), J <= I, at s_block_off(I,J), row-major inside (reduction buffer)
   double* b;                          // [n]
   double* diagU;                      // [n]   diag of the un-damped pose blocks
   double* cost_lin;                   // [1]   cost at the linearisation point (same buffer as S)
@@ -24,7 +25,23 @@ struct Work {
   double* dp;                         // [n]   camera step
   LmCtl* ctl;
   int world;                          // > 1: accept/reject runs as its own kernel after the all-reduce
+  long long* dbg;                     // optional clock64() trace (BA_DBG_TIMES=1), null otherwise
 };
+
+// phase timestamps of CTA 0 / thread 0 for latency hunting (store only: no load on the critical path)
+__device__ __forceinline__ void dbg_mark(const Work& w, int slot, int tag) {
+  if (w.dbg && blockIdx.x == 0 && threadIdx.x == 0 && slot < 2000) {
+    w.dbg[1 + 2 * slot] = tag;
+    w.dbg[2 + 2 * slot] = clock64();
+  }
+}
+
+__host__ __device__ __forceinline__ size_t s_block_off(int I, int J) {
+  return ((size_t)I * (I + 1) / 2 + J) * 36;
+}
+__host__ __device__ __forceinline__ size_t s_doubles(int n_cam) {
+  return (size_t)n_cam * (n_cam + 1) / 2 * 36;
+}
 
 // launch wrappers; every one returns the number of kernels it launched
 struct LmInit {

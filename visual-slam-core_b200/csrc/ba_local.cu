@@ -27,7 +27,7 @@ __global__ void k_init(Work w, const double* __restrict__ R_in, const double* __
     w.pose[1][i] = v;
   }
   for (int i = tid; i < 3 * w.n_pt; i += nth) w.X[0][i] = X_in[i];
-  long long nred = (long long)w.n * w.n + 2 * w.n + 1;   // S | b | diagU | cost_lin contiguous
+  long long nred = (long long)s_doubles(w.n_cam) + 2 * w.n + 1;   // S | b | diagU | cost_lin contiguous
   for (long long i = tid; i < nred; i += nth) w.S[i] = 0.0;
   for (int i = tid; i < w.n; i += nth) w.dp[i] = 0.0;
   if (tid == 0) {
@@ -55,7 +55,7 @@ __global__ void k_init(Work w, const double* __restrict__ R_in, const double* __
 
 int launch_init(const Work& w, const double* R_in, const double* t_in, const double* X_in,
                 const LmInit& p, cudaStream_t s) {
-  long long work = (long long)w.n * w.n + 3LL * w.n_pt;
+  long long work = (long long)s_doubles(w.n_cam) + 3LL * w.n_pt;
   int blocks = (int)((work + 255) / 256);
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -102,7 +102,6 @@ k_linearize_scatter(Work w) {
   const double lambda = ctl->lambda, delta = ctl->huber_delta;
   const double* __restrict__ pose = w.pose[cur];
   const double* __restrict__ X = w.X[cur];
-  const int n = w.n;
   double cost = 0.0;
 
   const int warp_global = blockIdx.x * kWarps + wid;
@@ -168,7 +167,7 @@ k_linearize_scatter(Work w) {
           T[3 * r + 2] = w0 * Vi[2] + w1 * Vi[4] + w2 * Vi[5];
         }
         if (activeA) {
-          double* Sd = w.S + (size_t)(6 * camA) * n + 6 * camA;
+          double* Sd = w.S + s_block_off(camA, camA);
           double au = ol.wu * ol.ru, av = ol.wv * ol.rv;
 #pragma unroll
           for (int r = 0; r < 6; ++r) {
@@ -178,7 +177,7 @@ k_linearize_scatter(Work w) {
               double u_rc = pur * ol.pu[c] + pvr * ol.pv[c];
               double s_rc = T[3 * r] * WA[3 * c] + T[3 * r + 1] * WA[3 * c + 1] +
                             T[3 * r + 2] * WA[3 * c + 2];
-              atomicAdd(Sd + (size_t)r * n + c, u_rc - s_rc);
+              atomicAdd(Sd + 6 * r + c, u_rc - s_rc);
             }
             atomicAdd(w.diagU + 6 * camA + r, pur * ol.pu[r] + pvr * ol.pv[r]);
             double br = -(au * ol.pu[r] + av * ol.pv[r]) + T[3 * r] * gl[0] +
@@ -220,14 +219,14 @@ k_linearize_scatter(Work w) {
             const int camB = sCam[wid][m];
             if (camB < 0 || camB > camA || baseB + m == iA) continue;
             const double* Wb = sW[wid][m];
-            double* Sd = w.S + (size_t)(6 * camA) * n + 6 * camB;
+            double* Sd = w.S + s_block_off(camA, camB);
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
               double b0 = Wb[3 * c], b1 = Wb[3 * c + 1], b2 = Wb[3 * c + 2];
 #pragma unroll
               for (int r = 0; r < 6; ++r) {
                 double s_rc = T[3 * r] * b0 + T[3 * r + 1] * b1 + T[3 * r + 2] * b2;
-                atomicAdd(Sd + (size_t)r * n + c, -s_rc);
+                atomicAdd(Sd + 6 * r + c, -s_rc);
               }
             }
           }
@@ -249,100 +248,348 @@ int launch_linearize_scatter(const Work& w, int sm_count, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------
-// reduced camera system: damping, Cholesky in shared memory, camera retraction
+// reduced camera system: damping, blocked (6x6) Cholesky in shared memory, camera retraction
+//
+// One CTA.  The matrix sits in shared memory in the same block-packed lower layout the
+// linearise kernels accumulate into, so the load is one coalesced copy.  Per block column K:
+//   (1) one thread factors the 6x6 diagonal block in registers and inverts the factor,
+//   (2) every row below (and the right-hand side, carried as one more row) is multiplied by
+//       L_KK^-T,
+//   (3) the trailing blocks get their rank-6 update, one thread per block row.
+// The forward substitution rides along with the factorisation (rhs row); the backward
+// substitution uses the stored inverse diagonal factors, two barriers per block.
 // ------------------------------------------------------------------------------------------
-static constexpr int kSolveThreads = 512;
-
-__device__ __forceinline__ int tri(int r, int c) { return ((r * (r + 1)) >> 1) + c; }
+static constexpr int kSolveThreads = 256;
+static constexpr size_t kSolveSmemMax = 227 * 1024 - 1024;   // opt-in limit minus static shared
 
 size_t rcs_cholesky_smem_bytes(int n) {
-  return sizeof(double) * ((size_t)(n + 1) * (n + 2) / 2 + n + 8);
+  const size_t nb = (size_t)n / 6;
+  return sizeof(double) * (nb * (nb + 1) / 2 * 37 + nb * 36 + 2 * (size_t)n + 8);
 }
-static constexpr size_t kSolveSmemMax = 227 * 1024 - 1024;   // opt-in limit minus static shared
 int rcs_cholesky_max_n() {
   int n = 6;
   while (rcs_cholesky_smem_bytes(n + 6) <= kSolveSmemMax) n += 6;
   return n;
 }
 
+// 1/sqrt(a) for the pivots: hardware approximation (MUFU.RSQ64H, ~2^-22) + two Newton steps.
+// No slow-path call, so nothing spills around it; a <= 0, inf or nan yield nan/inf and the
+// caller's pivot test rejects the step.
+__device__ __forceinline__ double fast_rsqrt(double a) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double e = fma(-a * r, r, 1.0);       // 1 - a r^2
+    r = fma(0.5 * r, e, r);
+  }
+  return r;
+}
+
+// Right-looking Cholesky of a 6x6 SPD block held in registers (lower triangle, row-major 6x6).
+// On return L holds the factor (upper part zero) and inv[k] = 1 / L[k][k].
+__device__ __forceinline__ bool chol6(double L[36], double inv[6]) {
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double akk = L[7 * k];
+    ok = ok && (akk > 0.0) && (akk < 1e300);
+    const double r = fast_rsqrt(akk);
+    inv[k] = r;
+    L[7 * k] = akk * r;
+#pragma unroll
+    for (int i = k + 1; i < 6; ++i) L[6 * i + k] *= r;
+#pragma unroll
+    for (int i = k + 1; i < 6; ++i)
+#pragma unroll
+      for (int j = k + 1; j <= i; ++j) L[6 * i + j] = fma(-L[6 * i + k], L[6 * j + k], L[6 * i + j]);
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = i + 1; j < 6; ++j) L[6 * i + j] = 0.0;
+  return ok;
+}
+
+// inverse of the lower-triangular 6x6 factor, column j by lane j (forward substitution on e_j)
+__device__ __forceinline__ void tri6_inv_col(const double* __restrict__ L, const double* __restrict__ dinv,
+                                             int j, double* __restrict__ Li) {
+  double col[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double a = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int q = 0; q < i; ++q) a = fma(-L[6 * i + q], col[q], a);
+    col[i] = (i < j) ? 0.0 : a * dinv[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) Li[6 * i + j] = col[i];
+}
+
+// shared-memory copy uses a 37-double block stride: with 36 (288 B) every block starts on one of
+// four bank groups and the per-block loads of the trailing update serialise 4- to 8-way
+static constexpr int kBS = 37;
+__device__ __forceinline__ int sblk(int I, int J) { return (I * (I + 1) / 2 + J) * kBS; }
+
 __global__ void __launch_bounds__(kSolveThreads, 1)
 k_rcs_cholesky(Work w) {
   extern __shared__ double sm[];
-  const int n = w.n;
-  double* A = sm;                                   // packed lower, rows 0..n (row n = rhs)
-  double* x = sm + (size_t)(n + 1) * (n + 2) / 2;   // solution
+  const int n = w.n, nb = w.n_cam;
+  const int nblk = nb * (nb + 1) / 2;
+  double* __restrict__ A = sm;                        // block-packed lower
+  double* __restrict__ Linv = A + (size_t)nblk * kBS; // inverse diagonal factors
+  double* __restrict__ y = Linv + (size_t)nb * 36;    // right-hand side -> L^-1 b
+  double* x = y + n;                                  // solution
   __shared__ int s_fail;
+  __shared__ double s_dinv[6];
   LmCtl* ctl = w.ctl;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
   const double lambda = ctl->lambda;
   const int cur = ctl->cur;
 
   if (tid == 0) {
-    s_fail = 0;
+    s_fail = (ctl->solve_fail != 0) ? 1 : 0;      // a linearise kernel may already have flagged the step
     if (ctl->iter == 0) {
       double c0 = *w.cost_lin;
       ctl->cost_cur = c0;
       ctl->cost_hist[0] = c0;
     }
   }
-  // load lower triangle (row per warp: contiguous in global and in packed storage), zero global
-  for (int r = wid; r < n; r += nw) {
-    double* Srow = w.S + (size_t)r * n;
-    const bool fx = w.fixed[r / 6] != 0;
-    for (int c = lane; c <= r; c += 32) {
-      double v = Srow[c];
-      Srow[c] = 0.0;
-      if (c == r) v = fx ? 1.0 : v + damp(w.diagU[r], lambda);
-      else if (fx || w.fixed[c / 6] != 0) v = 0.0;
-      A[tri(r, c)] = v;
+  dbg_mark(w, 0, 100);
+  // coalesced copy of the accumulated blocks (loads batched 8 deep); the global buffer is zeroed
+  // behind the copy for the next iteration
+  {
+    double* __restrict__ S = w.S;
+    const int total = nblk * 36;
+    for (int base = 0; base < total; base += 8 * nt) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * nt + tid;
+        v[u] = (i < total) ? S[i] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * nt + tid;
+        if (i < total) { A[(i / 36) * kBS + (i % 36)] = v[u]; S[i] = 0.0; }
+      }
     }
   }
+  double dU = 0.0;
+  if (tid < n) {
+    y[tid] = (w.fixed[tid / 6] != 0) ? 0.0 : w.b[tid];
+    dU = w.diagU[tid];
+  }
+  for (int c = tid + nt; c < n; c += nt) y[c] = (w.fixed[c / 6] != 0) ? 0.0 : w.b[c];
+  __syncthreads();
+  // damping of the pose blocks; fixed cameras -> identity rows/columns
   for (int c = tid; c < n; c += nt) {
-    double v = w.b[c];
+    const int cam = c / 6, r = c - 6 * cam;
+    double* D = A + sblk(cam, cam);
+    if (w.fixed[cam] != 0) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) D[6 * r + q] = (q == r) ? 1.0 : 0.0;
+    } else {
+      D[7 * r] += damp(c < nt ? dU : w.diagU[c], lambda);
+    }
+    w.diagU[c] = 0.0;
     w.b[c] = 0.0;
-    A[tri(n, c)] = (w.fixed[c / 6] != 0) ? 0.0 : v;
   }
-  __syncthreads();
-  for (int c = tid; c < n; c += nt) w.diagU[c] = 0.0;
   if (tid == 0) *w.cost_lin = 0.0;
+  __syncthreads();
+  dbg_mark(w, 1, 101);
 
-  // right-looking Cholesky on rows 0..n (the rhs row rides along: row n becomes y = L^-1 b)
-  for (int k = 0; k < n; ++k) {
-    const double akk = A[tri(k, k)];
-    if (!(akk > 0.0) || !isfinite(akk)) {
-      if (tid == 0) s_fail = 1;
-      break;                                   // uniform: every thread read the same value
+  // factor of the first diagonal block; later ones are factored by thread 0 right after it has
+  // updated them inside the trailing phase (look-ahead), off the other threads' critical path
+  double* Dinv = x;                     // x is free until the back substitution: 1/diag(L) lives there
+  auto factor_diag = [&](int K) {
+    double L[36], inv[6];
+    double* D = A + sblk(K, K);
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j < 6; ++j) L[6 * i + j] = (j <= i) ? D[6 * i + j] : 0.0;
+    if (!chol6(L, inv)) s_fail = 1;
+#pragma unroll
+    for (int q = 0; q < 36; ++q) D[q] = L[q];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) Dinv[6 * K + q] = inv[q];
+  };
+  if (tid == 0) factor_diag(0);
+  __syncthreads();
+
+  for (int K = 0; K < nb; ++K) {
+    if (K < 6) dbg_mark(w, 2 + 3 * K, 110);
+    if (s_fail) break;                    // uniform: written before the last barrier
+    const int m = nb - K - 1;
+    // (2) rows below + rhs row:  v <- v * L_KK^-T  (forward substitution along the row)
+    {
+      const double* __restrict__ Lk = A + sblk(K, K);
+      const double* __restrict__ di = Dinv + 6 * K;
+      for (int row = tid; row < 6 * m + 1; row += nt) {
+        double* v = (row < 6 * m) ? (A + sblk(K + 1 + row / 6, K) + 6 * (row % 6)) : (y + 6 * K);
+        double o[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) o[q] = v[q];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          o[q] *= di[q];
+#pragma unroll
+          for (int c = q + 1; c < 6; ++c) o[c] = fma(-o[q], Lk[6 * c + q], o[c]);
+        }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) v[q] = o[q];
+      }
     }
-    const double inv = 1.0 / sqrt(akk);
     __syncthreads();
-    for (int i = k + 1 + tid; i <= n; i += nt) A[tri(i, k)] *= inv;
-    if (tid == 0) A[tri(k, k)] = akk * inv;
-    __syncthreads();
-    for (int i = k + 1 + wid; i <= n; i += nw) {
-      const double lik = A[tri(i, k)];
-      const int jmax = (i < n) ? i : n - 1;
-      double* Ai = A + tri(i, 0);
-      for (int j = k + 1 + lane; j <= jmax; j += 32) Ai[j] -= lik * A[tri(j, k)];
+    if (K < 6) dbg_mark(w, 4 + 3 * K, 112);
+    // (3) trailing update of the blocks (I,J), K < J <= I, and of the rhs blocks
+    const int nblk_t = m * (m + 1) / 2;
+    if (nblk_t >= 48) {
+      // one thread per 6x6 block: 72 shared loads for 216 FMAs
+      for (int t = tid; t < nblk_t + m; t += nt) {
+        if (t < nblk_t) {
+          int I = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+          while (I * (I + 1) / 2 > t) --I;
+          while ((I + 1) * (I + 2) / 2 <= t) ++I;
+          const int J = t - I * (I + 1) / 2;
+          const double* __restrict__ Aik = A + sblk(K + 1 + I, K);
+          const double* __restrict__ Ajk = A + sblk(K + 1 + J, K);
+          double* __restrict__ Aij = A + sblk(K + 1 + I, K + 1 + J);
+          double bj[36];
+#pragma unroll
+          for (int q = 0; q < 36; ++q) bj[q] = Ajk[q];
+          // two block rows at a time: 12 independent accumulators cover the FP64 latency
+#pragma unroll
+          for (int r = 0; r < 6; r += 2) {
+            double a0[6], a1[6], c0[6], c1[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+              a0[q] = Aik[6 * r + q];
+              a1[q] = Aik[6 * r + 6 + q];
+              c0[q] = Aij[6 * r + q];
+              c1[q] = Aij[6 * r + 6 + q];
+            }
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+#pragma unroll
+              for (int c = 0; c < 6; ++c) {
+                c0[c] = fma(-a0[q], bj[6 * c + q], c0[c]);
+                c1[c] = fma(-a1[q], bj[6 * c + q], c1[c]);
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+              Aij[6 * r + q] = c0[q];
+              Aij[6 * r + 6 + q] = c1[q];
+            }
+          }
+          if (t == 0) factor_diag(K + 1);     // look-ahead: block (K+1,K+1) is final now
+        } else {
+          const int J = t - nblk_t;
+          const double* __restrict__ Ajk = A + sblk(K + 1 + J, K);
+          const double* yk = y + 6 * K;
+          double* yj = y + 6 * (K + 1 + J);
+#pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            double acc = yj[c];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) acc = fma(-yk[q], Ajk[6 * c + q], acc);
+            yj[c] = acc;
+          }
+        }
+      }
+    } else {
+      // few blocks left: one thread per block row keeps more lanes busy
+      for (int t = tid; t < 6 * nblk_t + m; t += nt) {
+        if (t < 6 * nblk_t) {
+          const int bi = t / 6, r = t - 6 * bi;
+          int I = (int)((sqrtf(8.0f * (float)bi + 1.0f) - 1.0f) * 0.5f);
+          while (I * (I + 1) / 2 > bi) --I;
+          while ((I + 1) * (I + 2) / 2 <= bi) ++I;
+          const int J = bi - I * (I + 1) / 2;
+          const double* __restrict__ Aik = A + sblk(K + 1 + I, K) + 6 * r;
+          const double* __restrict__ Ajk = A + sblk(K + 1 + J, K);
+          double* __restrict__ Aij = A + sblk(K + 1 + I, K + 1 + J) + 6 * r;
+          double a[6], acc[6];
+#pragma unroll
+          for (int q = 0; q < 6; ++q) { a[q] = Aik[q]; acc[q] = Aij[q]; }
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) acc[c] = fma(-a[q], Ajk[6 * c + q], acc[c]);
+          }
+#pragma unroll
+          for (int q = 0; q < 6; ++q) Aij[q] = acc[q];
+          if (t < 6) {                        // rows of block (K+1,K+1) = lanes 0..5 of warp 0: look-ahead
+            __syncwarp(0x3fu);
+            if (t == 0) factor_diag(K + 1);
+          }
+        } else {
+          const int J = t - 6 * nblk_t;
+          const double* __restrict__ Ajk = A + sblk(K + 1 + J, K);
+          const double* yk = y + 6 * K;
+          double* yj = y + 6 * (K + 1 + J);
+#pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            double acc = yj[c];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) acc = fma(-yk[q], Ajk[6 * c + q], acc);
+            yj[c] = acc;
+          }
+        }
+      }
     }
     __syncthreads();
   }
   __syncthreads();
+  dbg_mark(w, 20, 120);
   const bool fail = s_fail != 0;
   if (!fail) {
-    // back substitution L^T x = y, row-oriented: one barrier per unknown
-    double* y = A + tri(n, 0);
-    for (int k = n - 1; k >= 0; --k) {
-      const double xk = y[k] / A[tri(k, k)];
-      if (tid == 0) x[k] = xk;
-      const double* Lk = A + tri(k, 0);
-      for (int j = tid; j < k; j += nt) y[j] -= Lk[j] * xk;
-      __syncthreads();
+    // inverse diagonal factors for the back substitution, all blocks in parallel
+    for (int t = tid; t < 6 * nb; t += nt) {
+      const int K = t / 6;
+      tri6_inv_col(A + sblk(K, K), Dinv + 6 * K, t - 6 * K, Linv + K * 36);
     }
+    __syncthreads();
+    // backward substitution L^T x = y by ONE warp (warp-synchronous, no block barriers):
+    // x_K = L_KK^-T y_K by lanes 0..5, then y_J -= L_KJ^T x_K for J < K spread over the lanes
+    if (tid < 32) {
+      for (int K = nb - 1; K >= 0; --K) {
+        const double* __restrict__ Li = Linv + K * 36;
+        double xv = 0.0;
+        if (lane < 6) {
+          double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+            const double t2 = (r >= lane) ? Li[6 * r + lane] * y[6 * K + r] : 0.0;
+            if (r & 1) a1 += t2; else a0 += t2;
+          }
+          xv = a0 + a1;
+          x[6 * K + lane] = xv;
+        }
+        double xk[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) xk[r] = __shfl_sync(kFull, xv, r);
+        for (int t = lane; t < 6 * K; t += 32) {
+          const int J = t / 6, c = t - 6 * J;
+          const double* __restrict__ Akj = A + sblk(K, J);
+          double a0 = y[t], a1 = 0.0;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+            if (r & 1) a1 = fma(-Akj[6 * r + c], xk[r], a1); else a0 = fma(-Akj[6 * r + c], xk[r], a0);
+          }
+          y[t] = a0 + a1;
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
   } else {
     for (int c = tid; c < n; c += nt) x[c] = 0.0;
     __syncthreads();
   }
+  dbg_mark(w, 21, 130);
   bool bad = false;
   for (int c = tid; c < n; c += nt) {
     double v = x[c];
@@ -372,6 +619,7 @@ k_rcs_cholesky(Work w) {
 #pragma unroll
     for (int q = 0; q < 3; ++q) Pn[12 * c + 9 + q] = P[12 * c + 9 + q] + dt[q];
   }
+  dbg_mark(w, 22, 140);
 }
 
 int configure_kernels() {

@@ -234,7 +234,7 @@ class LocalBASolver:
         )
         n_cam, n_pt, n_obs = tens["R"].shape[0], tens["X"].shape[0], tens["oc"].shape[0]
         n = 6 * n_cam
-        S = np.zeros((n, n)); b = np.zeros(n); dU = np.zeros(n); cost = np.zeros(1)
+        Sp = np.zeros(n_cam * (n_cam + 1) // 2 * 36); b = np.zeros(n); dU = np.zeros(n); cost = np.zeros(1)
         stream = torch.cuda.current_stream(dev).cuda_stream
         torch.cuda.synchronize(dev)
         with self._lock:
@@ -242,6 +242,11 @@ class LocalBASolver:
                 self._h, n_cam, n_pt, n_obs, _dptr(intr), tens["R"].data_ptr(), tens["t"].data_ptr(),
                 tens["fixed"].data_ptr(), tens["X"].data_ptr(), tens["oc"].data_ptr(),
                 tens["op"].data_ptr(), tens["uv"].data_ptr(), tens["off"].data_ptr(), float(lam),
-                C.c_void_p(stream), _ptr(S), _ptr(b), _ptr(dU), _ptr(cost))
+                C.c_void_p(stream), _ptr(Sp), _ptr(b), _ptr(dU), _ptr(cost))
             _lib.check(self.lib, self._h, rc, "ba_debug_linearize")
+        S = np.zeros((n, n))                 # unpack the block-packed lower triangle
+        for i in range(n_cam):
+            for j in range(i + 1):
+                o = (i * (i + 1) // 2 + j) * 36
+                S[6 * i:6 * i + 6, 6 * j:6 * j + 6] = Sp[o:o + 36].reshape(6, 6)
         return S, b, dU, float(cost[0])
