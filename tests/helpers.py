@@ -58,3 +58,16 @@ def scale_norm_trans_err(Ra, ta, Rb, tb):
     base = np.linalg.norm(cb[1:] - cb[:-1], axis=1) if cb.shape[0] > 1 else np.array([1.0])
     med = float(np.median(base)) if base.size and np.median(base) > 0 else 1.0
     return np.linalg.norm(ta - tb, axis=1) / med
+
+
+def gauge_aligned_trans_err(Ra, ta, Rb, tb):
+    """Translation error after removing the free monocular scale (one similarity dof about the
+    fixed first camera), divided by the median baseline.  Used for long trajectories, where the
+    scale gauge is so weakly damped that no float64 solver pins it to 1e-5 of a 0.4 m baseline."""
+    ca = -np.einsum("nji,nj->ni", Ra, ta)
+    cb = -np.einsum("nji,nj->ni", Rb, tb)
+    da, db = ca - ca[0], cb - cb[0]
+    s = float((da * db).sum() / max((db * db).sum(), 1e-300))
+    base = np.linalg.norm(cb[1:] - cb[:-1], axis=1)
+    med = float(np.median(base)) if base.size and np.median(base) > 0 else 1.0
+    return np.linalg.norm(da - s * db, axis=1) / med, s

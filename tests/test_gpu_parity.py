@@ -10,7 +10,8 @@ import pytest
 from oracle import lm_oracle as O
 from visual_slam_core_b200 import B200Optimizer, LMConfig, LocalBASolver, packing, refgraph, synth
 
-from helpers import graph_from_golden, load_golden, rot_angle, scale_norm_trans_err, window_points
+from helpers import (gauge_aligned_trans_err, graph_from_golden, load_golden, rot_angle,
+                     scale_norm_trans_err, window_points)
 
 pytestmark = pytest.mark.gpu
 
@@ -34,23 +35,28 @@ def _oracle(p, cfg=None):
     return O.solve_local(p.intr, p.R, p.t, p.fixed, p.X, p.obs_cam, p.obs_pt, p.obs_uv, prm)
 
 
-def _check(p, res, ref):
+def _check(p, res, ref, gauge_free=False):
     np.testing.assert_array_equal(res.accepted, ref.accepted)
     np.testing.assert_allclose(res.lambda_hist, ref.lambda_hist, rtol=1e-12)
     np.testing.assert_allclose(res.cost_hist, ref.cost_hist, rtol=COST_RTOL)
     np.testing.assert_allclose(res.cand_cost_hist, ref.cand_cost_hist, rtol=COST_RTOL)
     ang = rot_angle(res.R, ref.R)
     terr = scale_norm_trans_err(res.R, res.t, ref.R, ref.t)
+    if gauge_free:
+        # long trajectory: compare after removing the free monocular scale (see helpers)
+        terr_raw = terr
+        terr, scale = gauge_aligned_trans_err(res.R, res.t, ref.R, ref.t)
+        assert abs(scale - 1.0) < 1e-6 and terr_raw.max() < 1e-3, (scale, terr_raw.max())
     assert ang.max() <= ROT_TOL, ang.max()
     assert terr.max() <= TRANS_TOL, terr.max()
     np.testing.assert_array_equal(res.flags, ref.flags)
     # points: compared where it matters, in the image (a weakly constrained depth can differ by
     # metres between two float64 implementations while reprojecting to the same pixel)
-    ru_a, rv_a = O.residuals(p.intr, ref.R, ref.t, res.X, p.obs_cam, p.obs_pt, p.obs_uv)
+    ru_a, rv_a = O.residuals(p.intr, res.R, res.t, res.X, p.obs_cam, p.obs_pt, p.obs_uv)
     ru_b, rv_b = O.residuals(p.intr, ref.R, ref.t, ref.X, p.obs_cam, p.obs_pt, p.obs_uv)
     reproj = max(np.abs(ru_a - ru_b).max(), np.abs(rv_a - rv_b).max()) if p.n_obs else 0.0
-    assert reproj <= 1e-3, reproj
-    assert np.mean(np.abs(res.X - ref.X).max(axis=1) > 1e-4) < 0.02
+    assert reproj <= (5e-2 if gauge_free else 1e-3), reproj
+    assert np.mean(np.abs(res.X - ref.X).max(axis=1) > (1e-3 if gauge_free else 1e-4)) < 0.02
     return dict(reproj_px=float(reproj),cost_rel=float(np.max(np.abs(res.cost_hist - ref.cost_hist) / ref.cost_hist)),
                 rot=float(ang.max()), trans=float(terr.max()),
                 x_max=float(np.abs(res.X - ref.X).max()))
@@ -96,6 +102,40 @@ def test_reduced_camera_system_matches_oracle(name, seed, lam, schur):
     np.testing.assert_allclose(b[free], b_ref[free], rtol=1e-9, atol=1e-9 * np.abs(b_ref).max())
     np.testing.assert_allclose(dU[free], dU_ref[free], rtol=1e-12)
     assert cost == pytest.approx(lin["cost"], rel=1e-13)
+
+
+@pytest.mark.parametrize("schur", ["tiled", "scatter"])
+@pytest.mark.parametrize("name,seed", [("T3", 1), ("T4", 2)])
+def test_large_window_sparse_pcg_matches_oracle(name, seed, schur):
+    """More cameras than the shared-memory Cholesky holds: block-sparse S + block-Jacobi PCG on the
+    GPU vs the oracle's sparse direct solve."""
+    p = synth.make_problem(name, seed=seed)
+    s = LocalBASolver(LMConfig(schur=schur, pcg_tol=1e-12, pcg_max_iter=3000))
+    res = s.solve_local(p.intr, p.R, p.t, p.fixed, p.X, p.obs_cam, p.obs_pt, p.obs_uv, p.pt_offsets)
+    s.close()
+    ref = _oracle(p)
+    assert res.solve_fail.sum() == 0
+    info = _check(p, res, ref, gauge_free=p.n_cam > 100)
+    print(f"\n[{name} seed {seed} {schur} pcg] achieved: {info} pcg iterations {res.pcg_iters.tolist()}")
+
+
+def test_unsorted_points_use_the_scatter_fallback():
+    """Points in random order: chunks span more cameras than the tiled kernel's window and go
+    through its per-point scatter fallback; the result must not change."""
+    p = synth.make_problem("T4", seed=2, sort_points=False)
+    s = LocalBASolver(LMConfig(pcg_tol=1e-12, pcg_max_iter=3000))
+    res = s.solve_local(p.intr, p.R, p.t, p.fixed, p.X, p.obs_cam, p.obs_pt, p.obs_uv, p.pt_offsets)
+    s.close()
+    _check(p, res, _oracle(p), gauge_free=True)
+
+
+def test_cholesky_refuses_windows_it_cannot_hold():
+    from visual_slam_core_b200._lib import B200BAError
+    p = synth.make_problem("T3", seed=1)
+    s = LocalBASolver(LMConfig(solver="cholesky"))
+    with pytest.raises(B200BAError):
+        s.solve_local(p.intr, p.R, p.t, p.fixed, p.X, p.obs_cam, p.obs_pt, p.obs_uv, p.pt_offsets)
+    s.close()
 
 
 def test_edge_cases_zero_obs_points_many_obs_points_extra_fixed(solver):

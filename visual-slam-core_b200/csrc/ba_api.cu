@@ -70,6 +70,9 @@ struct ba_handle {
   std::string err;
   // workspace
   DevBuf pose0, pose1, X0, X1, red, dp, ctl, cand, dbg;
+  // sparse path: structure + PCG workspace
+  DevBuf bits, wpre, row_nnz, row_ptr, col_idx, tpos, pcg;
+  int* h_nnzb = nullptr;          // pinned
   // staging for the host-pointer API
   DevBuf d_R, d_t, d_fixed, d_X, d_ocam, d_opt, d_ouv, d_off, d_flags, d_hist, d_acc, d_foff;
   LmCtl* h_ctl = nullptr;         // pinned
@@ -168,7 +171,7 @@ extern "C" void ba_default_params(ba_params* p) {
   p->max_iter = 10;
   p->solver_kind = BA_SOLVER_AUTO;
   p->schur_kind = BA_SCHUR_AUTO;
-  p->pcg_max_iter = 200;
+  p->pcg_max_iter = 500;
   p->pcg_tol = 1e-10;
   p->use_graph = 1;
   p->profile = 0;
@@ -207,7 +210,8 @@ extern "C" int ba_create(const ba_params* params, int device, ba_handle** out) {
   }
   if ((ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (ce = cudaEventCreate(&h->ev0)) != cudaSuccess || (ce = cudaEventCreate(&h->ev1)) != cudaSuccess ||
-      (ce = cudaMallocHost((void**)&h->h_ctl, sizeof(LmCtl))) != cudaSuccess) {
+      (ce = cudaMallocHost((void**)&h->h_ctl, sizeof(LmCtl))) != cudaSuccess ||
+      (ce = cudaMallocHost((void**)&h->h_nnzb, sizeof(int))) != cudaSuccess) {
     g_create_err = std::string("handle resources: ") + cudaGetErrorString(ce);
     delete h;
     return BA_ERR_CUDA;
@@ -228,11 +232,13 @@ extern "C" int ba_destroy(ba_handle* h) {
   if (h->graph) cudaGraphExecDestroy(h->graph);
   DevBuf* bufs[] = {&h->pose0, &h->pose1, &h->X0, &h->X1, &h->red, &h->dp, &h->ctl, &h->cand,
                     &h->d_R, &h->d_t, &h->d_fixed, &h->d_X, &h->d_ocam, &h->d_opt, &h->d_ouv,
-                    &h->d_off, &h->d_flags, &h->d_hist, &h->d_acc, &h->d_foff, &h->dbg};
+                    &h->d_off, &h->d_flags, &h->d_hist, &h->d_acc, &h->d_foff, &h->dbg,
+                    &h->bits, &h->wpre, &h->row_nnz, &h->row_ptr, &h->col_idx, &h->tpos, &h->pcg};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  if (h->h_nnzb) cudaFreeHost(h->h_nnzb);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -243,16 +249,22 @@ extern "C" int ba_destroy(ba_handle* h) {
 // ------------------------------------------------------------------------------------------
 // local BA
 // ------------------------------------------------------------------------------------------
+static bool want_sparse(const ba_handle* h, int n_cam) {
+  return h->prm.solver_kind == BA_SOLVER_PCG || 6 * n_cam > rcs_cholesky_max_n();
+}
+
+// workspace + kernel view.  sparse = block-sparse S + PCG (needs one host sync for the block count)
 static int make_work(ba_handle* h, int n_cam, int n_pt, int n_obs, const double intr[4],
                      const uint8_t* fixed, const int32_t* obs_cam, const int32_t* obs_pt,
-                     const float* obs_uv, const int32_t* pt_off, Work& w) {
+                     const float* obs_uv, const int32_t* pt_off, Work& w, bool sparse = false,
+                     cudaStream_t s = nullptr) {
   const int n = 6 * n_cam;
   int rc;
+  memset(&w, 0, sizeof(w));
   if ((rc = ensure(h, h->pose0, sizeof(double) * 12 * (size_t)n_cam))) return rc;
   if ((rc = ensure(h, h->pose1, sizeof(double) * 12 * (size_t)n_cam))) return rc;
   if ((rc = ensure(h, h->X0, sizeof(double) * 3 * (size_t)(n_pt + 1)))) return rc;
   if ((rc = ensure(h, h->X1, sizeof(double) * 3 * (size_t)(n_pt + 1)))) return rc;
-  if ((rc = ensure(h, h->red, sizeof(double) * (s_doubles(n_cam) + 2 * (size_t)n + 1)))) return rc;
   if ((rc = ensure(h, h->dp, sizeof(double) * (size_t)(n + 1)))) return rc;
   if ((rc = ensure(h, h->ctl, sizeof(LmCtl)))) return rc;
   if ((rc = ensure(h, h->cand, sizeof(double) * 2))) return rc;
@@ -261,10 +273,6 @@ static int make_work(ba_handle* h, int n_cam, int n_pt, int n_obs, const double 
   w.obs_cam = obs_cam; w.obs_pt = obs_pt; w.obs_uv = obs_uv; w.pt_off = pt_off; w.fixed = fixed;
   w.pose[0] = (double*)h->pose0.p; w.pose[1] = (double*)h->pose1.p;
   w.X[0] = (double*)h->X0.p; w.X[1] = (double*)h->X1.p;
-  w.S = (double*)h->red.p;
-  w.b = w.S + s_doubles(n_cam);
-  w.diagU = w.b + n;
-  w.cost_lin = w.diagU + n;
   w.cost_cand = (double*)h->cand.p;
   w.dp = (double*)h->dp.p;
   w.ctl = (LmCtl*)h->ctl.p;
@@ -276,6 +284,50 @@ static int make_work(ba_handle* h, int n_cam, int n_pt, int n_obs, const double 
     if ((rc = ensure(h, h->dbg, sizeof(long long) * 4096))) return rc;
     w.dbg = (long long*)h->dbg.p;
   }
+  if (!sparse) {
+    w.s_len = s_doubles(n_cam);
+  } else {
+    // symbolic phase: co-visibility bitmap -> block-CSR structure
+    const int W = (n_cam + 31) / 32;
+    if ((rc = ensure(h, h->bits, sizeof(unsigned) * (size_t)n_cam * W))) return rc;
+    if ((rc = ensure(h, h->wpre, sizeof(int) * (size_t)n_cam * W))) return rc;
+    if ((rc = ensure(h, h->row_nnz, sizeof(int) * (size_t)(n_cam + 1)))) return rc;
+    if ((rc = ensure(h, h->row_ptr, sizeof(int) * (size_t)(n_cam + 1)))) return rc;
+    w.bsr_W = W;
+    w.bsr_bits = (const unsigned*)h->bits.p;
+    w.bsr_wpre = (const int*)h->wpre.p;
+    w.bsr_row_ptr = (const int*)h->row_ptr.p;
+    launch_symbolic(w, (unsigned*)h->bits.p, (int*)h->wpre.p, (int*)h->row_nnz.p, (int*)h->row_ptr.p, s);
+    CK(cudaMemcpyAsync(h->h_nnzb, (int*)h->row_ptr.p + n_cam, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int nnzb = *h->h_nnzb;
+    if (nnzb <= 0) { h->err = "symbolic phase produced no blocks"; return BA_ERR_CUDA; }
+    if ((rc = ensure(h, h->col_idx, sizeof(int) * (size_t)nnzb))) return rc;
+    if ((rc = ensure(h, h->tpos, sizeof(int) * (size_t)nnzb))) return rc;
+    w.nnzb = nnzb;
+    w.bsr_col = (const int*)h->col_idx.p;
+    w.bsr_tpos = (const int*)h->tpos.p;
+    launch_symbolic_fill(w, (int*)h->col_idx.p, (int*)h->tpos.p, s);
+    w.s_len = (size_t)nnzb * 36;
+    // PCG workspace: r, z, p0, p1, Ap (n each), Minv (36 n_cam), accumulators
+    w.pcg_max_iter = h->prm.pcg_max_iter > 0 ? h->prm.pcg_max_iter : 200;
+    w.pcg_tol = h->prm.pcg_tol > 0 ? h->prm.pcg_tol : 1e-10;
+    const size_t nacc = 3 * (size_t)(w.pcg_max_iter + 2);
+    if ((rc = ensure(h, h->pcg, sizeof(double) * (5 * (size_t)n + 36 * (size_t)n_cam + nacc + 8)))) return rc;
+    double* q = (double*)h->pcg.p;
+    w.pcg_r = q; q += n;
+    w.pcg_z = q; q += n;
+    w.pcg_p[0] = q; q += n;
+    w.pcg_p[1] = q; q += n;
+    w.pcg_Ap = q; q += n;
+    w.pcg_Minv = q; q += 36 * (size_t)n_cam;
+    w.pcg_acc = q;
+  }
+  if ((rc = ensure(h, h->red, sizeof(double) * (w.s_len + 2 * (size_t)n + 1)))) return rc;
+  w.S = (double*)h->red.p;
+  w.b = w.S + w.s_len;
+  w.diagU = w.b + n;
+  w.cost_lin = w.diagU + n;
   return BA_OK;
 }
 
@@ -289,7 +341,9 @@ static int pick_schur(const ba_handle* h, const Work& w) {
 // enqueue the LM iterations (no init / finalize); returns kernels launched or < 0
 static int enqueue_lm_loop(ba_handle* h, const Work& w, int schur, cudaStream_t s) {
   int launches = 0;
-  const size_t nred = s_doubles(w.n_cam) + 2 * (size_t)w.n + 1;
+  const size_t nred = w.s_len + 2 * (size_t)w.n + 1;
+  const bool sparse = w.bsr_bits != nullptr;
+  const int pcg_grid = sparse ? pcg_grid_size(w.n_cam, h->sm_count) : 0;
   for (int it = 0; it < h->prm.max_iter; ++it) {
     prof_mark(h, TAG_LIN, s);
     launches += (schur == BA_SCHUR_TILED) ? launch_linearize_tiled(w, h->sm_count, s)
@@ -300,7 +354,12 @@ static int enqueue_lm_loop(ba_handle* h, const Work& w, int schur, cudaStream_t 
       if (r != 0) { h->err = std::string("ncclAllReduce(S): ") + (g_nccl.errstr ? g_nccl.errstr(r) : "?"); return BA_ERR_NCCL; }
     }
     prof_mark(h, TAG_SOLVE, s);
-    launches += launch_rcs_cholesky(w, s);
+    if (sparse) {
+      if (launch_rcs_pcg(w, pcg_grid, s) < 0) { h->err = std::string("cooperative PCG launch: ") + cudaGetErrorString(cudaGetLastError()); return BA_ERR_CUDA; }
+      launches += 1;
+    } else {
+      launches += launch_rcs_cholesky(w, s);
+    }
     prof_mark(h, TAG_BACK, s);
     launches += launch_backsub(w, h->sm_count, s);
     if (h->world > 1) {
@@ -361,12 +420,13 @@ extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t
     return BA_ERR_INVALID;
   CK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
-  if (6 * n_cam > rcs_cholesky_max_n() || h->prm.solver_kind == BA_SOLVER_PCG) {
-    h->err = "reduced camera system larger than the in-shared-memory Cholesky (PCG path not built yet)";
+  if (h->prm.solver_kind == BA_SOLVER_CHOLESKY && 6 * n_cam > rcs_cholesky_max_n()) {
+    h->err = "reduced camera system larger than the in-shared-memory Cholesky; use solver auto or pcg";
     return BA_ERR_TOO_LARGE;
   }
+  const bool sparse = want_sparse(h, n_cam);
   Work w;
-  int rc = make_work(h, n_cam, n_pt, n_obs, intr, cam_fixed, obs_cam, obs_pt, obs_uv, pt_offsets, w);
+  int rc = make_work(h, n_cam, n_pt, n_obs, intr, cam_fixed, obs_cam, obs_pt, obs_uv, pt_offsets, w, sparse, s);
   if (rc) return rc;
   const int schur = pick_schur(h, w);
   LmInit li{h->prm.lambda0, h->prm.huber_delta, h->prm.chi2_thr, h->prm.lambda_up,
@@ -379,7 +439,7 @@ extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t
   prof_mark(h, TAG_OTHER, s);
   launches += launch_init(w, cam_R, cam_t, X, li, s);
 
-  bool use_graph = h->prm.use_graph != 0 && h->prm.max_iter > 0 && !h->prm.profile;
+  bool use_graph = h->prm.use_graph != 0 && h->prm.max_iter > 0 && !h->prm.profile && !sparse;
   if (use_graph) {
     ba_handle::GraphKey key;
     key.n_cam = n_cam; key.n_pt = n_pt; key.n_obs = n_obs; key.max_iter = h->prm.max_iter;
@@ -421,6 +481,7 @@ extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     if (h->prm.profile) prof_collect(h);
     fill_report(h, h->h_ctl, report, BA_OK, ms, launches);
+    report->solver_used = sparse ? BA_SOLVER_PCG : BA_SOLVER_CHOLESKY;
     dump_dbg(h);
   }
   return BA_OK;
@@ -477,6 +538,7 @@ extern "C" int ba_solve_local_host(ba_handle* h, int32_t n_cam, int32_t n_pt, in
     int launches = 2 + h->prm.max_iter * (h->world > 1 ? 4 : 3);
     if (h->prm.profile) prof_collect(h);
     fill_report(h, h->h_ctl, report, BA_OK, ms, launches);
+    report->solver_used = want_sparse(h, n_cam) ? BA_SOLVER_PCG : BA_SOLVER_CHOLESKY;
   }
   return BA_OK;
 }
@@ -511,6 +573,7 @@ extern "C" int ba_debug_linearize(ba_handle* h, int32_t n_cam, int32_t n_pt, int
   if (!h || n_cam <= 0) return BA_ERR_INVALID;
   CK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
+  if (6 * n_cam > rcs_cholesky_max_n()) { h->err = "ba_debug_linearize: dense layout only"; return BA_ERR_TOO_LARGE; }
   Work w;
   int rc = make_work(h, n_cam, n_pt, n_obs, intr, cam_fixed, obs_cam, obs_pt, obs_uv, pt_offsets, w);
   if (rc) return rc;

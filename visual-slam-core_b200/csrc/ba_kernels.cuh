@@ -26,6 +26,18 @@ struct Work {
   LmCtl* ctl;
   int world;                          // > 1: accept/reject runs as its own kernel after the all-reduce
   long long* dbg;                     // optional clock64() trace (BA_DBG_TIMES=1), null otherwise
+  // block-sparse reduced camera matrix (large windows); all null / 0 for the dense packed layout
+  const unsigned* bsr_bits;           // [n_cam * bsr_W] structure bitmap (symmetric, diagonal set)
+  const int* bsr_wpre;                // [n_cam * bsr_W] set bits before each word of its row
+  const int* bsr_row_ptr;             // [n_cam + 1]
+  const int* bsr_col;                 // [nnzb]
+  const int* bsr_tpos;                // [nnzb] position of the transposed block
+  int bsr_W, nnzb;
+  size_t s_len;                       // doubles in S (dense packed: n_cam(n_cam+1)/2*36, sparse: nnzb*36)
+  // block-Jacobi PCG workspace (sparse path)
+  double* pcg_r; double* pcg_z; double* pcg_p[2]; double* pcg_Ap; double* pcg_Minv; double* pcg_acc;
+  int pcg_max_iter;
+  double pcg_tol;
 };
 
 // phase timestamps of CTA 0 / thread 0 for latency hunting (store only: no load on the critical path)
@@ -43,6 +55,19 @@ __host__ __device__ __forceinline__ size_t s_doubles(int n_cam) {
   return (size_t)n_cam * (n_cam + 1) / 2 * 36;
 }
 
+// position of block (a, b) in the block-sparse layout (the block must exist)
+__device__ __forceinline__ int bsr_find(const Work& w, int a, int b) {
+  const int word = b >> 5;
+  const size_t at = (size_t)a * w.bsr_W + word;
+  const unsigned m = __ldg(w.bsr_bits + at);
+  return __ldg(w.bsr_row_ptr + a) + __ldg(w.bsr_wpre + at) + __popc(m & ((1u << (b & 31)) - 1u));
+}
+// where block (a, b), a >= b, of the reduced camera matrix is accumulated
+__device__ __forceinline__ double* s_block_ptr(const Work& w, int a, int b) {
+  if (w.bsr_bits == nullptr) return w.S + s_block_off(a, b);
+  return w.S + (size_t)bsr_find(w, a, b) * 36;
+}
+
 // launch wrappers; every one returns the number of kernels it launched
 struct LmInit {
   double lambda0, huber_delta, chi2_thr, lambda_up, lambda_down, lambda_min, lambda_max, accept_rtol;
@@ -52,6 +77,10 @@ int launch_init(const Work& w, const double* R_in, const double* t_in, const dou
 int launch_linearize_scatter(const Work& w, int sm_count, cudaStream_t s);
 int launch_linearize_tiled(const Work& w, int sm_count, cudaStream_t s);
 int launch_rcs_cholesky(const Work& w, cudaStream_t s);
+int launch_symbolic(const Work& w, unsigned* bits, int* wpre, int* row_nnz, int* row_ptr, cudaStream_t s);
+int launch_symbolic_fill(const Work& w, int* col_idx, int* tpos, cudaStream_t s);
+int pcg_grid_size(int n_cam, int sm_count);
+int launch_rcs_pcg(const Work& w, int grid, cudaStream_t s);
 int launch_backsub(const Work& w, int sm_count, cudaStream_t s);
 int launch_accept(const Work& w, cudaStream_t s);
 int launch_finalize(const Work& w, double* R_out, double* t_out, double* X_out,

@@ -7,6 +7,7 @@
 //   k_backsub       point back-substitution, candidate state, candidate cost, accept/reject
 // All LM control state lives in device memory (LmCtl), so the loop never syncs with the host.
 #include "ba_kernels.cuh"
+#include "ba_scatter.cuh"
 
 namespace ba {
 
@@ -27,7 +28,7 @@ __global__ void k_init(Work w, const double* __restrict__ R_in, const double* __
     w.pose[1][i] = v;
   }
   for (int i = tid; i < 3 * w.n_pt; i += nth) w.X[0][i] = X_in[i];
-  long long nred = (long long)s_doubles(w.n_cam) + 2 * w.n + 1;   // S | b | diagU | cost_lin contiguous
+  long long nred = (long long)w.s_len + 2 * w.n + 1;   // S | b | diagU | cost_lin contiguous
   for (long long i = tid; i < nred; i += nth) w.S[i] = 0.0;
   for (int i = tid; i < w.n; i += nth) w.dp[i] = 0.0;
   if (tid == 0) {
@@ -55,7 +56,7 @@ __global__ void k_init(Work w, const double* __restrict__ R_in, const double* __
 
 int launch_init(const Work& w, const double* R_in, const double* t_in, const double* X_in,
                 const LmInit& p, cudaStream_t s) {
-  long long work = (long long)s_doubles(w.n_cam) + 3LL * w.n_pt;
+  long long work = (long long)w.s_len + 3LL * w.n_pt;
   int blocks = (int)((work + 255) / 256);
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -69,29 +70,6 @@ int launch_init(const Work& w, const double* R_in, const double* t_in, const dou
 // Works for any window size and any per-point observation count; used directly for
 // windows the tiled kernel does not cover and as an independent cross-check of it.
 // ------------------------------------------------------------------------------------------
-struct ObsIn {
-  int cam;
-  double u, v;
-};
-
-__device__ __forceinline__ ObsIn load_obs(const Work& w, int o) {
-  ObsIn r;
-  r.cam = __ldg(w.obs_cam + o);
-  float2 uv = __ldg(reinterpret_cast<const float2*>(w.obs_uv) + o);
-  r.u = (double)uv.x;
-  r.v = (double)uv.y;
-  return r;
-}
-
-__device__ __forceinline__ void make_W(const ObsLin& o, double W[18]) {
-#pragma unroll
-  for (int r = 0; r < 6; ++r) {
-    double a = o.wu * o.pu[r], b = o.wv * o.pv[r];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) W[3 * r + q] = a * o.lu[q] + b * o.lv[q];
-  }
-}
-
 __global__ void __launch_bounds__(kThreads, 1)
 k_linearize_scatter(Work w) {
   __shared__ double sW[kWarps][32][19];   // per-warp staging of W_ij (6x3), padded
@@ -103,145 +81,17 @@ k_linearize_scatter(Work w) {
   const double* __restrict__ pose = w.pose[cur];
   const double* __restrict__ X = w.X[cur];
   double cost = 0.0;
-
   const int warp_global = blockIdx.x * kWarps + wid;
   const int warp_total = gridDim.x * kWarps;
-  for (int j = warp_global; j < w.n_pt; j += warp_total) {
-    const int o0 = __ldg(w.pt_off + j);
-    const int k = __ldg(w.pt_off + j + 1) - o0;
-    if (k <= 0) continue;
-    const double X0 = X[3 * j], X1 = X[3 * j + 1], X2 = X[3 * j + 2];
-
-    // ---- pass 1: V_j, g_l,j, cost -------------------------------------------------------
-    double V[6] = {0, 0, 0, 0, 0, 0}, gl[3] = {0, 0, 0};
-    for (int base = 0; base < k; base += 32) {
-      int i = base + lane;
-      if (i < k) {
-        ObsIn in = load_obs(w, o0 + i);
-        ObsLin ol;
-        linearize_obs<false>(w.K, pose + 12 * in.cam, pose + 12 * in.cam + 9, X0, X1, X2, in.u,
-                             in.v, delta, ol);
-        V[0] += ol.wu * ol.lu[0] * ol.lu[0] + ol.wv * ol.lv[0] * ol.lv[0];
-        V[1] += ol.wu * ol.lu[0] * ol.lu[1] + ol.wv * ol.lv[0] * ol.lv[1];
-        V[2] += ol.wu * ol.lu[0] * ol.lu[2] + ol.wv * ol.lv[0] * ol.lv[2];
-        V[3] += ol.wu * ol.lu[1] * ol.lu[1] + ol.wv * ol.lv[1] * ol.lv[1];
-        V[4] += ol.wu * ol.lu[1] * ol.lu[2] + ol.wv * ol.lv[1] * ol.lv[2];
-        V[5] += ol.wu * ol.lu[2] * ol.lu[2] + ol.wv * ol.lv[2] * ol.lv[2];
-        double au = ol.wu * ol.ru, av = ol.wv * ol.rv;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) gl[q] += au * ol.lu[q] + av * ol.lv[q];
-        cost += huber_rho(ol.ru, delta) + huber_rho(ol.rv, delta);
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 6; ++q) V[q] = warp_sum(V[q]);
-#pragma unroll
-    for (int q = 0; q < 3; ++q) gl[q] = warp_sum(gl[q]);
-    V[0] += damp(V[0], lambda);
-    V[3] += damp(V[3], lambda);
-    V[5] += damp(V[5], lambda);
-    double Vi[6];
-    sym3_inverse(V, Vi);
-
-    // ---- pass 2: pose blocks, Schur complement ------------------------------------------
-    for (int baseA = 0; baseA < k; baseA += 32) {
-      const int iA = baseA + lane;
-      const bool validA = iA < k;
-      int camA = -1;
-      double WA[18], T[18];
-      bool activeA = false;
-      if (validA) {
-        ObsIn in = load_obs(w, o0 + iA);
-        camA = in.cam;
-        activeA = (w.fixed[camA] == 0);
-        ObsLin ol;
-        linearize_obs<true>(w.K, pose + 12 * camA, pose + 12 * camA + 9, X0, X1, X2, in.u, in.v,
-                            delta, ol);
-        make_W(ol, WA);
-        // T = W V^-1  (6x3)
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {
-          double w0 = WA[3 * r], w1 = WA[3 * r + 1], w2 = WA[3 * r + 2];
-          T[3 * r + 0] = w0 * Vi[0] + w1 * Vi[1] + w2 * Vi[2];
-          T[3 * r + 1] = w0 * Vi[1] + w1 * Vi[3] + w2 * Vi[4];
-          T[3 * r + 2] = w0 * Vi[2] + w1 * Vi[4] + w2 * Vi[5];
-        }
-        if (activeA) {
-          double* Sd = w.S + s_block_off(camA, camA);
-          double au = ol.wu * ol.ru, av = ol.wv * ol.rv;
-#pragma unroll
-          for (int r = 0; r < 6; ++r) {
-            double pur = ol.wu * ol.pu[r], pvr = ol.wv * ol.pv[r];
-#pragma unroll
-            for (int c = 0; c <= r; ++c) {
-              double u_rc = pur * ol.pu[c] + pvr * ol.pv[c];
-              double s_rc = T[3 * r] * WA[3 * c] + T[3 * r + 1] * WA[3 * c + 1] +
-                            T[3 * r + 2] * WA[3 * c + 2];
-              atomicAdd(Sd + 6 * r + c, u_rc - s_rc);
-            }
-            atomicAdd(w.diagU + 6 * camA + r, pur * ol.pu[r] + pvr * ol.pv[r]);
-            double br = -(au * ol.pu[r] + av * ol.pv[r]) + T[3 * r] * gl[0] +
-                        T[3 * r + 1] * gl[1] + T[3 * r + 2] * gl[2];
-            atomicAdd(w.b + 6 * camA + r, br);
-          }
-        }
-      }
-      for (int baseB = 0; baseB < k; baseB += 32) {
-        const int iB = baseB + lane;
-        // stage W of chunk B
-        if (baseB == baseA) {
-          sCam[wid][lane] = activeA ? camA : -1;
-          if (activeA) {
-#pragma unroll
-            for (int q = 0; q < 18; ++q) sW[wid][lane][q] = WA[q];
-          }
-        } else {
-          int camB = -1;
-          if (iB < k) {
-            ObsIn in = load_obs(w, o0 + iB);
-            if (w.fixed[in.cam] == 0) {
-              camB = in.cam;
-              ObsLin ol;
-              linearize_obs<true>(w.K, pose + 12 * camB, pose + 12 * camB + 9, X0, X1, X2, in.u,
-                                  in.v, delta, ol);
-              double WB[18];
-              make_W(ol, WB);
-#pragma unroll
-              for (int q = 0; q < 18; ++q) sW[wid][lane][q] = WB[q];
-            }
-          }
-          sCam[wid][lane] = camB;
-        }
-        __syncwarp();
-        const int mB = min(32, k - baseB);
-        if (activeA) {
-          for (int m = 0; m < mB; ++m) {
-            const int camB = sCam[wid][m];
-            if (camB < 0 || camB > camA || baseB + m == iA) continue;
-            const double* Wb = sW[wid][m];
-            double* Sd = w.S + s_block_off(camA, camB);
-#pragma unroll
-            for (int c = 0; c < 6; ++c) {
-              double b0 = Wb[3 * c], b1 = Wb[3 * c + 1], b2 = Wb[3 * c + 2];
-#pragma unroll
-              for (int r = 0; r < 6; ++r) {
-                double s_rc = T[3 * r] * b0 + T[3 * r + 1] * b1 + T[3 * r + 2] * b2;
-                atomicAdd(Sd + 6 * r + c, -s_rc);
-              }
-            }
-          }
-        }
-        __syncwarp();
-      }
-    }
-  }
+  for (int j = warp_global; j < w.n_pt; j += warp_total)
+    scatter_point(w, j, lane, lambda, delta, pose, X, sW[wid], sCam[wid], cost);
   cost = warp_sum(cost);
   if (lane == 0 && cost != 0.0) atomicAdd(w.cost_lin, cost);
 }
 
 int launch_linearize_scatter(const Work& w, int sm_count, cudaStream_t s) {
   int blocks = (w.n_pt + kWarps - 1) / kWarps;
-  if (blocks > sm_count) blocks = sm_count;
+  if (blocks > 2 * sm_count) blocks = 2 * sm_count;
   if (blocks < 1) blocks = 1;
   k_linearize_scatter<<<blocks, kThreads, 0, s>>>(w);
   return 1;

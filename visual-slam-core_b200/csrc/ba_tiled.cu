@@ -13,6 +13,7 @@
 #include <stdlib.h>
 
 #include "ba_kernels.cuh"
+#include "ba_scatter.cuh"
 
 namespace ba {
 
@@ -23,7 +24,8 @@ static constexpr int kYS = 19;      // Y stride (doubles), odd -> conflict-free 
 static constexpr int kJS = 15;      // Jt (12) + rt (2), padded to odd
 static constexpr int kNCmax = 40;
 
-bool tiled_supported(int n_cam) { return n_cam <= kNCmax; }
+// small windows use camera indices directly; larger ones a per-chunk camera window [cmin, cmin+L)
+bool tiled_supported(int n_cam) { (void)n_cam; return true; }
 
 struct TiledSmem {
   double Y[kTO * kYS];
@@ -34,7 +36,7 @@ struct TiledSmem {
   short ptl[kTO];              // chunk-local point of each staged observation
   int off[kTP + 1];
   double red[kTT / 32];
-  int npts, o_lo, p_next;
+  int npts, o_lo, cmin, cmax;
 };
 
 __device__ __forceinline__ int lower_bound_off(const int* __restrict__ off, int n, int target) {
@@ -47,7 +49,7 @@ __device__ __forceinline__ int lower_bound_off(const int* __restrict__ off, int 
   return lo;
 }
 
-template <int kDbg>
+template <int kDbg, bool kWindowed>
 __global__ void __launch_bounds__(kTT, 1)
 k_linearize_tiled(Work w) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -67,10 +69,6 @@ k_linearize_tiled(Work w) {
   int p_lo = (blockIdx.x == 0) ? 0 : lower_bound_off(w.pt_off, w.n_pt, t_lo);
   const int p_hi = (blockIdx.x == gridDim.x - 1) ? w.n_pt : lower_bound_off(w.pt_off, w.n_pt, t_hi);
 
-  // task list of phase B: nf*(nf-1)/2 off-diagonal blocks over cameras (all cameras enumerated;
-  // fixed ones never get a slot, so their tasks stay zero and are skipped at flush), then 2 per camera
-  const int n_off = ncam * (ncam - 1) / 2;
-  const int n_task = n_off + 2 * ncam;
   double cost = 0.0;
 
   int p = p_lo;
@@ -88,6 +86,8 @@ k_linearize_tiled(Work w) {
       int cnt = (c0 == 32) ? 32 + c1 : c0;
       sm.npts = cnt;
       sm.o_lo = __ldg(w.pt_off + p);
+      sm.cmin = 0x7fffffff;
+      sm.cmax = -1;
       if (cnt == 0) ctl->solve_fail = 2;      // a single point with more than kTO observations
     }
     __syncthreads();
@@ -95,10 +95,6 @@ k_linearize_tiled(Work w) {
     const int o_lo = sm.o_lo;
     if (npts == 0) { p += 1; __syncthreads(); continue; }
     if (tid <= npts) sm.off[tid] = __ldg(w.pt_off + p + tid) - o_lo;
-    for (int i = tid; i < npts * ncam; i += kTT) {
-      int pj = i / ncam, c = i - pj * ncam;
-      sm.slot[pj * kNCmax + c] = -1;
-    }
     __syncthreads();
     const int nobs_c = sm.off[npts];
 
@@ -125,8 +121,28 @@ k_linearize_tiled(Work w) {
       s[8] = au * ol.lu[2] + av * ol.lv[2];
       sm.ptl[i] = (short)pj;
       cost += huber_rho(ol.ru, delta) + huber_rho(ol.rv, delta);
+      if (kWindowed) { atomicMin(&sm.cmin, cam); atomicMax(&sm.cmax, cam); }
     }
     __syncthreads();
+    // camera window of this chunk: local index = cam - cmin, L cameras
+    const int cmin = kWindowed ? sm.cmin : 0;
+    const int L = kWindowed ? (sm.cmax - sm.cmin + 1) : ncam;
+    if (kWindowed && L > kNCmax) {
+      // cameras too far apart for the local window (e.g. a loop closure): scatter this chunk
+      __syncthreads();
+      double (*sW)[19] = reinterpret_cast<double (*)[19]>(sm.Y) + wid * 32;
+      int* sCam = sm.slot + wid * 32;
+      double dummy = 0.0;
+      for (int pj = wid; pj < npts; pj += kTT / 32)
+        scatter_point(w, p + pj, lane, lambda, delta, pose, X, sW, sCam, dummy);
+      p += npts;
+      __syncthreads();
+      continue;
+    }
+    for (int i = tid; i < npts * L; i += kTT) {
+      int pj = i / L, c = i - pj * L;
+      sm.slot[pj * kNCmax + c] = -1;
+    }
     // ---- per point: V, g_l -> C_j (C C^T = V^-1), z_j = C^T g_l -----------------------------
     if (tid < npts) {
       double V[6] = {0, 0, 0, 0, 0, 0}, gl[3] = {0, 0, 0};
@@ -194,14 +210,14 @@ k_linearize_tiled(Work w) {
         }
         jt[12] = su * ol.ru;
         jt[13] = sv * ol.rv;
-        nx = (short)atomicExch(&sm.slot[pj * kNCmax + cam], i);
+        nx = (short)atomicExch(&sm.slot[pj * kNCmax + (cam - cmin)], i);
       }
       sm.next[i] = nx;
     }
     __syncthreads();
     // ---- merge repeated (point, camera) observations: the head's Y becomes the block sum ------
-    for (int i = tid; i < npts * ncam; i += kTT) {
-      int pj = i / ncam, c = i - pj * ncam;
+    for (int i = tid; i < npts * L; i += kTT) {
+      int pj = i / L, c = i - pj * L;
       int h = sm.slot[pj * kNCmax + c];
       if (h >= 0 && sm.next[h] >= 0) {
         double* yh = sm.Y + h * kYS;
@@ -215,6 +231,10 @@ k_linearize_tiled(Work w) {
     __syncthreads();
 
     // ---- phase B: register-accumulated blocks ------------------------------------------------
+    // task list: L(L-1)/2 off-diagonal blocks of the window (cameras without a slot, e.g. fixed
+    // ones, never contribute and are skipped at flush), then two tasks per camera for the diagonal
+    const int n_off = L * (L - 1) / 2;
+    const int n_task = n_off + 2 * L;
     for (int task = tid; task < (kDbg == 2 ? 0 : n_task); task += kTT) {
       if (task < n_off) {
         // block (a, b), a > b: task = a(a-1)/2 + b
@@ -244,7 +264,7 @@ k_linearize_tiled(Work w) {
           }
         }
         if (any && (kDbg != 1 || acc[7] == 1.2345e300)) {
-          double* Sd = w.S + s_block_off(a, b);
+          double* Sd = s_block_ptr(w, cmin + a, cmin + b);
 #pragma unroll
           for (int q = 0; q < 36; ++q) atomicAdd(Sd + q, -acc[q]);
         }
@@ -301,7 +321,7 @@ k_linearize_tiled(Work w) {
           }
         }
         if (any && (kDbg != 1 || acc[7] == 1.2345e300)) {
-          double* Sd = w.S + s_block_off(a, a);
+          double* Sd = s_block_ptr(w, cmin + a, cmin + a);
           if (part == 0) {
             int e = 0;
 #pragma unroll
@@ -309,7 +329,7 @@ k_linearize_tiled(Work w) {
 #pragma unroll
               for (int c = 0; c <= r; ++c) atomicAdd(Sd + 6 * r + c, acc[e++]);
 #pragma unroll
-            for (int r = 0; r < 6; ++r) atomicAdd(w.diagU + 6 * a + r, acc[10 + r]);
+            for (int r = 0; r < 6; ++r) atomicAdd(w.diagU + 6 * (size_t)(cmin + a) + r, acc[10 + r]);
           } else {
             int e = 0;
 #pragma unroll
@@ -317,7 +337,7 @@ k_linearize_tiled(Work w) {
 #pragma unroll
               for (int c = 0; c <= r; ++c) atomicAdd(Sd + 6 * r + c, acc[e++]);
 #pragma unroll
-            for (int r = 0; r < 6; ++r) atomicAdd(w.b + 6 * a + r, acc[11 + r]);
+            for (int r = 0; r < 6; ++r) atomicAdd(w.b + 6 * (size_t)(cmin + a) + r, acc[11 + r]);
           }
         }
       }
@@ -338,24 +358,25 @@ k_linearize_tiled(Work w) {
 }
 
 int configure_tiled() {
-  cudaError_t e = cudaFuncSetAttribute(k_linearize_tiled<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(TiledSmem));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linearize_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TiledSmem));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linearize_tiled<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TiledSmem));
+  const int bytes = (int)sizeof(TiledSmem);
+  cudaError_t e = cudaFuncSetAttribute(k_linearize_tiled<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linearize_tiled<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linearize_tiled<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linearize_tiled<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   return e == cudaSuccess ? 0 : (int)e;
 }
 
 int launch_linearize_tiled(const Work& w, int sm_count, cudaStream_t s) {
-  if (!tiled_supported(w.n_cam)) return launch_linearize_scatter(w, sm_count, s);
   int blocks = sm_count;
   int by_obs = (w.n_obs + 127) / 128;            // do not spread tiny windows over idle CTAs
   if (blocks > by_obs) blocks = by_obs;
   if (blocks < 1) blocks = 1;
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("BA_TILED_DBG"); dbg = e ? atoi(e) : 0; }
-  if (dbg == 1) k_linearize_tiled<1><<<blocks, kTT, sizeof(TiledSmem), s>>>(w);
-  else if (dbg == 2) k_linearize_tiled<2><<<blocks, kTT, sizeof(TiledSmem), s>>>(w);
-  else k_linearize_tiled<0><<<blocks, kTT, sizeof(TiledSmem), s>>>(w);
+  if (w.n_cam > kNCmax) k_linearize_tiled<0, true><<<blocks, kTT, sizeof(TiledSmem), s>>>(w);
+  else if (dbg == 1) k_linearize_tiled<1, false><<<blocks, kTT, sizeof(TiledSmem), s>>>(w);
+  else if (dbg == 2) k_linearize_tiled<2, false><<<blocks, kTT, sizeof(TiledSmem), s>>>(w);
+  else k_linearize_tiled<0, false><<<blocks, kTT, sizeof(TiledSmem), s>>>(w);
   return 1;
 }
 

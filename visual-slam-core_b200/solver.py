@@ -31,7 +31,7 @@ class LMConfig:
     max_iter: int = 10
     solver: str = "auto"        # auto | cholesky | pcg
     schur: str = "auto"         # auto | scatter | tiled
-    pcg_max_iter: int = 200
+    pcg_max_iter: int = 500
     pcg_tol: float = 1e-10
     use_graph: bool = True
     profile: bool = False       # events around every kernel (disables the graph)
@@ -62,6 +62,7 @@ class SolveResult:
     lambda_hist: np.ndarray
     accepted: np.ndarray
     solve_fail: np.ndarray
+    pcg_iters: np.ndarray
     n_iter: int
     gpu_ms: float
     n_launches: int
@@ -162,6 +163,7 @@ class LocalBASolver:
             lambda_hist=np.array(rep.lambda_hist[:k]),
             accepted=np.array(rep.accepted[:k], dtype=np.uint8),
             solve_fail=np.array(rep.solve_fail[:k], dtype=np.int32),
+            pcg_iters=np.array(rep.pcg_iters[:k], dtype=np.int32),
             n_iter=k, gpu_ms=float(rep.gpu_ms), n_launches=int(rep.n_launches),
             extra=dict(ms_linearize=float(rep.ms_linearize), ms_solve=float(rep.ms_solve),
                        ms_backsub=float(rep.ms_backsub), ms_other=float(rep.ms_other)))

@@ -192,8 +192,14 @@ def make_problem(
     outlier_frac: float = 0.05,
     noise_px: float = 1.0,
     chunk: int = 250_000,
+    sort_points: Optional[bool] = None,
 ) -> BAProblem:
-    """Generate one of the named configs (or a custom size)."""
+    """Generate one of the named configs (or a custom size).
+
+    `sort_points` (default: on when n_cam > 40) orders the points by their anchor camera, the
+    order a SLAM map has naturally: `Map.optimize_local` collects points keyframe by keyframe
+    (map/map.py:159-169), so consecutive points are seen by neighbouring keyframes.
+    """
     if name is not None:
         cfg = dict(CONFIGS[name])
         n_cam = cfg["n_cam"] if n_cam is None else n_cam
@@ -209,6 +215,7 @@ def make_problem(
     win = n_cam if full else min(n_cam, 2 * k_max + 1)
     X_true = np.empty((n_pt, 3))
     counts = np.zeros(n_pt, dtype=np.int64)
+    anchor_all = np.zeros(n_pt, dtype=np.int64)
     cam_lists = []   # per chunk: (k_per_point, cams flat)
 
     for p0 in range(0, n_pt, chunk):
@@ -251,6 +258,7 @@ def make_problem(
         else:
             raise RuntimeError("could not place all points")
         X_true[p0:p1] = Xw
+        anchor_all[p0:p1] = anchors
         k = sel_mask.sum(axis=1)
         counts[p0:p1] = k
         # selected cameras, per point sorted ascending by camera index
@@ -263,6 +271,17 @@ def make_problem(
     n_obs = int(pt_offsets[-1])
     assert n_obs < 2**31
     obs_cam = np.concatenate(cam_lists).astype(np.int32)
+    if sort_points is None:
+        sort_points = n_cam > 40
+    if sort_points:
+        order = np.argsort(anchor_all, kind="stable")
+        new_counts = counts[order]
+        new_off = np.zeros(n_pt + 1, dtype=np.int64)
+        np.cumsum(new_counts, out=new_off[1:])
+        src = np.repeat(pt_offsets[:-1][order] - new_off[:-1], new_counts) + np.arange(n_obs, dtype=np.int64)
+        obs_cam = obs_cam[src]
+        X_true = X_true[order]
+        counts, pt_offsets = new_counts, new_off
     obs_pt = np.repeat(np.arange(n_pt, dtype=np.int32), counts)
 
     # measurements: exact projection + N(0,1px); 5% get an extra N(0,30px)
