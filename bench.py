@@ -42,9 +42,9 @@ UNIT = "LM iter/s"
 
 
 # --------------------------------------------------------------------------------------------
-def algorithmic_bytes(n_cam, n_pt, n_obs):
-    """SURVEY.md 8d-D4 / BASELINE.md 3 (float32 values, int32 indices, dense |S|)."""
-    S = (6 * n_cam) ** 2 * 4
+def algorithmic_bytes(n_cam, n_pt, n_obs, dense=True, nnzb=0):
+    """SURVEY.md 8d-D4 / BASELINE.md 3 (float32 values, int32 indices; |S| dense or 144 B per block)."""
+    S = (6 * n_cam) ** 2 * 4 if dense else 144 * nnzb
     b_rjs = 17 * n_obs + 48 * n_pt + 72 * n_cam + S
     b_iter = 33 * n_obs + 108 * n_pt + 72 * n_cam + 2 * S
     return b_rjs, b_iter
@@ -180,14 +180,30 @@ def run_b200(args, rank, local_rank, world):
         torch.cuda.synchronize(dev)
 
     max_iter = args.lm_iters
-    p = synth.make_problem(args.config, seed=rank)          # one independent window per GPU
+    sharded = args.shard or args.config in ("C4", "C5")
+    if sharded:
+        # BASELINE configs 4/5: ONE problem, points sharded over the ranks, cameras replicated; the
+        # reduced camera system and the costs are NCCL all-reduced inside the CUDA library
+        from visual_slam_core_b200 import dist as badist
+        full = synth.make_problem(args.config, seed=0)
+        p = full.shard_by_point(rank, world) if world > 1 else full
+        n_obs_total, n_pt_total = full.n_obs, full.n_pt
+        del full
+    else:
+        p = synth.make_problem(args.config, seed=rank)      # one independent window per GPU
+        n_obs_total, n_pt_total = p.n_obs, p.n_pt
     T = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(dev)
     R0, t0, X0 = T(p.R), T(p.t), T(p.X)
     R, t, X = R0.clone(), t0.clone(), X0.clone()
     fixed, oc, op, uv, off = T(p.fixed), T(p.obs_cam), T(p.obs_pt), T(p.obs_uv), T(p.pt_offsets)
     flags = torch.zeros(p.n_obs, dtype=torch.uint8, device=dev)
-    solver = LocalBASolver(LMConfig(max_iter=max_iter, schur=args.schur), device=local_rank)
+    lmcfg = dict(max_iter=max_iter, schur=args.schur, pcg_tol=args.pcg_tol, pcg_max_iter=args.pcg_max_iter)
+    solver = LocalBASolver(LMConfig(**lmcfg), device=local_rank)
+    if sharded and world > 1:
+        badist.init_solver(solver, rank, world, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    if sharded:
+        args.steps = min(args.steps, 3)
     stream = torch.cuda.current_stream(dev)
 
     def step(sync=False):
@@ -216,14 +232,18 @@ def run_b200(args, rank, local_rank, world):
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_max = float(tms.item())
-    value = world * args.steps * max_iter / (ms_max / 1e3)
+    n_windows = 1 if sharded else world
+    value = n_windows * args.steps * max_iter / (ms_max / 1e3)
 
     # ---- end to end through the host-buffer API (pinned host memory, copies inside the timed region)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a).copy()).pin_memory().numpy()
     hR, ht, hX = pin(p.R), pin(p.t), pin(p.X)
     hfixed, hoc, hop, huv, hoff = pin(p.fixed), pin(p.obs_cam), pin(p.obs_pt), pin(p.obs_uv), pin(p.pt_offsets)
     hflags = pin(np.zeros(p.n_obs, dtype=np.uint8))
-    e2e_solver = LocalBASolver(LMConfig(max_iter=max_iter, schur=args.schur), device=local_rank)
+    if sharded and world > 1:
+        e2e_solver = solver                                  # one communicator per process is enough
+    else:
+        e2e_solver = LocalBASolver(LMConfig(**lmcfg), device=local_rank)
 
     def e2e_step():
         np.copyto(hR, p.R); np.copyto(ht, p.t); np.copyto(hX, p.X)
@@ -240,7 +260,7 @@ def run_b200(args, rank, local_rank, world):
     te = torch.tensor([t_b - t_a], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.steps * max_iter / float(te.item())
+    e2e_value = n_windows * args.steps * max_iter / float(te.item())
     import ctypes as C
     from visual_slam_core_b200 import _lib
     h2d = sum(a.nbytes for a in (hR, ht, hfixed, hX, hoc, hop, huv, hoff))
@@ -248,18 +268,23 @@ def run_b200(args, rank, local_rank, world):
     final_cost = float(res.cost_hist[-1])
 
     # ---- profile pass: CUDA events around every kernel (no graph), same workload
-    prof = LocalBASolver(LMConfig(max_iter=max_iter, schur=args.schur, profile=True), device=local_rank)
+    if sharded and world > 1:
+        prof = solver
+        prof.set_config(LMConfig(profile=True, **lmcfg))
+    else:
+        prof = LocalBASolver(LMConfig(profile=True, **lmcfg), device=local_rank)
     acc = np.zeros(4)
-    n_prof = 5
+    n_prof = 5 if not sharded else 2
     for i in range(n_prof + 2):
         R.copy_(R0); t.copy_(t0); X.copy_(X0)
         r = prof.solve_local_device(p.intr, R, t, fixed, X, oc, op, uv, off, flags, stream=stream.cuda_stream, sync=True)
         if i >= 2:
             acc += np.array([r.ms_linearize, r.ms_solve, r.ms_backsub, r.ms_other])
     acc /= n_prof
+    pcg_iters = [int(v) for v in r.pcg_iters[:max_iter]]
     k_ms = {"linearize_schur": acc[0] / max_iter, "rcs_solve": acc[1] / max_iter,
             "backsub_cost": acc[2] / max_iter, "init_finalize_per_step": acc[3]}
-    b_rjs, b_iter = algorithmic_bytes(p.n_cam, p.n_pt, p.n_obs)
+    b_rjs, b_iter = algorithmic_bytes(p.n_cam, p.n_pt, p.n_obs, dense=p.n_cam <= 38, nnzb=33 * p.n_cam)
     peak, peak_src = hbm_peak()
     dom = max(("linearize_schur", "rcs_solve", "backsub_cost"), key=lambda k: k_ms[k])
     lin_gbs = b_rjs / (k_ms["linearize_schur"] * 1e-3) / 1e9
@@ -281,12 +306,18 @@ def run_b200(args, rank, local_rank, world):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.config, p), "lm_iterations_per_step": max_iter,
-                   "parallelism": "single GPU" if world == 1 else f"{world} independent windows, one per GPU (replicas)",
+        "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, p) if not sharded else
+                   f"{args.config}: {p.n_cam} cameras, {n_pt_total} points, {n_obs_total} observations, sharded by point over {world} GPU(s)",
+                   "lm_iterations_per_step": max_iter,
+                   "parallelism": "single GPU" if world == 1 else (
+                       f"points sharded over {world} GPUs, NCCL all-reduce of the reduced camera system" if sharded
+                       else f"{world} independent windows, one per GPU (replicas)"),
+                   "pcg": {"tol": args.pcg_tol, "iterations": pcg_iters} if p.n_cam > 38 else None,
                    "l2": "flushed between steps (256 MiB write); inside a step the window stays L2-resident by construction",
                    "schur": args.schur},
         "obs_per_s_residual_jacobian_schur": p.n_obs / (k_ms["linearize_schur"] * 1e-3) * world,
+        "shard_observations": p.n_obs,
         "kernel_ms_per_lm_iteration": k_ms,
         "final_cost": final_cost,
         "roofline": roofline,
@@ -296,7 +327,7 @@ def run_b200(args, rank, local_rank, world):
         "clocks": clocks,
     }
 
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and p.n_obs <= 400_000:
         from oracle import lm_oracle as O
         t_c = time.perf_counter()
         ref = O.solve_local(p.intr, p.R, p.t, p.fixed, p.X, p.obs_cam, p.obs_pt, p.obs_uv,
@@ -324,6 +355,9 @@ def main():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--lm-iters", type=int, default=10)
     ap.add_argument("--schur", default="auto")
+    ap.add_argument("--shard", action="store_true", help="shard ONE problem by point over the ranks (default for C4/C5)")
+    ap.add_argument("--pcg-tol", type=float, default=1e-10)
+    ap.add_argument("--pcg-max-iter", type=int, default=3000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

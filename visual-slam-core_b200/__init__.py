@@ -2,4 +2,4 @@
 from . import synth  # noqa: F401
 from .optimizer import B200Optimizer, BaseOptimizer, lm_config_from  # noqa: F401
 from .solver import LMConfig, LocalBASolver, SolveResult  # noqa: F401
-from . import packing, refgraph  # noqa: F401
+from . import dist, packing, refgraph  # noqa: F401

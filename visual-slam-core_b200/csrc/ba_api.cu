@@ -23,6 +23,7 @@ typedef int (*fn_get_uid)(nccl_uid*);
 typedef int (*fn_init_rank)(nccl_comm*, int, nccl_uid, int);
 typedef int (*fn_destroy)(nccl_comm);
 typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t);
+typedef int (*fn_allgather)(const void*, void*, size_t, int, nccl_comm, cudaStream_t);
 typedef const char* (*fn_errstr)(int);
 struct NcclApi {
   void* lib = nullptr;
@@ -30,6 +31,7 @@ struct NcclApi {
   fn_init_rank init_rank = nullptr;
   fn_destroy destroy = nullptr;
   fn_allreduce allreduce = nullptr;
+  fn_allgather allgather = nullptr;
   fn_errstr errstr = nullptr;
 };
 NcclApi g_nccl;
@@ -43,8 +45,9 @@ bool load_nccl() {
     g_nccl.init_rank = (fn_init_rank)dlsym(h, "ncclCommInitRank");
     g_nccl.destroy = (fn_destroy)dlsym(h, "ncclCommDestroy");
     g_nccl.allreduce = (fn_allreduce)dlsym(h, "ncclAllReduce");
+    g_nccl.allgather = (fn_allgather)dlsym(h, "ncclAllGather");
     g_nccl.errstr = (fn_errstr)dlsym(h, "ncclGetErrorString");
-    if (g_nccl.get_uid && g_nccl.init_rank && g_nccl.destroy && g_nccl.allreduce) {
+    if (g_nccl.get_uid && g_nccl.init_rank && g_nccl.destroy && g_nccl.allreduce && g_nccl.allgather) {
       g_nccl.lib = h;
       return true;
     }
@@ -52,7 +55,7 @@ bool load_nccl() {
   }
   return false;
 }
-constexpr int kNcclDouble = 8, kNcclSum = 0;
+constexpr int kNcclDouble = 8, kNcclSum = 0, kNcclUint32 = 3;
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -71,7 +74,7 @@ struct ba_handle {
   // workspace
   DevBuf pose0, pose1, X0, X1, red, dp, ctl, cand, dbg;
   // sparse path: structure + PCG workspace
-  DevBuf bits, wpre, row_nnz, row_ptr, col_idx, tpos, pcg;
+  DevBuf bits, wpre, row_nnz, row_ptr, col_idx, tpos, pcg, bits_all;
   int* h_nnzb = nullptr;          // pinned
   // staging for the host-pointer API
   DevBuf d_R, d_t, d_fixed, d_X, d_ocam, d_opt, d_ouv, d_off, d_flags, d_hist, d_acc, d_foff;
@@ -233,7 +236,8 @@ extern "C" int ba_destroy(ba_handle* h) {
   DevBuf* bufs[] = {&h->pose0, &h->pose1, &h->X0, &h->X1, &h->red, &h->dp, &h->ctl, &h->cand,
                     &h->d_R, &h->d_t, &h->d_fixed, &h->d_X, &h->d_ocam, &h->d_opt, &h->d_ouv,
                     &h->d_off, &h->d_flags, &h->d_hist, &h->d_acc, &h->d_foff, &h->dbg,
-                    &h->bits, &h->wpre, &h->row_nnz, &h->row_ptr, &h->col_idx, &h->tpos, &h->pcg};
+                    &h->bits, &h->wpre, &h->row_nnz, &h->row_ptr, &h->col_idx, &h->tpos, &h->pcg,
+                    &h->bits_all};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
@@ -297,7 +301,18 @@ static int make_work(ba_handle* h, int n_cam, int n_pt, int n_obs, const double 
     w.bsr_bits = (const unsigned*)h->bits.p;
     w.bsr_wpre = (const int*)h->wpre.p;
     w.bsr_row_ptr = (const int*)h->row_ptr.p;
-    launch_symbolic(w, (unsigned*)h->bits.p, (int*)h->wpre.p, (int*)h->row_nnz.p, (int*)h->row_ptr.p, s);
+    if (h->world > 1) {
+      // every rank must build the same structure: OR the co-visibility bitmaps of all shards
+      const size_t words = (size_t)n_cam * W;
+      if ((rc = ensure(h, h->bits_all, sizeof(unsigned) * words * h->world))) return rc;
+      launch_symbolic_mark(w, (unsigned*)h->bits.p, s);
+      int r = g_nccl.allgather(h->bits.p, h->bits_all.p, words, kNcclUint32, h->comm, s);
+      if (r != 0) { h->err = std::string("ncclAllGather(bitmap): ") + (g_nccl.errstr ? g_nccl.errstr(r) : "?"); return BA_ERR_NCCL; }
+      launch_symbolic_or(w, (const unsigned*)h->bits_all.p, h->world, (unsigned*)h->bits.p, s);
+      launch_symbolic_count(w, (unsigned*)h->bits.p, (int*)h->wpre.p, (int*)h->row_nnz.p, (int*)h->row_ptr.p, s);
+    } else {
+      launch_symbolic(w, (unsigned*)h->bits.p, (int*)h->wpre.p, (int*)h->row_nnz.p, (int*)h->row_ptr.p, s);
+    }
     CK(cudaMemcpyAsync(h->h_nnzb, (int*)h->row_ptr.p + n_cam, sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     const int nnzb = *h->h_nnzb;

@@ -78,6 +78,9 @@ int launch_linearize_scatter(const Work& w, int sm_count, cudaStream_t s);
 int launch_linearize_tiled(const Work& w, int sm_count, cudaStream_t s);
 int launch_rcs_cholesky(const Work& w, cudaStream_t s);
 int launch_symbolic(const Work& w, unsigned* bits, int* wpre, int* row_nnz, int* row_ptr, cudaStream_t s);
+int launch_symbolic_mark(const Work& w, unsigned* bits, cudaStream_t s);
+int launch_symbolic_or(const Work& w, const unsigned* all, int world, unsigned* bits, cudaStream_t s);
+int launch_symbolic_count(const Work& w, unsigned* bits, int* wpre, int* row_nnz, int* row_ptr, cudaStream_t s);
 int launch_symbolic_fill(const Work& w, int* col_idx, int* tpos, cudaStream_t s);
 int pcg_grid_size(int n_cam, int sm_count);
 int launch_rcs_pcg(const Work& w, int grid, cudaStream_t s);

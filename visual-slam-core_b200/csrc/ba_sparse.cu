@@ -132,17 +132,44 @@ __global__ void k_sym_tpos(Work w, int* __restrict__ tpos) {
   }
 }
 
-int launch_symbolic(const Work& w, unsigned* bits, int* wpre, int* row_nnz, int* row_ptr,
-                    cudaStream_t s) {
+int launch_symbolic_mark(const Work& w, unsigned* bits, cudaStream_t s) {
   cudaMemsetAsync(bits, 0, sizeof(unsigned) * (size_t)w.n_cam * w.bsr_W, s);
   int blocks = (w.n_pt + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   k_sym_mark<<<blocks, 256, 0, s>>>(w, bits);
+  return 1;
+}
+
+__global__ void k_sym_or(size_t words, int world, const unsigned* __restrict__ all, unsigned* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) {
+    unsigned m = 0u;
+    for (int r = 0; r < world; ++r) m |= all[(size_t)r * words + i];
+    out[i] = m;
+  }
+}
+
+int launch_symbolic_or(const Work& w, const unsigned* all, int world, unsigned* bits, cudaStream_t s) {
+  const size_t words = (size_t)w.n_cam * w.bsr_W;
+  int blocks = (int)((words + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  k_sym_or<<<blocks, 256, 0, s>>>(words, world, all, bits);
+  return 1;
+}
+
+int launch_symbolic_count(const Work& w, unsigned* bits, int* wpre, int* row_nnz, int* row_ptr, cudaStream_t s) {
   int rb = (w.n_cam + 7) / 8;
   if (rb > 148 * 8) rb = 148 * 8;
   k_sym_rowcount<<<rb, 256, 0, s>>>(w.n_cam, w.bsr_W, bits, wpre, row_nnz);
   k_sym_scan<<<1, 1024, 0, s>>>(w.n_cam, row_nnz, row_ptr);
+  return 2;
+}
+
+int launch_symbolic(const Work& w, unsigned* bits, int* wpre, int* row_nnz, int* row_ptr,
+                    cudaStream_t s) {
+  launch_symbolic_mark(w, bits, s);
+  launch_symbolic_count(w, bits, wpre, row_nnz, row_ptr, s);
   return 3;
 }
 

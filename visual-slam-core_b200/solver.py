@@ -101,6 +101,12 @@ class LocalBASolver:
         except Exception:
             pass
 
+    def dist_init(self, nccl_id: bytes, rank: int, world: int):
+        """Join the shard-by-point group: every rank then calls the same solve on its point shard."""
+        buf = (C.c_ubyte * len(nccl_id)).from_buffer_copy(nccl_id)
+        rc = self.lib.ba_dist_init(self._h, buf, int(rank), int(world))
+        _lib.check(self.lib, self._h, rc, "ba_dist_init")
+
     def set_config(self, cfg: LMConfig):
         self.cfg = cfg
         prm = cfg.to_c()
