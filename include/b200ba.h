@@ -50,7 +50,12 @@ enum {
 };
 
 /* solver_kind */
-enum { BA_SOLVER_AUTO = 0, BA_SOLVER_CHOLESKY = 1, BA_SOLVER_PCG = 2 };
+enum {
+  BA_SOLVER_AUTO = 0,      /* dense Cholesky if the window fits shared memory, else banded, else PCG */
+  BA_SOLVER_CHOLESKY = 1,  /* dense in-shared-memory blocked Cholesky (windows up to 38 keyframes) */
+  BA_SOLVER_PCG = 2,       /* block-sparse S + block-Jacobi PCG (any co-visibility structure) */
+  BA_SOLVER_BAND = 3       /* block-banded S + direct banded Cholesky (co-visibility bandwidth <= 32 keyframes) */
+};
 /* schur_kind */
 enum { BA_SCHUR_AUTO = 0, BA_SCHUR_SCATTER = 1, BA_SCHUR_TILED = 2 };
 
@@ -76,7 +81,7 @@ typedef struct ba_report {
   int32_t status;                       /* BA_OK or error */
   int32_t n_iter;                       /* LM iterations executed (= max_iter) */
   int32_t n_accepted;
-  int32_t solver_used;                  /* BA_SOLVER_CHOLESKY / BA_SOLVER_PCG */
+  int32_t solver_used;                  /* BA_SOLVER_CHOLESKY / BA_SOLVER_PCG / BA_SOLVER_BAND */
   double cost_hist[BA_MAX_ITER + 1];    /* [0] initial cost, [i+1] cost after iteration i */
   double cand_cost_hist[BA_MAX_ITER];   /* candidate cost evaluated by iteration i */
   double lambda_hist[BA_MAX_ITER];      /* damping used by iteration i */
@@ -89,6 +94,8 @@ typedef struct ba_report {
   float ms_solve;
   float ms_backsub;
   float ms_other;                       /* init + finalize (+ collectives when sharded) */
+  int32_t band_width;                   /* BA_SOLVER_BAND: co-visibility bandwidth in keyframes, else -1 */
+  int32_t s_blocks;                     /* 6x6 blocks of the reduced camera matrix that are stored / all-reduced */
 } ba_report;
 
 typedef struct ba_handle ba_handle;

@@ -105,18 +105,55 @@ def test_reduced_camera_system_matches_oracle(name, seed, lam, schur):
 
 
 @pytest.mark.parametrize("schur", ["tiled", "scatter"])
+@pytest.mark.parametrize("solver_kind", ["pcg", "auto"])
 @pytest.mark.parametrize("name,seed", [("T3", 1), ("T4", 2)])
-def test_large_window_sparse_pcg_matches_oracle(name, seed, schur):
-    """More cameras than the shared-memory Cholesky holds: block-sparse S + block-Jacobi PCG on the
-    GPU vs the oracle's sparse direct solve."""
+def test_large_window_matches_oracle(name, seed, schur, solver_kind):
+    """More cameras than the shared-memory Cholesky holds.  `pcg`: block-sparse S + block-Jacobi
+    PCG; `auto`: the window is a sequential trajectory, so the block-banded S + direct banded
+    Cholesky is picked.  Both vs the oracle's sparse direct solve."""
     p = synth.make_problem(name, seed=seed)
-    s = LocalBASolver(LMConfig(schur=schur, pcg_tol=1e-12, pcg_max_iter=3000))
+    s = LocalBASolver(LMConfig(schur=schur, solver=solver_kind, pcg_tol=1e-12, pcg_max_iter=3000))
     res = s.solve_local(p.intr, p.R, p.t, p.fixed, p.X, p.obs_cam, p.obs_pt, p.obs_uv, p.pt_offsets)
     s.close()
     ref = _oracle(p)
     assert res.solve_fail.sum() == 0
+    assert res.extra["solver_used"] == ("pcg" if solver_kind == "pcg" else "band")
+    if solver_kind == "auto":
+        assert res.extra["band_width"] == 11 and res.pcg_iters.sum() == 0
     info = _check(p, res, ref, gauge_free=p.n_cam > 100)
-    print(f"\n[{name} seed {seed} {schur} pcg] achieved: {info} pcg iterations {res.pcg_iters.tolist()}")
+    print(f"\n[{name} seed {seed} {schur} {solver_kind}] achieved: {info} pcg iterations {res.pcg_iters.tolist()}")
+
+
+@pytest.mark.parametrize("name,seed", [("T0", 1), ("T1", 2), ("T2", 3), ("C1", 0)])
+def test_banded_solver_on_small_windows_matches_oracle(name, seed):
+    """The banded layout and factorisation forced onto windows the dense solver also handles
+    (bandwidth = n_cam - 1 when every keyframe pair is co-visible)."""
+    p = synth.make_problem(name, seed=seed)
+    s = LocalBASolver(LMConfig(solver="band"))
+    res = s.solve_local(p.intr, p.R, p.t, p.fixed, p.X, p.obs_cam, p.obs_pt, p.obs_uv, p.pt_offsets)
+    s.close()
+    assert res.extra["solver_used"] == "band" and 0 < res.extra["band_width"] < p.n_cam
+    info = _check(p, res, _oracle(p))
+    print(f"\n[{name} seed {seed} band w={res.extra['band_width']}] achieved: {info}")
+    assert info["cost_rel"] < 1e-9
+
+
+def test_wide_covisibility_falls_back_to_pcg_and_band_refuses():
+    """Co-visibility wider than the banded solver's 32 keyframes: `auto` takes the PCG path,
+    an explicit `band` request is refused (no silent downgrade)."""
+    from visual_slam_core_b200._lib import B200BAError
+    p = synth.make_problem(n_cam=60, n_pt=1500, k_mean=45.0, k_max=60, seed=3)
+    span = max(int(p.obs_cam[a:b].max() - p.obs_cam[a:b].min()) for a, b in zip(p.pt_offsets[:-1], p.pt_offsets[1:]))
+    assert span > 32
+    s = LocalBASolver(LMConfig(solver="band"))
+    with pytest.raises(B200BAError):
+        s.solve_local(p.intr, p.R, p.t, p.fixed, p.X, p.obs_cam, p.obs_pt, p.obs_uv, p.pt_offsets)
+    s.close()
+    s = LocalBASolver(LMConfig(pcg_tol=1e-12, pcg_max_iter=3000))
+    res = s.solve_local(p.intr, p.R, p.t, p.fixed, p.X, p.obs_cam, p.obs_pt, p.obs_uv, p.pt_offsets)
+    s.close()
+    assert res.extra["solver_used"] == "pcg"
+    _check(p, res, _oracle(p))
 
 
 def test_unsorted_points_use_the_scatter_fallback():

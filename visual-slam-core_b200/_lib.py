@@ -11,7 +11,7 @@ BA_MAX_ITER = 64
 BA_NCCL_ID_BYTES = 128
 BA_OK = 0
 BA_ERR_INVALID, BA_ERR_CUDA, BA_ERR_TOO_LARGE, BA_ERR_NCCL, BA_ERR_NO_DEVICE = -1, -2, -3, -4, -5
-BA_SOLVER_AUTO, BA_SOLVER_CHOLESKY, BA_SOLVER_PCG = 0, 1, 2
+BA_SOLVER_AUTO, BA_SOLVER_CHOLESKY, BA_SOLVER_PCG, BA_SOLVER_BAND = 0, 1, 2, 3
 BA_SCHUR_AUTO, BA_SCHUR_SCATTER, BA_SCHUR_TILED = 0, 1, 2
 
 
@@ -37,7 +37,7 @@ class BAReport(C.Structure):
         ("pcg_iters", C.c_int32 * BA_MAX_ITER),
         ("gpu_ms", C.c_float), ("n_launches", C.c_int32),
         ("ms_linearize", C.c_float), ("ms_solve", C.c_float), ("ms_backsub", C.c_float),
-        ("ms_other", C.c_float),
+        ("ms_other", C.c_float), ("band_width", C.c_int32), ("s_blocks", C.c_int32),
     ]
 
 

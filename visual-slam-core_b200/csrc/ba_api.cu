@@ -55,7 +55,7 @@ bool load_nccl() {
   }
   return false;
 }
-constexpr int kNcclDouble = 8, kNcclSum = 0, kNcclUint32 = 3;
+constexpr int kNcclDouble = 8, kNcclSum = 0, kNcclMax = 2, kNcclUint32 = 3, kNcclInt32 = 2;
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -75,6 +75,9 @@ struct ba_handle {
   DevBuf pose0, pose1, X0, X1, red, dp, ctl, cand, dbg;
   // sparse path: structure + PCG workspace
   DevBuf bits, wpre, row_nnz, row_ptr, col_idx, tpos, pcg, bits_all;
+  // banded path: factor columns, forward-substituted rhs, inverse pivots, bandwidth scalar
+  DevBuf band_L, band_y, band_dinv, band_wbuf;
+  int last_solver = BA_SOLVER_CHOLESKY, last_band_w = -1, last_s_blocks = 0;
   int* h_nnzb = nullptr;          // pinned
   // staging for the host-pointer API
   DevBuf d_R, d_t, d_fixed, d_X, d_ocam, d_opt, d_ouv, d_off, d_flags, d_hist, d_acc, d_foff;
@@ -237,7 +240,7 @@ extern "C" int ba_destroy(ba_handle* h) {
                     &h->d_R, &h->d_t, &h->d_fixed, &h->d_X, &h->d_ocam, &h->d_opt, &h->d_ouv,
                     &h->d_off, &h->d_flags, &h->d_hist, &h->d_acc, &h->d_foff, &h->dbg,
                     &h->bits, &h->wpre, &h->row_nnz, &h->row_ptr, &h->col_idx, &h->tpos, &h->pcg,
-                    &h->bits_all};
+                    &h->bits_all, &h->band_L, &h->band_y, &h->band_dinv, &h->band_wbuf};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
@@ -253,18 +256,64 @@ extern "C" int ba_destroy(ba_handle* h) {
 // ------------------------------------------------------------------------------------------
 // local BA
 // ------------------------------------------------------------------------------------------
-static bool want_sparse(const ba_handle* h, int n_cam) {
-  return h->prm.solver_kind == BA_SOLVER_PCG || 6 * n_cam > rcs_cholesky_max_n();
+enum { MODE_DENSE = 0, MODE_PCG = 1, MODE_BAND = 2 };
+
+// co-visibility bandwidth in keyframes (max over points of the camera-index spread); one host sync
+static int band_width(ba_handle* h, int n_pt, const int32_t* obs_cam, const int32_t* pt_off,
+                      cudaStream_t s, int* out) {
+  int rc;
+  if ((rc = ensure(h, h->band_wbuf, sizeof(int)))) return rc;
+  Work w;
+  memset(&w, 0, sizeof(w));
+  w.n_pt = n_pt; w.obs_cam = obs_cam; w.pt_off = pt_off;
+  launch_band_width(w, (int*)h->band_wbuf.p, s);
+  if (h->world > 1) {
+    int r = g_nccl.allreduce(h->band_wbuf.p, h->band_wbuf.p, 1, kNcclInt32, kNcclMax, h->comm, s);
+    if (r != 0) { h->err = std::string("ncclAllReduce(bandwidth): ") + (g_nccl.errstr ? g_nccl.errstr(r) : "?"); return BA_ERR_NCCL; }
+  }
+  CK(cudaMemcpyAsync(h->h_nnzb, h->band_wbuf.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  *out = *h->h_nnzb;
+  return BA_OK;
+}
+
+// which layout / solver this window gets
+static int pick_mode(ba_handle* h, int n_cam, int n_pt, const int32_t* obs_cam, const int32_t* pt_off,
+                     cudaStream_t s, int* mode, int* bw) {
+  const int kind = h->prm.solver_kind;
+  const bool dense_fits = 6 * n_cam <= rcs_cholesky_max_n();
+  *bw = -1;
+  if (kind == BA_SOLVER_PCG) { *mode = MODE_PCG; return BA_OK; }
+  if (kind == BA_SOLVER_CHOLESKY || (kind == BA_SOLVER_AUTO && dense_fits)) {
+    if (!dense_fits) {
+      h->err = "reduced camera system larger than the in-shared-memory Cholesky; use solver auto, band or pcg";
+      return BA_ERR_TOO_LARGE;
+    }
+    *mode = MODE_DENSE;
+    return BA_OK;
+  }
+  int wv = 0;
+  int rc = band_width(h, n_pt, obs_cam, pt_off, s, &wv);
+  if (rc) return rc;
+  if (wv >= n_cam) wv = n_cam - 1;
+  if (wv <= band_max_w()) { *mode = MODE_BAND; *bw = wv; return BA_OK; }
+  if (kind == BA_SOLVER_BAND) {
+    h->err = "co-visibility bandwidth exceeds the banded solver (32 keyframes); use solver auto or pcg";
+    return BA_ERR_TOO_LARGE;
+  }
+  *mode = MODE_PCG;
+  return BA_OK;
 }
 
 // workspace + kernel view.  sparse = block-sparse S + PCG (needs one host sync for the block count)
 static int make_work(ba_handle* h, int n_cam, int n_pt, int n_obs, const double intr[4],
                      const uint8_t* fixed, const int32_t* obs_cam, const int32_t* obs_pt,
-                     const float* obs_uv, const int32_t* pt_off, Work& w, bool sparse = false,
-                     cudaStream_t s = nullptr) {
+                     const float* obs_uv, const int32_t* pt_off, Work& w, int mode = MODE_DENSE,
+                     cudaStream_t s = nullptr, int bw = -1) {
   const int n = 6 * n_cam;
   int rc;
   memset(&w, 0, sizeof(w));
+  w.band_w = -1;
   if ((rc = ensure(h, h->pose0, sizeof(double) * 12 * (size_t)n_cam))) return rc;
   if ((rc = ensure(h, h->pose1, sizeof(double) * 12 * (size_t)n_cam))) return rc;
   if ((rc = ensure(h, h->X0, sizeof(double) * 3 * (size_t)(n_pt + 1)))) return rc;
@@ -288,8 +337,17 @@ static int make_work(ba_handle* h, int n_cam, int n_pt, int n_obs, const double 
     if ((rc = ensure(h, h->dbg, sizeof(long long) * 4096))) return rc;
     w.dbg = (long long*)h->dbg.p;
   }
-  if (!sparse) {
+  if (mode == MODE_DENSE) {
     w.s_len = s_doubles(n_cam);
+  } else if (mode == MODE_BAND) {
+    w.band_w = bw;
+    w.s_len = (size_t)n_cam * (bw + 1) * 36;
+    if ((rc = ensure(h, h->band_L, sizeof(double) * w.s_len))) return rc;
+    if ((rc = ensure(h, h->band_y, sizeof(double) * (size_t)n))) return rc;
+    if ((rc = ensure(h, h->band_dinv, sizeof(double) * (size_t)n))) return rc;
+    w.band_L = (double*)h->band_L.p;
+    w.band_y = (double*)h->band_y.p;
+    w.band_dinv = (double*)h->band_dinv.p;
   } else {
     // symbolic phase: co-visibility bitmap -> block-CSR structure
     const int W = (n_cam + 31) / 32;
@@ -369,7 +427,9 @@ static int enqueue_lm_loop(ba_handle* h, const Work& w, int schur, cudaStream_t 
       if (r != 0) { h->err = std::string("ncclAllReduce(S): ") + (g_nccl.errstr ? g_nccl.errstr(r) : "?"); return BA_ERR_NCCL; }
     }
     prof_mark(h, TAG_SOLVE, s);
-    if (sparse) {
+    if (w.band_w >= 0) {
+      launches += launch_rcs_band(w, s);
+    } else if (sparse) {
       if (launch_rcs_pcg(w, pcg_grid, s) < 0) { h->err = std::string("cooperative PCG launch: ") + cudaGetErrorString(cudaGetLastError()); return BA_ERR_CUDA; }
       launches += 1;
     } else {
@@ -407,7 +467,9 @@ static void fill_report(const ba_handle* h, const LmCtl* c, ba_report* rep, int 
   rep->status = status;
   rep->n_iter = c->iter;
   rep->n_accepted = c->n_accepted;
-  rep->solver_used = BA_SOLVER_CHOLESKY;
+  rep->solver_used = h->last_solver;
+  rep->band_width = h->last_band_w;
+  rep->s_blocks = h->last_s_blocks;
   for (int i = 0; i <= BA_MAX_ITER; ++i) rep->cost_hist[i] = c->cost_hist[i];
   for (int i = 0; i < BA_MAX_ITER; ++i) {
     rep->cand_cost_hist[i] = c->cand_hist[i];
@@ -435,14 +497,16 @@ extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t
     return BA_ERR_INVALID;
   CK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
-  if (h->prm.solver_kind == BA_SOLVER_CHOLESKY && 6 * n_cam > rcs_cholesky_max_n()) {
-    h->err = "reduced camera system larger than the in-shared-memory Cholesky; use solver auto or pcg";
-    return BA_ERR_TOO_LARGE;
-  }
-  const bool sparse = want_sparse(h, n_cam);
-  Work w;
-  int rc = make_work(h, n_cam, n_pt, n_obs, intr, cam_fixed, obs_cam, obs_pt, obs_uv, pt_offsets, w, sparse, s);
+  int mode = MODE_DENSE, bw = -1;
+  int rc = pick_mode(h, n_cam, n_pt, obs_cam, pt_offsets, s, &mode, &bw);
   if (rc) return rc;
+  const bool sparse = mode != MODE_DENSE;
+  Work w;
+  rc = make_work(h, n_cam, n_pt, n_obs, intr, cam_fixed, obs_cam, obs_pt, obs_uv, pt_offsets, w, mode, s, bw);
+  if (rc) return rc;
+  h->last_solver = mode == MODE_DENSE ? BA_SOLVER_CHOLESKY : (mode == MODE_BAND ? BA_SOLVER_BAND : BA_SOLVER_PCG);
+  h->last_band_w = bw;
+  h->last_s_blocks = (int)(w.s_len / 36);
   const int schur = pick_schur(h, w);
   LmInit li{h->prm.lambda0, h->prm.huber_delta, h->prm.chi2_thr, h->prm.lambda_up,
             h->prm.lambda_down, h->prm.lambda_min, h->prm.lambda_max, h->prm.accept_rtol};
@@ -496,7 +560,6 @@ extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     if (h->prm.profile) prof_collect(h);
     fill_report(h, h->h_ctl, report, BA_OK, ms, launches);
-    report->solver_used = sparse ? BA_SOLVER_PCG : BA_SOLVER_CHOLESKY;
     dump_dbg(h);
   }
   return BA_OK;
@@ -553,7 +616,6 @@ extern "C" int ba_solve_local_host(ba_handle* h, int32_t n_cam, int32_t n_pt, in
     int launches = 2 + h->prm.max_iter * (h->world > 1 ? 4 : 3);
     if (h->prm.profile) prof_collect(h);
     fill_report(h, h->h_ctl, report, BA_OK, ms, launches);
-    report->solver_used = want_sparse(h, n_cam) ? BA_SOLVER_PCG : BA_SOLVER_CHOLESKY;
   }
   return BA_OK;
 }

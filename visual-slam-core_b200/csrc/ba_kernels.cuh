@@ -33,6 +33,12 @@ struct Work {
   const int* bsr_col;                 // [nnzb]
   const int* bsr_tpos;                // [nnzb] position of the transposed block
   int bsr_W, nnzb;
+  // block-banded reduced camera matrix (sequential windows): S_band[I][d] = block (I, I-d), d = 0..band_w;
+  // band_w < 0 when the layout is not banded
+  int band_w;
+  double* band_L;                     // [n_cam][band_w+1][36] columns of the Cholesky factor
+  double* band_y;                     // [n]  L^-1 b
+  double* band_dinv;                  // [n]  1 / diag(L)
   size_t s_len;                       // doubles in S (dense packed: n_cam(n_cam+1)/2*36, sparse: nnzb*36)
   // block-Jacobi PCG workspace (sparse path)
   double* pcg_r; double* pcg_z; double* pcg_p[2]; double* pcg_Ap; double* pcg_Minv; double* pcg_acc;
@@ -64,6 +70,7 @@ __device__ __forceinline__ int bsr_find(const Work& w, int a, int b) {
 }
 // where block (a, b), a >= b, of the reduced camera matrix is accumulated
 __device__ __forceinline__ double* s_block_ptr(const Work& w, int a, int b) {
+  if (w.band_w >= 0) return w.S + ((size_t)a * (w.band_w + 1) + (a - b)) * 36;
   if (w.bsr_bits == nullptr) return w.S + s_block_off(a, b);
   return w.S + (size_t)bsr_find(w, a, b) * 36;
 }
@@ -84,6 +91,10 @@ int launch_symbolic_count(const Work& w, unsigned* bits, int* wpre, int* row_nnz
 int launch_symbolic_fill(const Work& w, int* col_idx, int* tpos, cudaStream_t s);
 int pcg_grid_size(int n_cam, int sm_count);
 int launch_rcs_pcg(const Work& w, int grid, cudaStream_t s);
+int launch_band_width(const Work& w, int* out, cudaStream_t s);
+int launch_rcs_band(const Work& w, cudaStream_t s);
+int configure_band();
+int band_max_w();
 int launch_backsub(const Work& w, int sm_count, cudaStream_t s);
 int launch_accept(const Work& w, cudaStream_t s);
 int launch_finalize(const Work& w, double* R_out, double* t_out, double* X_out,

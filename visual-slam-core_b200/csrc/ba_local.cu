@@ -476,6 +476,8 @@ int configure_kernels() {
   cudaError_t e = cudaFuncSetAttribute(k_rcs_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kSolveSmemMax);
   if (e != cudaSuccess) return (int)e;
+  int r = configure_band();
+  if (r != 0) return r;
   return configure_tiled();
 }
 

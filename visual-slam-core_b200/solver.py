@@ -29,7 +29,7 @@ class LMConfig:
     lambda_max: float = 1e8
     accept_rtol: float = 1e-8
     max_iter: int = 10
-    solver: str = "auto"        # auto | cholesky | pcg
+    solver: str = "auto"        # auto | cholesky | pcg | band
     schur: str = "auto"         # auto | scatter | tiled
     pcg_max_iter: int = 500
     pcg_tol: float = 1e-10
@@ -43,7 +43,7 @@ class LMConfig:
         p.lambda_min, p.lambda_max = self.lambda_min, self.lambda_max
         p.accept_rtol = self.accept_rtol
         p.max_iter = int(self.max_iter)
-        p.solver_kind = {"auto": 0, "cholesky": 1, "pcg": 2}[self.solver]
+        p.solver_kind = {"auto": 0, "cholesky": 1, "pcg": 2, "band": 3}[self.solver]
         p.schur_kind = {"auto": 0, "scatter": 1, "tiled": 2}[self.schur]
         p.pcg_max_iter, p.pcg_tol = int(self.pcg_max_iter), float(self.pcg_tol)
         p.use_graph = 1 if self.use_graph else 0
@@ -172,7 +172,9 @@ class LocalBASolver:
             pcg_iters=np.array(rep.pcg_iters[:k], dtype=np.int32),
             n_iter=k, gpu_ms=float(rep.gpu_ms), n_launches=int(rep.n_launches),
             extra=dict(ms_linearize=float(rep.ms_linearize), ms_solve=float(rep.ms_solve),
-                       ms_backsub=float(rep.ms_backsub), ms_other=float(rep.ms_other)))
+                       ms_backsub=float(rep.ms_backsub), ms_other=float(rep.ms_other),
+                       solver_used={1: "cholesky", 2: "pcg", 3: "band"}.get(int(rep.solver_used), "?"),
+                       band_width=int(rep.band_width), s_blocks=int(rep.s_blocks)))
 
     # ------------------------------------------------------------------ local BA, torch CUDA tensors
     def solve_local_device(self, intr, R, t, fixed, X, obs_cam, obs_pt, obs_uv, pt_offsets,
