@@ -57,7 +57,12 @@ enum {
   BA_SOLVER_BAND = 3       /* block-banded S + direct banded Cholesky (co-visibility bandwidth <= 32 keyframes) */
 };
 /* schur_kind */
-enum { BA_SCHUR_AUTO = 0, BA_SCHUR_SCATTER = 1, BA_SCHUR_TILED = 2 };
+enum {
+  BA_SCHUR_AUTO = 0,     /* = BA_SCHUR_STREAM */
+  BA_SCHUR_SCATTER = 1,  /* warp per point, one float64 RED per entry (no ordering requirement) */
+  BA_SCHUR_TILED = 2,    /* round-1 v2 kernel: thread-owned blocks over a slot table */
+  BA_SCHUR_STREAM = 3    /* compact block lists, Q lanes per block, rows sorted by camera */
+};
 
 typedef struct ba_params {
   double huber_delta;   /* config.optimization.huber_delta, torch_optimizer.py:108 */

@@ -62,7 +62,7 @@ def _check(p, res, ref, gauge_free=False):
                 x_max=float(np.abs(res.X - ref.X).max()))
 
 
-@pytest.mark.parametrize("schur", ["scatter", "tiled"])
+@pytest.mark.parametrize("schur", ["scatter", "tiled", "stream"])
 @pytest.mark.parametrize("name,seed", [("T0", 1), ("T1", 2), ("T2", 3), ("T2", 4), ("C1", 0)])
 def test_lm_trajectory_matches_oracle(name, seed, schur):
     p = synth.make_problem(name, seed=seed)
@@ -76,7 +76,7 @@ def test_lm_trajectory_matches_oracle(name, seed, schur):
     assert info["cost_rel"] < 1e-9
 
 
-@pytest.mark.parametrize("schur", ["scatter", "tiled"])
+@pytest.mark.parametrize("schur", ["scatter", "tiled", "stream"])
 @pytest.mark.parametrize("name,seed,lam", [("T0", 1, 1e-4), ("T1", 2, 1e-2), ("T2", 3, 1e-6)])
 def test_reduced_camera_system_matches_oracle(name, seed, lam, schur):
     """S (before damping of the pose blocks), b and diag(U) of one linearisation."""
@@ -104,7 +104,7 @@ def test_reduced_camera_system_matches_oracle(name, seed, lam, schur):
     assert cost == pytest.approx(lin["cost"], rel=1e-13)
 
 
-@pytest.mark.parametrize("schur", ["tiled", "scatter"])
+@pytest.mark.parametrize("schur", ["tiled", "scatter", "stream"])
 @pytest.mark.parametrize("solver_kind", ["pcg", "auto"])
 @pytest.mark.parametrize("name,seed", [("T3", 1), ("T4", 2)])
 def test_large_window_matches_oracle(name, seed, schur, solver_kind):
@@ -153,6 +153,51 @@ def test_wide_covisibility_falls_back_to_pcg_and_band_refuses():
     res = s.solve_local(p.intr, p.R, p.t, p.fixed, p.X, p.obs_cam, p.obs_pt, p.obs_uv, p.pt_offsets)
     s.close()
     assert res.extra["solver_used"] == "pcg"
+    _check(p, res, _oracle(p))
+
+
+@pytest.mark.parametrize("schur", ["scatter", "stream"])
+def test_repeated_observations_and_oversized_points(schur):
+    """The same (point, keyframe) observed several times (multi-sensor keyframes,
+    torch_optimizer.py:86-95 iterates every cam_id) and one point with more observations than a
+    staged chunk holds: one linearisation against the oracle."""
+    p = synth.make_problem(n_cam=14, n_pt=400, k_mean=6.0, k_max=14, seed=11)
+    rng = np.random.default_rng(3)
+    from visual_slam_core_b200.synth import _project, INTR
+    new_cam, new_pt, new_uv = [], [], []
+    for j in range(p.n_pt):
+        sl = slice(p.pt_offsets[j], p.pt_offsets[j + 1])
+        cams, uvs = p.obs_cam[sl].tolist(), p.obs_uv[sl].tolist()
+        if j % 7 == 0 and cams:                       # a second sensor sees the point again
+            cams = cams + [cams[0], cams[-1]]
+            uvs = uvs + [[uvs[0][0] + 0.5, uvs[0][1] - 0.25], [uvs[-1][0] - 1.0, uvs[-1][1] + 0.75]]
+        if j == 123:                                  # 700 observations of one point
+            rep = rng.integers(0, p.n_cam, 700)
+            u, v, _ = _project(p.R_true[rep], p.t_true[rep], np.broadcast_to(p.X_true[j], (700, 3)), INTR)
+            cams = rep.tolist()
+            uvs = (np.stack([u, v], 1) + rng.normal(0, 1.0, (700, 2))).astype(np.float32).tolist()
+        new_cam += cams; new_pt += [j] * len(cams); new_uv += uvs
+    p.obs_cam = np.array(new_cam, np.int32); p.obs_pt = np.array(new_pt, np.int32)
+    p.obs_uv = np.array(new_uv, np.float32).reshape(-1, 2)
+    p.pt_offsets = np.concatenate([[0], np.cumsum(np.bincount(p.obs_pt, minlength=p.n_pt))]).astype(np.int32)
+    lam = 1e-3
+    s = LocalBASolver(LMConfig(schur=schur))
+    S, b, dU, cost = s.debug_linearize(p.intr, p.R, p.t, p.fixed, p.X, p.obs_cam, p.obs_pt, p.obs_uv,
+                                       p.pt_offsets, lam)
+    res = s.solve_local(p.intr, p.R, p.t, p.fixed, p.X, p.obs_cam, p.obs_pt, p.obs_uv, p.pt_offsets)
+    s.close()
+    lin = O.linearize(p.intr, p.R, p.t, p.fixed, p.X, p.obs_cam, p.obs_pt, p.obs_uv, 5.0)
+    S_ref, b_ref, _, _, _ = O.build_rcs(lin, lam, p.fixed, p.obs_cam.astype(np.int64),
+                                        p.obs_pt.astype(np.int64), p.n_cam, p.n_pt)
+    n = 6 * p.n_cam
+    S_dev = np.tril(S)
+    S_dev[np.arange(n), np.arange(n)] += O.damp_diag(dU, lam)
+    fx = np.nonzero(np.repeat(p.fixed != 0, 6))[0]
+    S_dev[fx, :] = 0; S_dev[:, fx] = 0; S_dev[fx, fx] = 1.0
+    assert np.abs(S_dev - np.tril(S_ref)).max() <= 1e-11 * np.abs(S_ref).max()
+    free = np.repeat(p.fixed == 0, 6)
+    np.testing.assert_allclose(b[free], b_ref[free], rtol=1e-9, atol=1e-9 * np.abs(b_ref).max())
+    assert cost == pytest.approx(lin["cost"], rel=1e-13)
     _check(p, res, _oracle(p))
 
 

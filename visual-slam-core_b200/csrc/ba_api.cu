@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -406,9 +407,14 @@ static int make_work(ba_handle* h, int n_cam, int n_pt, int n_obs, const double 
 
 static int pick_schur(const ba_handle* h, const Work& w) {
   int kind = h->prm.schur_kind;
-  if (kind == BA_SCHUR_AUTO) kind = tiled_supported(w.n_cam) ? BA_SCHUR_TILED : BA_SCHUR_SCATTER;
-  if (kind == BA_SCHUR_TILED && !tiled_supported(w.n_cam)) kind = BA_SCHUR_SCATTER;
+  if (kind == BA_SCHUR_AUTO) kind = BA_SCHUR_STREAM;
   return kind;
+}
+
+static int launch_linearize(const Work& w, int schur, int sm_count, cudaStream_t s) {
+  if (schur == BA_SCHUR_STREAM) return launch_linearize_stream(w, sm_count, s);
+  if (schur == BA_SCHUR_TILED) return launch_linearize_tiled(w, sm_count, s);
+  return launch_linearize_scatter(w, sm_count, s);
 }
 
 // enqueue the LM iterations (no init / finalize); returns kernels launched or < 0
@@ -419,8 +425,7 @@ static int enqueue_lm_loop(ba_handle* h, const Work& w, int schur, cudaStream_t 
   const int pcg_grid = sparse ? pcg_grid_size(w.n_cam, h->sm_count) : 0;
   for (int it = 0; it < h->prm.max_iter; ++it) {
     prof_mark(h, TAG_LIN, s);
-    launches += (schur == BA_SCHUR_TILED) ? launch_linearize_tiled(w, h->sm_count, s)
-                                          : launch_linearize_scatter(w, h->sm_count, s);
+    launches += launch_linearize(w, schur, h->sm_count, s);
     if (h->world > 1) {
       prof_mark(h, TAG_OTHER, s);
       int r = g_nccl.allreduce(w.S, w.S, nred, kNcclDouble, kNcclSum, h->comm, s);
@@ -452,11 +457,14 @@ static void dump_dbg(ba_handle* h) {
   std::vector<long long> hb(4096);
   cudaMemcpy(hb.data(), h->dbg.p, sizeof(long long) * 4096, cudaMemcpyDeviceToHost);
   fprintf(stderr, "[ba dbg]");
+  std::vector<std::pair<long long, long long>> ev;      // (clock, tag) in time order
+  for (int i = 0; i < 2000; ++i)
+    if (hb[2 + 2 * i] != 0) ev.push_back({hb[2 + 2 * i], hb[1 + 2 * i]});
+  std::sort(ev.begin(), ev.end());
   long long prev = 0;
-  for (int i = 0; i < 2000; ++i) {
-    if (hb[2 + 2 * i] == 0) continue;
-    fprintf(stderr, " %lld:%lld", hb[1 + 2 * i], prev ? hb[2 + 2 * i] - prev : 0LL);
-    prev = hb[2 + 2 * i];
+  for (auto& e : ev) {
+    fprintf(stderr, " %lld:%lld", e.second, prev ? e.first - prev : 0LL);
+    prev = e.first;
   }
   fprintf(stderr, "\n");
 }
@@ -657,8 +665,7 @@ extern "C" int ba_debug_linearize(ba_handle* h, int32_t n_cam, int32_t n_pt, int
   LmInit li{lambda, h->prm.huber_delta, h->prm.chi2_thr, h->prm.lambda_up,
             h->prm.lambda_down, h->prm.lambda_min, h->prm.lambda_max, h->prm.accept_rtol};
   launch_init(w, cam_R, cam_t, X, li, s);
-  if (pick_schur(h, w) == BA_SCHUR_TILED) launch_linearize_tiled(w, h->sm_count, s);
-  else launch_linearize_scatter(w, h->sm_count, s);
+  launch_linearize(w, pick_schur(h, w), h->sm_count, s);
   const size_t n = (size_t)w.n;
   if (S_host) CK(cudaMemcpyAsync(S_host, w.S, sizeof(double) * s_doubles(w.n_cam), cudaMemcpyDeviceToHost, s));
   if (b_host) CK(cudaMemcpyAsync(b_host, w.b, sizeof(double) * n, cudaMemcpyDeviceToHost, s));

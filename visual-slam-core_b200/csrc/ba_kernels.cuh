@@ -83,6 +83,8 @@ int launch_init(const Work& w, const double* R_in, const double* t_in, const dou
                 const LmInit& p, cudaStream_t s);
 int launch_linearize_scatter(const Work& w, int sm_count, cudaStream_t s);
 int launch_linearize_tiled(const Work& w, int sm_count, cudaStream_t s);
+int launch_linearize_stream(const Work& w, int sm_count, cudaStream_t s);
+int configure_stream();
 int launch_rcs_cholesky(const Work& w, cudaStream_t s);
 int launch_symbolic(const Work& w, unsigned* bits, int* wpre, int* row_nnz, int* row_ptr, cudaStream_t s);
 int launch_symbolic_mark(const Work& w, unsigned* bits, cudaStream_t s);

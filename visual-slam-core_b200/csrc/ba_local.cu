@@ -478,6 +478,8 @@ int configure_kernels() {
   if (e != cudaSuccess) return (int)e;
   int r = configure_band();
   if (r != 0) return r;
+  r = configure_stream();
+  if (r != 0) return r;
   return configure_tiled();
 }
 
