@@ -62,7 +62,7 @@ def _check(p, res, ref, gauge_free=False):
                 x_max=float(np.abs(res.X - ref.X).max()))
 
 
-@pytest.mark.parametrize("schur", ["scatter", "tiled", "stream"])
+@pytest.mark.parametrize("schur", ["scatter", "tiled", "stream", "mma"])
 @pytest.mark.parametrize("name,seed", [("T0", 1), ("T1", 2), ("T2", 3), ("T2", 4), ("C1", 0)])
 def test_lm_trajectory_matches_oracle(name, seed, schur):
     p = synth.make_problem(name, seed=seed)
@@ -76,7 +76,7 @@ def test_lm_trajectory_matches_oracle(name, seed, schur):
     assert info["cost_rel"] < 1e-9
 
 
-@pytest.mark.parametrize("schur", ["scatter", "tiled", "stream"])
+@pytest.mark.parametrize("schur", ["scatter", "tiled", "stream", "mma"])
 @pytest.mark.parametrize("name,seed,lam", [("T0", 1, 1e-4), ("T1", 2, 1e-2), ("T2", 3, 1e-6)])
 def test_reduced_camera_system_matches_oracle(name, seed, lam, schur):
     """S (before damping of the pose blocks), b and diag(U) of one linearisation."""
@@ -104,7 +104,7 @@ def test_reduced_camera_system_matches_oracle(name, seed, lam, schur):
     assert cost == pytest.approx(lin["cost"], rel=1e-13)
 
 
-@pytest.mark.parametrize("schur", ["tiled", "scatter", "stream"])
+@pytest.mark.parametrize("schur", ["tiled", "scatter", "stream", "mma"])
 @pytest.mark.parametrize("solver_kind", ["pcg", "auto"])
 @pytest.mark.parametrize("name,seed", [("T3", 1), ("T4", 2)])
 def test_large_window_matches_oracle(name, seed, schur, solver_kind):
@@ -156,7 +156,7 @@ def test_wide_covisibility_falls_back_to_pcg_and_band_refuses():
     _check(p, res, _oracle(p))
 
 
-@pytest.mark.parametrize("schur", ["scatter", "stream"])
+@pytest.mark.parametrize("schur", ["scatter", "stream", "mma"])
 def test_repeated_observations_and_oversized_points(schur):
     """The same (point, keyframe) observed several times (multi-sensor keyframes,
     torch_optimizer.py:86-95 iterates every cam_id) and one point with more observations than a

@@ -407,11 +407,17 @@ static int make_work(ba_handle* h, int n_cam, int n_pt, int n_obs, const double 
 
 static int pick_schur(const ba_handle* h, const Work& w) {
   int kind = h->prm.schur_kind;
-  if (kind == BA_SCHUR_AUTO) kind = BA_SCHUR_STREAM;
+  if (kind == BA_SCHUR_AUTO) {
+    // lane-per-keyframe staging needs the cameras of consecutive points inside a 20-keyframe window:
+    // whole local windows, or sequential (banded) co-visibility
+    const bool seq = w.band_w >= 0 && w.band_w < mma_window();
+    kind = (w.n_cam <= mma_window() || seq) ? BA_SCHUR_MMA : BA_SCHUR_STREAM;
+  }
   return kind;
 }
 
 static int launch_linearize(const Work& w, int schur, int sm_count, cudaStream_t s) {
+  if (schur == BA_SCHUR_MMA) return launch_linearize_mma(w, sm_count, s);
   if (schur == BA_SCHUR_STREAM) return launch_linearize_stream(w, sm_count, s);
   if (schur == BA_SCHUR_TILED) return launch_linearize_tiled(w, sm_count, s);
   return launch_linearize_scatter(w, sm_count, s);

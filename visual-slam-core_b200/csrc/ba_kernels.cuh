@@ -85,6 +85,9 @@ int launch_linearize_scatter(const Work& w, int sm_count, cudaStream_t s);
 int launch_linearize_tiled(const Work& w, int sm_count, cudaStream_t s);
 int launch_linearize_stream(const Work& w, int sm_count, cudaStream_t s);
 int configure_stream();
+int launch_linearize_mma(const Work& w, int sm_count, cudaStream_t s);
+int configure_mma();
+int mma_window();
 int launch_rcs_cholesky(const Work& w, cudaStream_t s);
 int launch_symbolic(const Work& w, unsigned* bits, int* wpre, int* row_nnz, int* row_ptr, cudaStream_t s);
 int launch_symbolic_mark(const Work& w, unsigned* bits, cudaStream_t s);

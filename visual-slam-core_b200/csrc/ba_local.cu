@@ -480,6 +480,8 @@ int configure_kernels() {
   if (r != 0) return r;
   r = configure_stream();
   if (r != 0) return r;
+  r = configure_mma();
+  if (r != 0) return r;
   return configure_tiled();
 }
 

@@ -1,0 +1,587 @@
+// Linearise + Schur on the FP64 tensor path (mma.sync m8n8k4 f64), the default for local windows
+// and for sequential (banded) co-visibility.  One CTA per SM, 640 threads, warp specialised:
+//
+//  * 12 STAGING warps (120 registers each, setmaxnreg).  A warp linearises one point at a time with
+//    lane a <-> camera (base + a) of a window of kWin keyframes: the point block V_j / g_l is a
+//    butterfly reduction over the lanes, every lane then holds C_j (C C^T = (V + lambda diag V)^-1),
+//    forms Y_aj = W_aj C_j (6x3) in registers and
+//      - writes it into a DENSE shared-memory panel  Yt[3 p + d][6 a + r]  (zeros where camera a does
+//        not see point p),
+//      - adds the camera's own sums U_a = sum J_p^T w J_p and b_a into a PRIVATE shared-memory column
+//        (a lane always serves the same camera: no atomics, no pose gathers, no slot tables on the
+//        per-observation path).
+//    Offsets, camera indices, pixels and coordinates of the NEXT point are prefetched while the
+//    current one is linearised.
+//  * 8 MMA warps (56 registers each).  The Schur complement of a panel of 12 points is the symmetric
+//    product  S -= Yt^T Yt : a warp owns two 24x24 macro tiles (4 x 4 cameras, 3 x 3 mma tiles) whose
+//    accumulators live in a thread-private fragment layout in shared memory between panels (two
+//    conflict-free 64-bit accesses per element and panel), so the register file goes to the
+//    latency-bound staging warps.  Operand fragments are 64-bit shared loads, conflict-free because
+//    the panel stride is 8 (mod 16) doubles.
+//  * The panel is double buffered between the two groups with named barriers (full / empty), so
+//    global-load latency, FP64 FMAs and DMMAs overlap without a CTA-wide barrier.
+//
+//  window "whole"   (n_cam <= kWin): base = 0, one flush of float64 REDs per CTA.
+//  window "sliding" (any n_cam): the window follows the points (which must arrive roughly sorted
+//    along the trajectory); accumulators are flushed only when the window has to move, and macro
+//    tiles whose cameras do not appear in a panel are skipped.
+// A point outside the window, with repeated (point, keyframe) observations or with more than 32
+// observations goes through the warp-per-point scatter routine (ba_scatter.cuh) on the spot.
+#include <stdlib.h>
+
+#include "ba_kernels.cuh"
+#include "ba_scatter.cuh"
+
+namespace ba {
+
+namespace {
+
+constexpr int kSW = 12;                 // staging warps (3 warpgroups)
+constexpr int kXW = 8;                  // mma warps (2 warpgroups)
+constexpr int kMT = (kSW + kXW) * 32;
+constexpr int kST = kSW * 32;
+constexpr int kWin = 20;                // cameras per window: 5 macro rows of 4 cameras
+constexpr int kG = kWin / 4;
+constexpr int kNMacro = kG * (kG + 1) / 2;   // 15 macro tiles of the lower triangle
+constexpr int kYS = 6 * kWin;           // panel row stride in doubles: 120 = 8 (mod 16)
+constexpr int kPts = kSW;               // points per panel (one per staging warp)
+constexpr int kK = 3 * kPts;            // panel rows (36: nine mma k-steps)
+constexpr int kPS = 13;                 // pose stride in shared memory (odd: conflict-free per-lane rows)
+constexpr int kScratch = 32 * 19 + 16;  // scatter_point: sW[32][19] + sCam[32]
+constexpr int kBarFull = 1, kBarEmpty = 3, kBarStage = 5;
+constexpr int kNone = 0x7fffffff;
+
+static_assert(kYS % 16 == 8, "panel stride must be 8 mod 16 doubles for conflict-free fragments");
+static_assert(kNMacro <= 2 * kXW, "two macro tiles per mma warp");
+static_assert(kK % 4 == 0, "whole k-steps");
+
+struct PanelFlags {
+  int rebase;          // a point did not fit the window
+  int cmin;            // smallest camera among the points of the panel
+};
+
+struct __align__(16) MmaSmem {
+  double Yt[2][kK * kYS];
+  double Sacc[kNMacro][18][32];   // macro-tile accumulators in mma fragment order, private per thread
+  double Uacc[kSW][27][kWin];     // per staging warp and camera lane: U lower (21) + b (6); private
+  double scr[kScratch];           // scatter_point scratch (one warp at a time, see lock)
+  double pose[32 * kPS];
+  double red[kSW];
+  float2 suv[kSW][32];
+  int slot[kSW][32];
+  PanelFlags pf[3];            // panel n uses pf[n % 3]: written while staging n, read after it, cleared one panel later
+  int pbase[2];                // window base the panel in buffer b was staged with
+  unsigned pmask[2][kPts];     // cameras (window-relative bits) with a non-zero row block, per staged point
+  int lock;
+};
+
+__device__ __forceinline__ int lower_bound_off(const int* __restrict__ off, int n, int target) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(off + mid) < target) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// 1/sqrt(a): hardware approximation (MUFU.RSQ64H, ~2^-22) + two Newton steps
+__device__ __forceinline__ double fast_rsqrt(double a) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double e = fma(-a * r, r, 1.0);
+    r = fma(0.5 * r, e, r);
+  }
+  return r;
+}
+template <int kId, int kN>
+__device__ __forceinline__ void bar_sync() {
+  asm volatile("bar.sync %0, %1;" ::"n"(kId), "n"(kN) : "memory");
+}
+template <int kId, int kN>
+__device__ __forceinline__ void bar_arrive() {
+  asm volatile("bar.arrive %0, %1;" ::"n"(kId), "n"(kN) : "memory");
+}
+
+// the rare fallback stays out of line so that its registers do not count against the hot loops
+__device__ __noinline__ void scatter_point_cold(const Work& w, int j, int lane, double lambda, double delta,
+                                                const double* __restrict__ pose, const double* __restrict__ X,
+                                                double* scratch, int* lock, double* cost) {
+  if (lane == 0) {
+    while (atomicCAS(lock, 0, 1) != 0) {}
+  }
+  __syncwarp();
+  double (*sW)[19] = reinterpret_cast<double (*)[19]>(scratch);
+  int* sCam = reinterpret_cast<int*>(scratch + 32 * 19);
+  double c = 0.0;
+  scatter_point(w, j, lane, lambda, delta, pose, X, sW, sCam, c);
+  *cost += c;
+  __syncwarp();
+  if (lane == 0) { __threadfence_block(); atomicExch(lock, 0); }
+}
+
+// what a staging warp holds about a point before it linearises it
+struct PointIn {
+  int o0, k;          // observation range (k < 0: no point)
+  int cam;            // camera of observation o0 + lane (kNone past the end)
+  float2 uv;          // its pixel
+  double X0, X1, X2;
+};
+
+__device__ __forceinline__ void load_range(const Work& w, int j, int p_hi, int& o0, int& k) {
+  if (j < p_hi) {
+    o0 = __ldg(w.pt_off + j);
+    k = __ldg(w.pt_off + j + 1) - o0;
+  } else {
+    o0 = 0; k = -1;
+  }
+}
+__device__ __forceinline__ void load_point(const Work& w, const double* __restrict__ X, int j, int lane, PointIn& in) {
+  in.cam = kNone;
+  in.uv = make_float2(0.f, 0.f);
+  in.X0 = in.X1 = in.X2 = 0.0;
+  if (in.k >= 0) {
+    if (lane < in.k) {
+      in.cam = __ldg(w.obs_cam + in.o0 + lane);
+      in.uv = __ldg(reinterpret_cast<const float2*>(w.obs_uv) + in.o0 + lane);
+    }
+    in.X0 = X[3 * (size_t)j]; in.X1 = X[3 * (size_t)j + 1]; in.X2 = X[3 * (size_t)j + 2];
+  }
+}
+
+// clock64 trace of one chosen thread of CTA 0 (BA_DBG_TIMES=1)
+__device__ __forceinline__ void mark(const Work& w, bool who, int slot, int tag) {
+  if (w.dbg && blockIdx.x == 0 && who && slot < 2000) {
+    w.dbg[1 + 2 * slot] = tag;
+    w.dbg[2 + 2 * slot] = clock64();
+  }
+}
+
+__device__ __forceinline__ void tile_of(int t, int& I, int& J) {
+  I = 0;
+  while (t > I) { t -= I + 1; ++I; }
+  J = t;
+}
+
+// one macro tile over one panel: accumulators come from and go back to their shared-memory slots
+__device__ __forceinline__ void mma_macro_tile(const double* __restrict__ Y, int ksteps, int I, int J,
+                                               double* __restrict__ acc /* [18][32] + lane */) {
+  double c[9][2];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) { c[q][0] = acc[(2 * q) * 32]; c[q][1] = acc[(2 * q + 1) * 32]; }
+  const double* pa = Y + 24 * I;
+  const double* pb = Y + 24 * J;
+#pragma unroll 3
+  for (int kk = 0; kk < ksteps; ++kk) {
+    double a[3], b[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { a[i] = pa[8 * i]; b[i] = pb[8 * i]; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) dmma(c[3 * i + j][0], c[3 * i + j][1], a[i], b[j]);
+    pa += 4 * kYS;
+    pb += 4 * kYS;
+  }
+#pragma unroll
+  for (int q = 0; q < 9; ++q) { acc[(2 * q) * 32] = c[q][0]; acc[(2 * q + 1) * 32] = c[q][1]; }
+}
+
+// macro tile -> float64 REDs; entries that are exactly zero belong to absent blocks and are skipped
+__device__ __forceinline__ void flush_macro_tile(const Work& w, int base, int mI, int mJ, int lane,
+                                                 double* __restrict__ acc) {
+#pragma unroll 1
+  for (int e = 0; e < 18; ++e) {
+    const double v = acc[e * 32];
+    if (v == 0.0) continue;
+    acc[e * 32] = 0.0;
+    const int t = e >> 1, h = e & 1;
+    const int i = t / 3, j = t - 3 * i;
+    const int m = 24 * mI + 8 * i + (lane >> 2);
+    const int n2 = 24 * mJ + 8 * j + 2 * (lane & 3) + h;
+    const int a = m / 6, r = m - 6 * a, b = n2 / 6, cc = n2 - 6 * b;
+    if (a > b || (a == b && cc <= r)) atomicAdd(s_block_ptr(w, base + a, base + b) + 6 * r + cc, -v);
+  }
+}
+
+}  // namespace
+
+template <bool kSliding>
+__global__ void __launch_bounds__(kMT, 1)
+k_linearize_mma(const __grid_constant__ Work w) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MmaSmem& sm = *reinterpret_cast<MmaSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  LmCtl* ctl = w.ctl;
+  const int cur = ctl->cur;
+  const double lambda = ctl->lambda, delta = ctl->huber_delta;
+  const double* __restrict__ pose = w.pose[cur];
+  const double* __restrict__ X = w.X[cur];
+
+  // this CTA's points: equal observation share
+  const long long nobs = w.n_obs;
+  const int t_lo = (int)(nobs * blockIdx.x / gridDim.x);
+  const int t_hi = (int)(nobs * (blockIdx.x + 1) / gridDim.x);
+  const int p_lo = (blockIdx.x == 0) ? 0 : lower_bound_off(w.pt_off, w.n_pt, t_lo);
+  const int p_hi = (blockIdx.x == gridDim.x - 1) ? w.n_pt : lower_bound_off(w.pt_off, w.n_pt, t_hi);
+  const int n_panels = (p_hi - p_lo + kPts - 1) / kPts;
+
+  if (wid >= kSW) {
+    // =============================== MMA warps ===============================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    const int mw = wid - kSW;
+    int I0, J0, I1, J1;
+    tile_of(mw, I0, J0);
+    const bool has1 = mw + kXW < kNMacro;
+    tile_of(has1 ? mw + kXW : mw, I1, J1);
+    double* acc0 = &sm.Sacc[mw][0][lane];
+    double* acc1 = &sm.Sacc[has1 ? mw + kXW : mw][0][lane];
+#pragma unroll
+    for (int e = 0; e < 18; ++e) { acc0[e * 32] = 0.0; if (has1) acc1[e * 32] = 0.0; }
+    const int foff = (lane & 3) * kYS + (lane >> 2);
+    int acc_base = -1;
+    const bool me = tid == kST;
+    mark(w, me, 200, 400);
+    for (int n = 0; n < n_panels; ++n) {
+      const int b = n & 1;
+      if (b == 0) bar_sync<kBarFull, kMT>(); else bar_sync<kBarFull + 1, kMT>();
+      if (n < 8) mark(w, me, 201 + 2 * n, 410 + n);
+      const int base_n = sm.pbase[b];
+      if (base_n != acc_base) {
+        if (acc_base >= 0) {
+          flush_macro_tile(w, acc_base, I0, J0, lane, acc0);
+          if (has1) flush_macro_tile(w, acc_base, I1, J1, lane, acc1);
+        }
+        acc_base = base_n;
+      }
+      const int npts = min(kPts, p_hi - (p_lo + n * kPts));
+      const int ksteps = (3 * npts + 3) >> 2;
+      bool do0 = true, do1 = has1;
+      if (kSliding) {
+        unsigned m = (lane < kPts) ? sm.pmask[b][lane] : 0u;
+        m = __reduce_or_sync(kFull, m);
+        unsigned rows = 0;                       // macro rows with at least one camera present
+#pragma unroll
+        for (int g = 0; g < kG; ++g) rows |= ((m >> (4 * g)) & 0xfu) ? (1u << g) : 0u;
+        do0 = ((rows >> I0) & 1u) && ((rows >> J0) & 1u);
+        do1 = has1 && ((rows >> I1) & 1u) && ((rows >> J1) & 1u);
+      }
+      const double* Y = sm.Yt[b] + foff;
+      if (do0) mma_macro_tile(Y, ksteps, I0, J0, acc0);
+      if (do1) mma_macro_tile(Y, ksteps, I1, J1, acc1);
+      if (n + 2 < n_panels) {
+        if (b == 0) bar_arrive<kBarEmpty, kMT>(); else bar_arrive<kBarEmpty + 1, kMT>();
+      }
+      if (n < 8) mark(w, me, 202 + 2 * n, 420 + n);
+    }
+    mark(w, me, 230, 430);
+    if (acc_base >= 0) {
+      flush_macro_tile(w, acc_base, I0, J0, lane, acc0);
+      if (has1) flush_macro_tile(w, acc_base, I1, J1, lane, acc1);
+    }
+    mark(w, me, 231, 431);
+    return;
+  }
+
+  // ================================= staging warps ===========================================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+  mark(w, tid == 0, 30, 300);
+  if (tid < 3) { sm.pf[tid].rebase = 0; sm.pf[tid].cmin = kNone; }
+  if (tid == 0) sm.lock = 0;
+  sm.slot[wid][lane] = -1;
+  int base = 0;
+  if (kSliding) {
+    // window start: the smallest camera of the first panel's observations
+    bar_sync<kBarStage, kST>();
+    if (p_lo < p_hi) {
+      const int q_hi = min(p_hi, p_lo + kPts);
+      const int o_a = __ldg(w.pt_off + p_lo), o_b = __ldg(w.pt_off + q_hi);
+      int c = kNone;
+      for (int o = o_a + tid; o < o_b && o < o_a + 8 * kST; o += kST) c = min(c, __ldg(w.obs_cam + o));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c = min(c, __shfl_xor_sync(kFull, c, o));
+      if (lane == 0 && c != kNone) atomicMin(&sm.pf[2].cmin, c);
+    }
+    bar_sync<kBarStage, kST>();
+    base = (sm.pf[2].cmin == kNone) ? 0 : sm.pf[2].cmin;
+    bar_sync<kBarStage, kST>();
+    if (tid == 0) sm.pf[2].cmin = kNone;
+  }
+
+  double* __restrict__ Ul = &sm.Uacc[wid][0][lane < kWin ? lane : 0];   // this lane's column of the private sums
+  if (lane < kWin) {
+#pragma unroll
+    for (int q = 0; q < 27; ++q) Ul[q * kWin] = 0.0;
+  }
+  double cost = 0.0;
+  bool cam_free = false;
+
+  auto load_window = [&]() {
+    // poses of the window into shared memory, one padded row per camera (staging group only)
+    for (int i = tid; i < 12 * kWin; i += kST) {
+      const int a = i / 12, q = i - 12 * a;
+      const int cam = base + a;
+      sm.pose[a * kPS + q] = (cam < w.n_cam) ? pose[12 * (size_t)cam + q] : 0.0;
+    }
+    const int cam = base + lane;
+    cam_free = (lane < kWin) && (cam < w.n_cam) && (w.fixed[cam] == 0);
+    bar_sync<kBarStage, kST>();
+  };
+
+  auto flush_cams = [&]() {
+    // per-camera sums: across the staging warps, then one RED per entry
+    bar_sync<kBarStage, kST>();
+    for (int t = tid; t < 27 * kWin; t += kST) {
+      const int q = t / kWin, a = t - q * kWin;
+      const int cam = base + a;
+      double s = 0.0;
+#pragma unroll
+      for (int ww = 0; ww < kSW; ++ww) { s += sm.Uacc[ww][q][a]; sm.Uacc[ww][q][a] = 0.0; }
+      if (cam >= w.n_cam || s == 0.0) continue;
+      if (q < 21) {
+        int r = 0, e = q;
+        while (e > r) { e -= r + 1; ++r; }
+        atomicAdd(s_block_ptr(w, cam, cam) + 6 * r + e, s);
+        if (e == r) atomicAdd(w.diagU + 6 * (size_t)cam + r, s);
+      } else {
+        atomicAdd(w.b + 6 * (size_t)cam + (q - 21), s);
+      }
+    }
+    bar_sync<kBarStage, kST>();
+  };
+
+  load_window();
+  mark(w, tid == 0, 31, 301);
+
+  // software pipeline over this warp's points j = p_lo + wid, + kSW, ...: ranges two ahead, data one ahead
+  PointIn in, nx;
+  int o0_2, k_2;
+  {
+    const int j0 = p_lo + wid;
+    load_range(w, j0, p_hi, in.o0, in.k);
+    load_point(w, X, j0, lane, in);
+    load_range(w, j0 + kSW, p_hi, nx.o0, nx.k);
+    load_range(w, j0 + 2 * kSW, p_hi, o0_2, k_2);
+  }
+  const double* __restrict__ P = sm.pose + lane * kPS;
+
+#pragma unroll 1
+  for (int n = 0; n < n_panels; ++n) {
+    const int b = n & 1;
+    const int fs = n % 3;
+    if (n >= 2) { if (b == 0) bar_sync<kBarEmpty, kMT>(); else bar_sync<kBarEmpty + 1, kMT>(); }
+    double* __restrict__ Y = sm.Yt[b];
+    const int slot = wid;
+    const int j = p_lo + n * kPts + slot;
+    // ---- prefetch: data of the next point, range of the one after ---------------------------
+    load_point(w, X, j + kSW, lane, nx);
+    int o0_3, k_3;
+    load_range(w, j + 3 * kSW, p_hi, o0_3, k_3);
+
+    unsigned present = 0u;
+    bool valid = in.k >= 0;
+    int ia = -1;
+    float2 uv = make_float2(0.f, 0.f);
+    if (valid) {
+      const int k = in.k;
+      bool ok = k <= 32;
+      int rel = -1;
+      __syncwarp();
+      if (ok && lane < k) {
+        rel = in.cam - base;
+        if (rel < 0 || rel >= kWin) ok = false;
+        else { sm.slot[wid][rel] = lane; sm.suv[wid][rel] = in.uv; }
+      }
+      __syncwarp();
+      if (rel >= 0 && rel < kWin && sm.slot[wid][rel] != lane) ok = false;     // repeated (point, keyframe)
+      ia = sm.slot[wid][lane];
+      uv = sm.suv[wid][lane];
+      ok = __all_sync(kFull, ok);
+      __syncwarp();
+      sm.slot[wid][lane] = -1;
+      if (kSliding && k > 0 && k <= 32) {
+        int c = in.cam;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c = min(c, __shfl_xor_sync(kFull, c, o));
+        if (lane == 0) { atomicMin(&sm.pf[fs].cmin, c); if (!ok) sm.pf[fs].rebase = 1; }
+      }
+      if (!ok) {
+        // out of the window / repeated / oversized: the scatter routine takes the point
+        scatter_point_cold(w, j, lane, lambda, delta, pose, X, sm.scr, &sm.lock, &cost);
+        ia = -1;
+        valid = false;
+      }
+    }
+    const bool seen = valid && ia >= 0;
+    const bool act = seen && cam_free;
+    double* dst = Y + (size_t)(3 * slot) * kYS + 6 * (lane < kWin ? lane : 0);
+    if (valid) {
+      // ---- phase 1: projection, weights, point block contributions ---------------------------
+      double Y0 = 0, Y1 = 0, Y2 = 0, ja = 0, jb = 0, jc = 0, jd = 0, ru = 0, rv = 0, wu = 0, wv = 0;
+      double V[6] = {0, 0, 0, 0, 0, 0}, gl[3] = {0, 0, 0};
+      if (seen) {
+        const double R0 = P[0], R1 = P[1], R2 = P[2], R3 = P[3], R4 = P[4], R5 = P[5], R6 = P[6], R7 = P[7], R8 = P[8];
+        Y0 = R0 * in.X0 + R1 * in.X1 + R2 * in.X2;
+        Y1 = R3 * in.X0 + R4 * in.X1 + R5 * in.X2;
+        Y2 = R6 * in.X0 + R7 * in.X1 + R8 * in.X2;
+        const double xc = Y0 + P[9], yc = Y1 + P[10], zc = Y2 + P[11];
+        const double iz = 1.0 / (zc + kDepthEps);
+        const double xz = xc * iz, yz = yc * iz;
+        ru = w.K.fx * xz + w.K.cx - (double)uv.x;
+        rv = w.K.fy * yz + w.K.cy - (double)uv.y;
+        wu = huber_w(ru, delta);
+        wv = huber_w(rv, delta);
+        ja = w.K.fx * iz; jc = -w.K.fx * xz * iz;
+        jb = w.K.fy * iz; jd = -w.K.fy * yz * iz;
+        const double lu0 = ja * R0 + jc * R6, lu1 = ja * R1 + jc * R7, lu2 = ja * R2 + jc * R8;
+        const double lv0 = jb * R3 + jd * R6, lv1 = jb * R4 + jd * R7, lv2 = jb * R5 + jd * R8;
+        const double ul0 = wu * lu0, ul1 = wu * lu1, ul2 = wu * lu2;
+        const double vl0 = wv * lv0, vl1 = wv * lv1, vl2 = wv * lv2;
+        V[0] = ul0 * lu0 + vl0 * lv0;
+        V[1] = ul0 * lu1 + vl0 * lv1;
+        V[2] = ul0 * lu2 + vl0 * lv2;
+        V[3] = ul1 * lu1 + vl1 * lv1;
+        V[4] = ul1 * lu2 + vl1 * lv2;
+        V[5] = ul2 * lu2 + vl2 * lv2;
+        gl[0] = ul0 * ru + vl0 * rv;
+        gl[1] = ul1 * ru + vl1 * rv;
+        gl[2] = ul2 * ru + vl2 * rv;
+        cost += huber_rho(ru, delta) + huber_rho(rv, delta);
+      }
+#pragma unroll
+      for (int q = 0; q < 6; ++q) V[q] = warp_sum(V[q]);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) gl[q] = warp_sum(gl[q]);
+      present = __ballot_sync(kFull, act);
+      if (act) {
+        // ---- phase 2: C_j with C C^T = (V + lambda diag V)^-1, z = C^T g_l ---------------------
+        V[0] += damp(V[0], lambda);
+        V[3] += damp(V[3], lambda);
+        V[5] += damp(V[5], lambda);
+        // LDL^T of V; V^-1 = M^T D^-1 M with M = L^-1 (unit lower) -> C = M^T D^-1/2 (upper);
+        // pivots through 1/sqrt (hardware seed + two Newton steps, no slow-path call): s = d^-1/2, 1/d = s^2
+        const double r0 = fast_rsqrt(V[0]);
+        const double i0 = r0 * r0;
+        const double l10 = V[1] * i0, l20 = V[2] * i0;
+        const double d1 = V[3] - l10 * V[1];
+        const double e1 = V[4] - l20 * V[1];
+        const double r1 = fast_rsqrt(d1);
+        const double i1 = r1 * r1;
+        const double l21 = e1 * i1;
+        const double d2 = V[5] - l20 * V[2] - l21 * e1;
+        const double r2 = fast_rsqrt(d2);
+        const bool pd = (V[0] > 0.0) && (d1 > 0.0) && (d2 > 0.0) && isfinite(r0) && isfinite(r1) && isfinite(r2);
+        const double c00 = pd ? r0 : 0.0, c11 = pd ? r1 : 0.0, c22 = pd ? r2 : 0.0;
+        const double c01 = -l10 * c11, c02 = (l10 * l21 - l20) * c22, c12 = -l21 * c22;
+        const double z0 = c00 * gl[0];
+        const double z1 = c01 * gl[0] + c11 * gl[1];
+        const double z2 = c02 * gl[0] + c12 * gl[1] + c22 * gl[2];
+        // ---- phase 3: pose rows, W = J_p^T w J_l, Y = W C, camera sums ------------------------
+        const double lu0 = ja * P[0] + jc * P[6], lu1 = ja * P[1] + jc * P[7], lu2 = ja * P[2] + jc * P[8];
+        const double lv0 = jb * P[3] + jd * P[6], lv1 = jb * P[4] + jd * P[7], lv2 = jb * P[5] + jd * P[8];
+        double pu[6], pv[6];
+        pu[0] = jc * Y1;             pu[1] = ja * Y2 - jc * Y0;  pu[2] = -ja * Y1;
+        pu[3] = ja;                  pu[4] = 0.0;                pu[5] = jc;
+        pv[0] = -jb * Y2 + jd * Y1;  pv[1] = -jd * Y0;           pv[2] = jb * Y0;
+        pv[3] = 0.0;                 pv[4] = jb;                 pv[5] = jd;
+        const double au = wu * ru, av = wv * rv;
+        int e2 = 0;
+        double yp[3];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          const double pa = wu * pu[r], pb = wv * pv[r];
+          const double w0 = pa * lu0 + pb * lv0;
+          const double w1 = pa * lu1 + pb * lv1;
+          const double w2 = pa * lu2 + pb * lv2;
+          const double y0 = w0 * c00;
+          const double y1 = w0 * c01 + w1 * c11;
+          const double y2 = w0 * c02 + w1 * c12 + w2 * c22;
+          if (r & 1) {
+            // panel row d, columns 6 a + r - 1, 6 a + r
+            *reinterpret_cast<double2*>(dst + r - 1) = make_double2(yp[0], y0);
+            *reinterpret_cast<double2*>(dst + kYS + r - 1) = make_double2(yp[1], y1);
+            *reinterpret_cast<double2*>(dst + 2 * kYS + r - 1) = make_double2(yp[2], y2);
+          } else {
+            yp[0] = y0; yp[1] = y1; yp[2] = y2;
+          }
+#pragma unroll
+          for (int c2 = 0; c2 <= r; ++c2, ++e2) Ul[e2 * kWin] += pa * pu[c2] + pb * pv[c2];
+          Ul[(21 + r) * kWin] += y0 * z0 + y1 * z1 + y2 * z2 - (au * pu[r] + av * pv[r]);
+        }
+      }
+    }
+    if (!act && lane < kWin) {
+      const double2 zz = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        double2* p2 = reinterpret_cast<double2*>(dst + d * kYS);
+        p2[0] = zz; p2[1] = zz; p2[2] = zz;
+      }
+    }
+    if (kSliding && lane == 0) sm.pmask[b][slot] = present;
+    // rotate the pipeline
+    in = nx;
+    nx.o0 = o0_2; nx.k = k_2;
+    o0_2 = o0_3; k_2 = k_3;
+
+    if (wid == 0 && lane == 0) sm.pbase[b] = base;
+    bool rebase = false;
+    int cmin = kNone;
+    if (kSliding) {
+      bar_sync<kBarStage, kST>();
+      cmin = sm.pf[fs].cmin;
+      rebase = sm.pf[fs].rebase != 0 && cmin != kNone && cmin != base;
+      const int fp = (fs == 0) ? 2 : fs - 1;            // flags of the previous panel: everyone has read them
+      if (tid == 0) { sm.pf[fp].rebase = 0; sm.pf[fp].cmin = kNone; }
+    }
+    __threadfence_block();
+    if (b == 0) bar_arrive<kBarFull, kMT>(); else bar_arrive<kBarFull + 1, kMT>();
+    if (n < 8) mark(w, tid == 0, 32 + n, 310 + n);
+    if (rebase) {
+      // the window has to move: flush this group's sums and restart at the panel's first camera;
+      // the mma warps flush their tiles when they see the new base on the next panel
+      flush_cams();
+      base = cmin;
+      load_window();
+    }
+  }
+  mark(w, tid == 0, 60, 330);
+  flush_cams();
+  mark(w, tid == 0, 61, 331);
+
+  cost = warp_sum(cost);
+  if (lane == 0) sm.red[wid] = cost;
+  bar_sync<kBarStage, kST>();
+  if (tid == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < kSW; ++i) s += sm.red[i];
+    if (s != 0.0) atomicAdd(w.cost_lin, s);
+  }
+}
+
+int configure_mma() {
+  const int bytes = (int)sizeof(MmaSmem);
+  cudaError_t e = cudaFuncSetAttribute(k_linearize_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linearize_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+int mma_window() { return kWin; }
+
+int launch_linearize_mma(const Work& w, int sm_count, cudaStream_t s) {
+  int blocks = sm_count;
+  const int by_pts = (w.n_pt + kPts - 1) / kPts;
+  if (blocks > by_pts) blocks = by_pts;
+  if (blocks < 1) blocks = 1;
+  if (w.n_cam <= kWin) k_linearize_mma<false><<<blocks, kMT, sizeof(MmaSmem), s>>>(w);
+  else k_linearize_mma<true><<<blocks, kMT, sizeof(MmaSmem), s>>>(w);
+  return 1;
+}
+
+}  // namespace ba
