@@ -78,3 +78,32 @@ def adam_local_ba(intr, R, t, fixed, X, obs_cam, obs_pt, obs_uv, n_iter: int, lr
         t_out = np.stack([ts[i].detach().numpy() for i in range(n_cam)])
         X_out = Xt.detach().numpy().copy()
     return dict(R=R_out, t=t_out, X=X_out, losses=losses, secs=secs)
+
+
+def adam_initial(intr, R_ref, t_ref, R_cur, t_cur, X_sel, uv_ref, uv_cur, n_iter: int, lr: float):
+    """Restatement of `TorchOptimizer.optimize_initial`'s loop (torch_optimizer.py:268-305): Adam on
+    the UNCONSTRAINED 3x3 `R_cur`, `t_cur` and the selected points, loss = SmoothL1(mean, beta = 1)
+    of the reference view + of the current view, depth clamped at 1e-8, float32.  Inputs are the
+    arrays the reference builds at :222-272 (see `packing.pack_initial`)."""
+    K = torch.tensor(np.array([[intr[0], 0, intr[2]], [0, intr[1], intr[3]], [0, 0, 1]]), dtype=torch.float32)
+    Rr = torch.tensor(np.asarray(R_ref), dtype=torch.float32)
+    tr = torch.tensor(np.asarray(t_ref), dtype=torch.float32)
+    Rc = torch.tensor(np.asarray(R_cur), dtype=torch.float32, requires_grad=True)
+    tc = torch.tensor(np.asarray(t_cur), dtype=torch.float32, requires_grad=True)
+    X = torch.tensor(np.asarray(X_sel, dtype=np.float32), requires_grad=True)
+    pr = torch.tensor(np.asarray(uv_ref, dtype=np.float32))
+    pc = torch.tensor(np.asarray(uv_cur, dtype=np.float32))
+    opt = torch.optim.Adam([Rc, tc, X], lr=lr)
+    loss_fn = torch.nn.SmoothL1Loss()
+    losses = []
+    for _ in range(n_iter):
+        opt.zero_grad()
+        Xr = (Rr @ X.T + tr.reshape(3, 1)).T
+        ur = (K @ (Xr / Xr[:, 2:].clamp(min=1e-8)).T).T[:, :2]
+        Xc = (Rc @ X.T + tc.reshape(3, 1)).T
+        uc = (K @ (Xc / Xc[:, 2:].clamp(min=1e-8)).T).T[:, :2]
+        loss = loss_fn(ur, pr) + loss_fn(uc, pc)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.item()))
+    return dict(R_cur=Rc.detach().numpy(), t_cur=tc.detach().numpy(), X=X.detach().numpy(), losses=losses)

@@ -195,8 +195,77 @@ def save_case(name, case, out):
     print("wrote", path, "obs", out["ref_obs"].shape[0], "loss0", out["loss0"])
 
 
+def run_reference_initial(ref, case, n_iter, lr):
+    """`TorchOptimizer.optimize_initial` (torch_optimizer.py:209-317) on the first two keyframes and
+    ALL points of the case, the way `Map.optimize_initial` (map/map.py:143-148) hands them over."""
+    cam, kfs, mps = to_reference_graph(ref, case)
+    tmp = tempfile.mkdtemp()
+    cfg = ref["Config"](optimization=ref["OptimizationConfig"](lr=lr, n_iter=n_iter))
+    opt = ref["TorchOptimizer"](cfg, device="cpu", log_dir=tmp)
+    ok = opt.optimize_initial(kfs, mps)
+    return dict(ok=ok, R_out=np.array([kf.R_w2c for kf in kfs]), t_out=np.array([kf.t_w2c for kf in kfs]),
+                X_out=np.array([m.position for m in mps]),
+                kf_ids=np.array([kf.keyframe_id for kf in kfs], dtype=np.int64))
+
+
+def save_initial(name, case, out, n_iter, lr):
+    n_all = case["n_all"]
+    kp_off = np.zeros(n_all + 1, dtype=np.int64)
+    kp_off[1:] = np.cumsum([len(k) for k in case["kps"]])
+    kp_flat = np.array([p for k in case["kps"] for p in k], dtype=np.float32).reshape(-1, 2)
+    ob_off = np.zeros(len(case["obs"]) + 1, dtype=np.int64)
+    ob_off[1:] = np.cumsum([len(o) for o in case["obs"]])
+    ob_flat = np.array([e for o in case["obs"] for e in o], dtype=np.int64).reshape(-1, 3)
+    path = os.path.join(HERE, f"ref_initial_{name}.npz")
+    np.savez_compressed(
+        path, intr=case["intr"], R=case["R"], t=case["t"], X=case["X"], n_kf=case["n_kf"],
+        kp_off=kp_off, kp_flat=kp_flat, ob_off=ob_off, ob_flat=ob_flat, kf_ids=out["kf_ids"],
+        ref_ok=out["ok"], ref_R_out=out["R_out"], ref_t_out=out["t_out"], ref_X_out=out["X_out"],
+        n_iter=n_iter, lr=lr)
+    print("wrote", path, "ok", out["ok"])
+
+
+def make_pose_only_golden():
+    """`estimate_motion_from_2d3d` (utils/motion_estimation.py:57-132) on synthetic frames: the
+    return tuple (shapes, dtypes, failure cases) and the pose OpenCV finds, as a sanity
+    cross-check of the pose-only LM (OpenCV minimises plain L2 after RANSAC, so only loosely comparable)."""
+    import cv2
+    from visual_slam.utils.motion_estimation import estimate_motion_from_2d3d
+    rng = np.random.default_rng(21)
+    fx = fy = 700.0
+    cx, cy = 640.0, 360.0
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    n = 300
+    Xw = np.stack([rng.uniform(-4, 4, n), rng.uniform(-2, 2, n), rng.uniform(6, 25, n)], axis=1)
+    R = rot_y(0.07).T
+    t = np.array([0.3, -0.05, 0.2])
+    Xc = Xw @ R.T + t
+    uv = np.stack([fx * Xc[:, 0] / Xc[:, 2] + cx, fy * Xc[:, 1] / Xc[:, 2] + cy], axis=1)
+    uv += rng.normal(0, 0.5, uv.shape)
+    out_idx = rng.choice(n, 30, replace=False)
+    uv[out_idx] += rng.normal(0, 40.0, (30, 2))
+    pts3d = Xw.astype(np.float32)
+    pts2d = uv.astype(np.float32)
+    cv2.setRNGSeed(42)
+    R_cv, t_cv, ok, inl = estimate_motion_from_2d3d(pts3d, pts2d, K, None, True)
+    few = estimate_motion_from_2d3d(pts3d[:3], pts2d[:3], K)
+    path = os.path.join(HERE, "ref_pose_only.npz")
+    np.savez_compressed(path, K=K, pts3d=pts3d, pts2d=pts2d, R_true=R, t_true=t, outliers=np.sort(out_idx),
+                        ref_R=R_cv, ref_t=t_cv, ref_ok=ok, ref_inliers=inl,
+                        ref_inliers_dtype=str(inl.dtype), ref_few_is_none=np.array([x is None for x in few[:2]] + [few[2] is False, few[3] is None]))
+    print("wrote", path, "ok", ok, "inliers", None if inl is None else inl.shape, inl.dtype)
+
+
 def main():
     ref = import_reference()
+    # two-view initial refinement (torch_optimizer.py:209-317): irregular observations included so the
+    # selection rule (:240-258) and the zip() write-back (:313-314) are exercised
+    for name, cs, n_iter, lr in [("a", dict(seed=31, n_kf=2, n_pt=60, n_extra_kf=1), 3, 1e-3),
+                                 ("few", dict(seed=32, n_kf=2, n_pt=6, n_extra_kf=0, irregular=False), 2, 1e-3)]:
+        case = build_case(**cs)
+        out = run_reference_initial(ref, case, n_iter, lr)
+        save_initial(name, case, out, n_iter, lr)
+    make_pose_only_golden()
     specs = [
         ("a", dict(seed=11, n_kf=4, n_pt=40, n_extra_kf=1), dict(n_iter=1, lr=1e-4, delta=5.0)),
         ("b", dict(seed=12, n_kf=6, n_pt=120, n_extra_kf=2), dict(n_iter=3, lr=1e-3, delta=5.0)),

@@ -1,0 +1,175 @@
+"""SURVEY 8f 'next' rows on the CPU: packer fast path (N1), two-view initial refinement (N2),
+pose-only call-site format (N3), outlier consumption (N4), the local-mapping call site (A8)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref_adam
+from visual_slam_core_b200 import B200Optimizer, handlers, motion, packing, refgraph, synth
+from visual_slam_core_b200.solver import SolveResult
+
+from helpers import GOLDEN, graph_from_golden, load_golden, window_points
+
+
+def _assert_same_window(a, b):
+    for f in ("intr", "R", "t", "fixed", "X", "obs_cam", "obs_pt", "obs_uv", "obs_cam_id", "pt_offsets"):
+        np.testing.assert_array_equal(getattr(a, f), getattr(b, f), err_msg=f)
+
+
+# ---------------------------------------------------------------------------------------- N1
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_observation_table_packs_like_the_reference_loop(name):
+    table = packing.ObservationTable(capacity=8)             # small: exercises growth
+    table.install(refgraph.KeyFrame)
+    try:
+        g = load_golden(name)
+        cam, kfs, mps = graph_from_golden(g)
+    finally:
+        table.uninstall()
+    window = kfs[: int(g["n_kf"])]
+    pts = window_points(window)
+    _assert_same_window(table.pack(window, pts), packing.pack_window(window, pts))
+    # a different window over the same table (keyframes 1..), gauge moves with it
+    if len(kfs) > 3:
+        w2 = kfs[1:]
+        p2 = window_points(w2)
+        _assert_same_window(table.pack(w2, p2), packing.pack_window(w2, p2))
+
+
+def test_observation_table_multi_sensor_order_and_removal():
+    table = packing.ObservationTable()
+    table.install(refgraph.KeyFrame)
+    try:
+        cam = refgraph.Camera(1280, 720, 700, 700, 640, 360)
+        kps = lambda n: [refgraph.KeyPoint(10.0 * i, 5.0 * i) for i in range(n)]
+        kfs = [refgraph.KeyFrame(cam, [kps(8), kps(8)], np.eye(3), np.zeros(3)) for _ in range(3)]
+        mps = [refgraph.MapPoint([0.1 * j, 0.0, 5.0]) for j in range(4)]
+        # interleaved insertion: the reference groups a point's observations by keyframe
+        kfs[0].add_map_point(0, 1, mps[0]); kfs[1].add_map_point(0, 2, mps[0]); kfs[0].add_map_point(1, 3, mps[0])
+        kfs[2].add_map_point(1, 0, mps[1]); kfs[0].add_map_point(0, 4, mps[1])
+        kfs[1].add_map_point(0, 5, mps[2]); kfs[1].add_map_point(0, 6, mps[2])      # second write: first wins
+        kfs[2].add_map_point(0, 7, mps[3]); kfs[1].add_map_point(1, 7, mps[3])
+        _assert_same_window(table.pack(kfs, mps), packing.pack_window(kfs, mps))
+        kfs[0].remove_map_point(0, 1)                                               # map/keyframe.py:93-100
+        _assert_same_window(table.pack(kfs, mps), packing.pack_window(kfs, mps))
+    finally:
+        table.uninstall()
+
+
+def test_fast_path_is_faster_on_a_real_window():
+    import time
+    p = synth.make_problem("T2", seed=3)
+    table = packing.ObservationTable()
+    table.install(refgraph.KeyFrame)
+    try:
+        cam, kfs, mps = refgraph.graph_from_problem(p)
+    finally:
+        table.uninstall()
+    pts = window_points(kfs)
+    t0 = time.perf_counter(); a = packing.pack_window(kfs, pts); t1 = time.perf_counter()
+    b = table.pack(kfs, pts); t2 = time.perf_counter()
+    _assert_same_window(b, a)
+    assert (t2 - t1) < (t1 - t0)
+
+
+# ---------------------------------------------------------------------------------------- N2
+def _initial_golden(name):
+    return np.load(os.path.join(GOLDEN, f"ref_initial_{name}.npz"))
+
+
+def test_initial_selection_and_adam_restatement_match_the_reference():
+    g = _initial_golden("a")
+    cam, kfs, mps = graph_from_golden(g)
+    pi = packing.pack_initial(kfs, mps)
+    assert bool(g["ref_ok"]) and len(pi.selected) >= packing.MIN_OBSERVATIONS
+    out = ref_adam.adam_initial(pi.window.intr, pi.window.R[0], pi.window.t[0], pi.window.R[1], pi.window.t[1],
+                                pi.window.X, pi.uv_ref, pi.uv_cur, n_iter=int(g["n_iter"]), lr=float(g["lr"]))
+    # the reference writes back kf_cur only (:308-311) ...
+    np.testing.assert_allclose(out["R_cur"], g["ref_R_out"][1], atol=2e-6)
+    np.testing.assert_allclose(out["t_cur"], g["ref_t_out"][1], atol=2e-6)
+    np.testing.assert_array_equal(g["ref_R_out"][0], g["R"][0])
+    # ... and pairs the selected points with the FIRST len(selected) map points (zip, :313-314)
+    n = len(pi.selected)
+    np.testing.assert_allclose(out["X"], g["ref_X_out"][:n], atol=2e-5)
+    np.testing.assert_array_equal(g["ref_X_out"][n:], g["X"][n:])
+    assert not np.array_equal(pi.selected, np.arange(n))      # the fixture does exercise the misalignment
+
+
+def test_initial_returns_false_on_few_points_like_the_reference():
+    g = _initial_golden("few")
+    cam, kfs, mps = graph_from_golden(g)
+    assert not bool(g["ref_ok"])
+    before = [m.position.copy() for m in mps], kfs[1].t_w2c.copy()
+    opt = B200Optimizer(log_dir=None)
+    assert opt.optimize_initial(kfs, mps) is False            # early return: no GPU needed
+    assert opt.optimize_initial(kfs[:1], mps) is False
+    assert opt.optimize_initial(kfs, []) is False
+    np.testing.assert_array_equal(kfs[1].t_w2c, before[1])
+    for m, x in zip(mps, before[0]):
+        np.testing.assert_array_equal(m.position, x)
+    np.testing.assert_array_equal(g["ref_X_out"], g["X"])       # and the reference left everything alone too
+
+
+# ---------------------------------------------------------------------------------------- N3
+def test_pose_only_call_site_failure_tuple_matches_the_reference():
+    g = np.load(os.path.join(GOLDEN, "ref_pose_only.npz"))
+    assert g["ref_few_is_none"].all()                           # reference: (None, None, False, None)
+    out = motion.refine_motion_from_2d3d(g["pts3d"][:3], g["pts2d"][:3], g["K"])
+    assert out == (None, None, False, None)
+    assert g["ref_inliers"].ndim == 2 and g["ref_inliers"].shape[1] == 1 and str(g["ref_inliers_dtype"]) == "int32"
+    with pytest.raises(ValueError):
+        motion.refine_motion_from_2d3d(g["pts3d"], g["pts2d"], g["K"], dist=np.array([0.1, 0, 0, 0, 0]))
+
+
+# ---------------------------------------------------------------------------------------- N4 / A8
+def test_mean_reprojection_error_matches_the_reference_formula():
+    p = synth.make_problem("T1", seed=4)
+    cam, kfs, mps = refgraph.graph_from_problem(p)
+    pts = window_points(kfs)
+    pw = packing.pack_window(kfs, pts)
+    # per keyframe as utils/geometry.py:232-247, weighted by count as map/map.py:137-141
+    tot, cnt = 0.0, 0
+    K = cam.K
+    for i, kf in enumerate(kfs):
+        sel = pw.obs_cam == i
+        if not sel.any():
+            continue
+        P3, P2 = pw.X[pw.obs_pt[sel]], pw.obs_uv[sel].astype(float)
+        pc = (pw.R[i] @ P3.T + pw.t[i].reshape(3, 1)).T
+        pn = pc[:, :2] / pc[:, 2:].clip(min=1e-8)
+        proj = (K @ np.concatenate([pn, np.ones((len(pn), 1))], axis=1).T).T[:, :2]
+        tot += float(np.mean(np.linalg.norm(P2 - proj, axis=1))) * len(P3)
+        cnt += len(P3)
+    assert handlers.mean_reprojection_error(pw) == pytest.approx(tot / cnt, rel=1e-6)
+
+
+def test_cull_bad_points_consumes_the_flags():
+    p = synth.make_problem("T0", seed=2)
+    cam, kfs, mps = refgraph.graph_from_problem(p)
+    pts = window_points(kfs)
+    pw = packing.pack_window(kfs, pts)
+    flags = np.zeros(pw.n_obs, dtype=np.uint8)
+    j_bad = int(np.argmax(np.diff(pw.pt_offsets) >= 2))
+    flags[pw.pt_offsets[j_bad]:pw.pt_offsets[j_bad + 1]] = 1    # every observation of one point
+    o_single = int(pw.pt_offsets[(j_bad + 1) % len(pts)])       # one observation of another
+    flags[o_single] = 1
+    opt = B200Optimizer(log_dir=None)
+    opt.last_packed = pw
+    opt.last_result = SolveResult(R=pw.R, t=pw.t, X=pw.X, flags=flags, cost_hist=np.zeros(1), cand_cost_hist=np.zeros(0),
+                                  lambda_hist=np.zeros(0), accepted=np.zeros(0, np.uint8), solve_fail=np.zeros(0, np.int32),
+                                  pcg_iters=np.zeros(0, np.int32), n_iter=0, gpu_ms=0.0, n_launches=0)
+    n_obs_before = sum(len(c) for m in pts for c in m.get_observations().values())
+    n_bad = opt.cull_bad_points(kfs, pts, min_observations=1)
+    assert n_bad == 1 and not pts[j_bad].is_valid()
+    assert pts[j_bad].get_observations() == {}
+    n_obs_after = sum(len(c) for m in pts for c in m.get_observations().values())
+    assert n_obs_before - n_obs_after == int(flags.sum())
+    kf = kfs[int(pw.obs_cam[o_single])]
+    assert pts[int(pw.obs_pt[o_single])] not in kf.get_all_mappoints().values()
+
+
+def test_local_optimize_call_site_needs_more_than_two_keyframes():
+    p = synth.make_problem("T0", seed=2)
+    cam, kfs, mps = refgraph.graph_from_problem(p)
+    assert handlers.local_optimize(B200Optimizer(log_dir=None), kfs[:2]) is False     # local_handler.py:37-40

@@ -8,6 +8,7 @@ objects; nothing is raised to the caller: any failure is logged and reported as 
 """
 from __future__ import annotations
 
+import dataclasses
 import logging
 import os
 import threading
@@ -92,6 +93,9 @@ class B200Optimizer(BaseOptimizer):
         self.last_result: Optional[SolveResult] = None
         self.last_packed: Optional[packing.PackedWindow] = None
         self.mark_bad_points = bool(getattr(getattr(config, "optimization", None), "mark_bad_points", False))
+        # optional incremental SoA mirror of the observation graph (packing.ObservationTable):
+        # when set, windows are packed from it instead of walking the object graph
+        self.table: Optional[packing.ObservationTable] = None
 
     def _get_solver(self) -> LocalBASolver:
         if self._solver is None:
@@ -104,7 +108,10 @@ class B200Optimizer(BaseOptimizer):
             self.logger.info(f"[B200Optimizer] keyframes - {len(keyframes)}, points - {len(map_points)}.")
             if not keyframes:
                 return False
-            pw = packing.pack_window(keyframes, map_points)      # snapshot up front, as :46-95
+            if self.table is not None:
+                pw = self.table.pack(keyframes, map_points)
+            else:
+                pw = packing.pack_window(keyframes, map_points)  # snapshot up front, as :46-95
             self.logger.info(f"[B200Optimizer] observations - {pw.n_obs}.")
             if pw.n_obs < packing.MIN_OBSERVATIONS:              # :99-101: False, nothing mutated
                 self.logger.warning("[B200Optimizer] too few observations for local optimisation.")
@@ -149,9 +156,74 @@ class B200Optimizer(BaseOptimizer):
         return self.optimize_local(keyframes, map_points)
 
     def optimize_initial(self, keyframes: List[Any], map_points: List[Any]) -> bool:
-        """Two-view refinement (reference: torch_optimizer.py:209-317) on the same LM solver:
-        first keyframe fixed, second free, points free, local-BA objective."""
-        if len(keyframes) < 2 or len(map_points) == 0:     # :215-217
-            self.logger.warning("[B200Optimizer] not enough data for optimize_initial")
+        """Two-view refinement (reference: torch_optimizer.py:209-317) on the LM solver.
+
+        Kept from the reference: `kf_ref, kf_cur = keyframes[:2]`, reference view fixed; only points
+        seen in BOTH views with `cam_id == 0` and in-range keypoints take part (`:240-258`); fewer
+        than 10 of them -> `False`, nothing mutated (`:265-267`); the objective is the sum over both
+        views of SmoothL1(beta = 1) = per-component Huber with delta = 1 px (`:282,296-298`; the
+        reference's mean reduction only rescales it).  Deliberately different: the
+        reference optimises the nine entries of `R_cur` freely, so its result is not a rotation
+        (`:228,284`), and its write-back pairs the selected points with the FIRST `len(selected)`
+        entries of `map_points` (`zip`, `:313-314`); here `R_cur` stays on SO(3) and every selected
+        point gets its own refined position.  The reference writes back `kf_cur` only (`:308-311`).
+        """
+        try:
+            if len(keyframes) < 2 or len(map_points) == 0:     # :215-217
+                self.logger.warning("[B200Optimizer] not enough data for optimize_initial")
+                return False
+            pi = packing.pack_initial(keyframes, map_points)
+            if len(pi.selected) < packing.MIN_OBSERVATIONS:    # :265-267
+                self.logger.warning("[B200Optimizer] too few observations for optimize_initial.")
+                return False
+            pw = pi.window
+            lm = dataclasses.replace(self._lm, huber_delta=1.0)
+            with self._lock:
+                solver = self._get_solver()
+                solver.set_config(lm)
+                try:
+                    res = solver.solve_local(pw.intr, pw.R, pw.t, pw.fixed, pw.X, pw.obs_cam, pw.obs_pt,
+                                             pw.obs_uv, pw.pt_offsets)
+                finally:
+                    solver.set_config(self._lm)
+            if not (np.isfinite(res.R).all() and np.isfinite(res.t).all() and np.isfinite(res.X).all()):
+                self.logger.error("[B200Optimizer] non-finite result; nothing written back.")
+                return False
+            n = 2 * len(pi.selected)
+            self.logger.info(f"[Initial BA] points={len(pi.selected)}, loss {res.cost_hist[0] / n:.4f} -> "
+                             f"{res.cost_hist[-1] / n:.4f} (SmoothL1 mean per view pair)")
+            keyframes[1].set_pose_Rt(np.array(res.R[1], dtype=np.float64),
+                                     np.array(res.t[1], dtype=np.float64).reshape(3, 1))
+            for j, pos in zip(pi.selected, res.X):
+                map_points[int(j)].update_position(np.asarray(pos))
+            self.last_result, self.last_packed = res, pw
+            return True
+        except Exception as e:
+            self.logger.error(f"[B200Optimizer] optimize_initial failed: {e!r}")
             return False
-        return self.optimize_local(list(keyframes[:2]), map_points)
+
+    # ------------------------------------------------------------------------------ outliers -> map
+    def cull_bad_points(self, keyframes: List[Any], map_points: List[Any], min_observations: int = 2) -> int:
+        """What the stub `LocalHandler.cull_bad_points` (`handlers/local_handler.py:79-80`) was waiting
+        for: drop the observations flagged by the last `optimize_local` over the same window
+        (`KeyFrame.remove_map_point`, `map/keyframe.py:93-100`, which also removes the point's
+        observation) and `mark_as_bad()` (`map/map_point.py:75-78`) the points left with fewer than
+        `min_observations` in-window observations.  Returns the number of points marked bad."""
+        res, pw = self.last_result, self.last_packed
+        if res is None or pw is None or res.flags is None or len(map_points) != pw.X.shape[0] \
+                or len(keyframes) != pw.R.shape[0] or pw.obs_cam_id.shape[0] != res.flags.shape[0]:
+            return 0
+        flagged = np.flatnonzero(res.flags)
+        for o in flagged:
+            kf, mp, cam_id = keyframes[int(pw.obs_cam[o])], map_points[int(pw.obs_pt[o])], int(pw.obs_cam_id[o])
+            ob = mp.get_observations().get(kf.keyframe_id, {})
+            if cam_id in ob and hasattr(kf, "remove_map_point"):
+                kf.remove_map_point(cam_id, ob[cam_id])
+        left = np.bincount(pw.obs_pt, weights=(res.flags == 0).astype(np.float64), minlength=len(map_points))
+        had = np.diff(pw.pt_offsets)
+        n_bad = 0
+        for j in np.flatnonzero((had > 0) & (left < min_observations)):
+            map_points[int(j)].mark_as_bad()
+            n_bad += 1
+        self.logger.info(f"[B200Optimizer] culled {len(flagged)} observations, marked {n_bad} points bad.")
+        return n_bad

@@ -15,6 +15,7 @@ Mirrored surface (reference file:line):
   MapPoint.position / get_observations / update_position / mark_as_bad / is_valid
                                             map/map_point.py:28,45-47,61-63,75-89
   Observations.add semantics (first write wins)            map/observation.py:10-22
+  KeyFrame.remove_map_point / MapPoint.remove_observation  map/keyframe.py:93-100, map/observation.py:32-50
   Map.optimize_local (collect + dedup by id)               map/map.py:150-171
 """
 from __future__ import annotations
@@ -65,6 +66,20 @@ class MapPoint:
         with self._lock:
             return {kf: cams.copy() for kf, cams in self._obs.items()}
 
+    def remove_observation(self, kf_id: int, cam_id: Optional[int] = None) -> bool:
+        with self._lock:                                   # map/observation.py:32-50
+            if kf_id not in self._obs:
+                return False
+            if cam_id is None:
+                self._obs.pop(kf_id, None)
+                return True
+            if cam_id in self._obs[kf_id]:
+                del self._obs[kf_id][cam_id]
+                if not self._obs[kf_id]:
+                    del self._obs[kf_id]
+                return True
+            return False
+
     def update_position(self, new_position):
         with self._lock:
             self.position = np.asarray(new_position, dtype=float)
@@ -113,6 +128,13 @@ class KeyFrame:
         with self._lock:
             self.map_points[(cam_id, kp_idx)] = mp
             mp.add_observation(self.keyframe_id, cam_id, kp_idx)
+
+    def remove_map_point(self, cam_id: int, kp_idx: int):
+        with self._lock:                                   # map/keyframe.py:93-100
+            key = (cam_id, kp_idx)
+            if key in self.map_points:
+                self.map_points[key].remove_observation(self.keyframe_id, cam_id)
+                del self.map_points[key]
 
     def get_all_mappoints(self) -> Dict[Tuple[int, int], MapPoint]:
         with self._lock:
