@@ -147,6 +147,9 @@ static int ensure(ba_handle* h, DevBuf& b, size_t bytes) {
   return BA_OK;
 }
 
+namespace ba { int mma_max_active_clusters(int cluster); }
+extern "C" int ba_debug_max_active_clusters(int cluster) { return ba::mma_max_active_clusters(cluster); }
+
 extern "C" int ba_version(void) { return 100; }
 
 extern "C" const char* ba_error_string(int code) {

@@ -56,6 +56,23 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// butterfly sums of a symmetric 3x3 (6) and a 3-vector side by side: nine independent
+// shuffle/add chains per step instead of nine dependent five-step chains one after the other
+__device__ __forceinline__ void warp_sum_6_3(double (&V)[6], double (&g)[3]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double tv[6], tg[3];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) tv[q] = __shfl_xor_sync(kFull, V[q], o);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) tg[q] = __shfl_xor_sync(kFull, g[q], o);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) V[q] += tv[q];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) g[q] += tg[q];
+  }
+}
+
 // sin(x)/x with a Taylor branch below 1e-4 (same as oracle/lm_oracle.py:sinc)
 __device__ __forceinline__ double sinc(double x) {
   double x2 = x * x;

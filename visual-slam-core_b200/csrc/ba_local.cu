@@ -544,10 +544,7 @@ k_backsub(Work w) {
         for (int r = 0; r < 3; ++r) q[r] += au * ol.lu[r] + av * ol.lv[r];
       }
     }
-#pragma unroll
-    for (int r = 0; r < 6; ++r) V[r] = warp_sum(V[r]);
-#pragma unroll
-    for (int r = 0; r < 3; ++r) q[r] = warp_sum(q[r]);
+    warp_sum_6_3(V, q);
     V[0] += damp(V[0], lambda);
     V[3] += damp(V[3], lambda);
     V[5] += damp(V[5], lambda);

@@ -27,6 +27,7 @@
 //    tiles whose cameras do not appear in a panel are skipped.
 // A point outside the window, with repeated (point, keyframe) observations or with more than 32
 // observations goes through the warp-per-point scatter routine (ba_scatter.cuh) on the spot.
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 #include "ba_kernels.cuh"
@@ -49,6 +50,7 @@ constexpr int kK = 3 * kPts;            // panel rows (36: nine mma k-steps)
 constexpr int kPS = 13;                 // pose stride in shared memory (odd: conflict-free per-lane rows)
 constexpr int kScratch = 32 * 19 + 16;  // scatter_point: sW[32][19] + sCam[32]
 constexpr int kBarFull = 1, kBarEmpty = 3, kBarStage = 5;
+constexpr int kCluster = 2;             // whole-window mode: CTAs of a cluster add their tiles through DSMEM before the REDs
 constexpr int kNone = 0x7fffffff;
 
 static_assert(kYS % 16 == 8, "panel stride must be 8 mod 16 doubles for conflict-free fragments");
@@ -154,12 +156,14 @@ __device__ __forceinline__ void load_point(const Work& w, const double* __restri
   }
 }
 
-// clock64 trace of one chosen thread of CTA 0 (BA_DBG_TIMES=1)
+// clock64 trace of one chosen thread of CTA 0 (compile with -DBA_MMA_TRACE, run with BA_DBG_TIMES=1)
 __device__ __forceinline__ void mark(const Work& w, bool who, int slot, int tag) {
+#ifdef BA_MMA_TRACE
   if (w.dbg && blockIdx.x == 0 && who && slot < 2000) {
     w.dbg[1 + 2 * slot] = tag;
     w.dbg[2 + 2 * slot] = clock64();
   }
+#endif
 }
 
 __device__ __forceinline__ void tile_of(int t, int& I, int& J) {
@@ -171,12 +175,13 @@ __device__ __forceinline__ void tile_of(int t, int& I, int& J) {
 // one macro tile over one panel: accumulators come from and go back to their shared-memory slots
 __device__ __forceinline__ void mma_macro_tile(const double* __restrict__ Y, int ksteps, int I, int J,
                                                double* __restrict__ acc /* [18][32] + lane */) {
+  const bool diag = I == J;
   double c[9][2];
 #pragma unroll
   for (int q = 0; q < 9; ++q) { c[q][0] = acc[(2 * q) * 32]; c[q][1] = acc[(2 * q + 1) * 32]; }
   const double* pa = Y + 24 * I;
   const double* pb = Y + 24 * J;
-#pragma unroll 3
+#pragma unroll 1
   for (int kk = 0; kk < ksteps; ++kk) {
     double a[3], b[3];
 #pragma unroll
@@ -184,7 +189,8 @@ __device__ __forceinline__ void mma_macro_tile(const double* __restrict__ Y, int
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-      for (int j = 0; j < 3; ++j) dmma(c[3 * i + j][0], c[3 * i + j][1], a[i], b[j]);
+      for (int j = 0; j < 3; ++j)
+        if (j <= i || !diag) dmma(c[3 * i + j][0], c[3 * i + j][1], a[i], b[j]);   // diagonal macro tile: lower part only
     pa += 4 * kYS;
     pb += 4 * kYS;
   }
@@ -195,8 +201,11 @@ __device__ __forceinline__ void mma_macro_tile(const double* __restrict__ Y, int
 // macro tile -> float64 REDs; entries that are exactly zero belong to absent blocks and are skipped
 __device__ __forceinline__ void flush_macro_tile(const Work& w, int base, int mI, int mJ, int lane,
                                                  double* __restrict__ acc) {
+  // CTAs start at different entries so that they do not all hit the same addresses at the same time
+  const int rot = blockIdx.x % 18;
 #pragma unroll 1
-  for (int e = 0; e < 18; ++e) {
+  for (int e0 = 0; e0 < 18; ++e0) {
+    const int e = (e0 + rot >= 18) ? e0 + rot - 18 : e0 + rot;
     const double v = acc[e * 32];
     if (v == 0.0) continue;
     acc[e * 32] = 0.0;
@@ -207,6 +216,38 @@ __device__ __forceinline__ void flush_macro_tile(const Work& w, int base, int mI
     const int a = m / 6, r = m - 6 * a, b = n2 / 6, cc = n2 - 6 * b;
     if (a > b || (a == b && cc <= r)) atomicAdd(s_block_ptr(w, base + a, base + b) + 6 * r + cc, -v);
   }
+}
+
+// Whole-window mode, all 640 threads of every CTA of the cluster: the CTA pair's macro-tile accumulators
+// (same window base 0) are summed through distributed shared memory, each CTA takes half of the
+// entries and issues ONE float64 RED per entry for the whole cluster.
+__device__ __forceinline__ void cluster_flush(const Work& w, MmaSmem& sm, int tid) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  cluster.sync();                                   // every CTA's accumulators are complete
+  const unsigned rank = cluster.block_rank();
+  constexpr int kTotal = kNMacro * 18 * 32;
+  constexpr int kShare = (kTotal + kCluster - 1) / kCluster;
+  const double* src[kCluster];
+#pragma unroll
+  for (int q = 0; q < kCluster; ++q) src[q] = cluster.map_shared_rank(&sm.Sacc[0][0][0], q);
+  const int lo = rank * kShare, hi = min(kTotal, lo + kShare);
+  for (int idx = lo + tid; idx < hi; idx += kMT) {
+    double v = 0.0;
+#pragma unroll
+    for (int q = 0; q < kCluster; ++q) v += src[q][idx];
+    if (v == 0.0) continue;
+    const int t = idx / 576, e = (idx - 576 * t) >> 5, lane = idx & 31;
+    int mI, mJ;
+    tile_of(t, mI, mJ);
+    const int tt = e >> 1, h = e & 1;
+    const int i = tt / 3, j = tt - 3 * i;
+    const int m = 24 * mI + 8 * i + (lane >> 2);
+    const int n2 = 24 * mJ + 8 * j + 2 * (lane & 3) + h;
+    const int a = m / 6, r = m - 6 * a, b = n2 / 6, cc = n2 - 6 * b;
+    if (a > b || (a == b && cc <= r)) atomicAdd(s_block_ptr(w, a, b) + 6 * r + cc, -v);
+  }
+  cluster.sync();                                   // nobody leaves while its shared memory is being read
 }
 
 }  // namespace
@@ -280,10 +321,17 @@ k_linearize_mma(const __grid_constant__ Work w) {
       if (n < 8) mark(w, me, 202 + 2 * n, 420 + n);
     }
     mark(w, me, 230, 430);
-    if (acc_base >= 0) {
-      flush_macro_tile(w, acc_base, I0, J0, lane, acc0);
-      if (has1) flush_macro_tile(w, acc_base, I1, J1, lane, acc1);
+    if (kSliding) {
+      if (acc_base >= 0) {
+        const bool swap = has1 && ((blockIdx.x / 18) & 1);
+        if (swap) flush_macro_tile(w, acc_base, I1, J1, lane, acc1);
+        flush_macro_tile(w, acc_base, I0, J0, lane, acc0);
+        if (has1 && !swap) flush_macro_tile(w, acc_base, I1, J1, lane, acc1);
+      }
+      mark(w, me, 231, 431);
+      return;
     }
+    cluster_flush(w, sm, tid);
     mark(w, me, 231, 431);
     return;
   }
@@ -336,7 +384,8 @@ k_linearize_mma(const __grid_constant__ Work w) {
   auto flush_cams = [&]() {
     // per-camera sums: across the staging warps, then one RED per entry
     bar_sync<kBarStage, kST>();
-    for (int t = tid; t < 27 * kWin; t += kST) {
+    for (int t0 = tid; t0 < 27 * kWin; t0 += kST) {
+      const int t = (t0 + 67 * (int)blockIdx.x) % (27 * kWin);      // CTAs start at different entries
       const int q = t / kWin, a = t - q * kWin;
       const int cam = base + a;
       double s = 0.0;
@@ -453,10 +502,7 @@ k_linearize_mma(const __grid_constant__ Work w) {
         gl[2] = ul2 * ru + vl2 * rv;
         cost += huber_rho(ru, delta) + huber_rho(rv, delta);
       }
-#pragma unroll
-      for (int q = 0; q < 6; ++q) V[q] = warp_sum(V[q]);
-#pragma unroll
-      for (int q = 0; q < 3; ++q) gl[q] = warp_sum(gl[q]);
+      warp_sum_6_3(V, gl);     // butterfly over the lanes, the nine sums side by side
       present = __ballot_sync(kFull, act);
       if (act) {
         // ---- phase 2: C_j with C C^T = (V + lambda diag V)^-1, z = C^T g_l ---------------------
@@ -563,6 +609,7 @@ k_linearize_mma(const __grid_constant__ Work w) {
     for (int i = 0; i < kSW; ++i) s += sm.red[i];
     if (s != 0.0) atomicAdd(w.cost_lin, s);
   }
+  if (!kSliding) cluster_flush(w, sm, tid);
 }
 
 int configure_mma() {
@@ -574,13 +621,47 @@ int configure_mma() {
 
 int mma_window() { return kWin; }
 
+// how many clusters of the whole-window kernel can be resident at once (diagnostics)
+int mma_max_active_clusters(int cluster) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(148 / cluster * cluster);
+  cfg.blockDim = dim3(kMT);
+  cfg.dynamicSmemBytes = sizeof(MmaSmem);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = -1;
+  if (cudaOccupancyMaxActiveClusters(&n, k_linearize_mma<false>, &cfg) != cudaSuccess) return -1;
+  return n;
+}
+
 int launch_linearize_mma(const Work& w, int sm_count, cudaStream_t s) {
   int blocks = sm_count;
   const int by_pts = (w.n_pt + kPts - 1) / kPts;
   if (blocks > by_pts) blocks = by_pts;
   if (blocks < 1) blocks = 1;
-  if (w.n_cam <= kWin) k_linearize_mma<false><<<blocks, kMT, sizeof(MmaSmem), s>>>(w);
-  else k_linearize_mma<true><<<blocks, kMT, sizeof(MmaSmem), s>>>(w);
+  if (w.n_cam <= kWin) {
+    blocks = (blocks + kCluster - 1) / kCluster * kCluster;      // CTAs without points only join the flush
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(kMT);
+    cfg.dynamicSmemBytes = sizeof(MmaSmem);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, k_linearize_mma<false>, w) != cudaSuccess) return -1;
+  } else {
+    k_linearize_mma<true><<<blocks, kMT, sizeof(MmaSmem), s>>>(w);
+  }
   return 1;
 }
 

@@ -59,10 +59,7 @@ __device__ __forceinline__ void scatter_point(const Work& w, int j, int lane, do
       cost += huber_rho(ol.ru, delta) + huber_rho(ol.rv, delta);
     }
   }
-#pragma unroll
-  for (int q = 0; q < 6; ++q) V[q] = warp_sum(V[q]);
-#pragma unroll
-  for (int q = 0; q < 3; ++q) gl[q] = warp_sum(gl[q]);
+  warp_sum_6_3(V, gl);
   V[0] += damp(V[0], lambda);
   V[3] += damp(V[3], lambda);
   V[5] += damp(V[5], lambda);
