@@ -273,17 +273,18 @@ def run_b200(args, rank, local_rank, world):
         prof.set_config(LMConfig(profile=True, **lmcfg))
     else:
         prof = LocalBASolver(LMConfig(profile=True, **lmcfg), device=local_rank)
-    acc = np.zeros(4)
+    acc = np.zeros(5)
     n_prof = 5 if not sharded else 2
     for i in range(n_prof + 2):
         R.copy_(R0); t.copy_(t0); X.copy_(X0)
         r = prof.solve_local_device(p.intr, R, t, fixed, X, oc, op, uv, off, flags, stream=stream.cuda_stream, sync=True)
         if i >= 2:
-            acc += np.array([r.ms_linearize, r.ms_solve, r.ms_backsub, r.ms_other])
+            acc += np.array([r.ms_linearize, r.ms_solve, r.ms_backsub, r.ms_other, r.ms_comm])
     acc /= n_prof
     pcg_iters = [int(v) for v in r.pcg_iters[:max_iter]]
     k_ms = {"linearize_schur": acc[0] / max_iter, "rcs_solve": acc[1] / max_iter,
-            "backsub_cost": acc[2] / max_iter, "init_finalize_per_step": acc[3]}
+            "backsub_cost": acc[2] / max_iter, "init_finalize_per_step": acc[3],
+            "nccl_allreduce": acc[4] / max_iter}
     b_rjs, b_iter = algorithmic_bytes(p.n_cam, p.n_pt, p.n_obs, dense=p.n_cam <= 38, nnzb=33 * p.n_cam)
     peak, peak_src = hbm_peak()
     dom = max(("linearize_schur", "rcs_solve", "backsub_cost"), key=lambda k: k_ms[k])
@@ -294,6 +295,11 @@ def run_b200(args, rank, local_rank, world):
             traffic = json.load(f).get(args.config, {}).get("linearize_schur")
     except Exception:
         pass
+    k_obs = np.diff(p.pt_offsets).astype(np.float64)
+    flops = 300.0 * p.n_obs + 216.0 * float((k_obs * k_obs).sum())       # SURVEY 8d-D4 "algorithmic flops"
+    fp64_peak = 36.6                                                     # TFLOP/s, scripts/fp64_peak.cu on this pool's B200
+    fp64_tf = flops / (k_ms["linearize_schur"] * 1e-3) / 1e12
+    resident = b_iter < 100e6
     roofline = {"bound": "hbm", "kernel": "k_linearize (residual+Jacobian+Schur)", "achieved": lin_gbs, "peak": peak,
                 "unit": "GB/s", "frac": lin_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": b_rjs, "launch_ms": k_ms["linearize_schur"],
@@ -301,7 +307,11 @@ def run_b200(args, rank, local_rank, world):
                 "whole_iteration": {"algorithmic_bytes": b_iter,
                                     "achieved": b_iter / (ms_max / 1e3 / (args.steps * max_iter)) / 1e9,
                                     "frac": b_iter / (ms_max / 1e3 / (args.steps * max_iter)) / 1e9 / peak},
-                "note": "window is L2-resident (working set << 126 MB L2): latency/atomics-bound, see DESIGN.md"}
+                "fp64": {"algorithmic_flop_per_launch": flops, "achieved_tflops": fp64_tf, "peak_tflops": fp64_peak,
+                         "frac": fp64_tf / fp64_peak,
+                         "note": "all arithmetic is float64 (vector FMA + mma.m8n8k4.f64); measured peak of scripts/fp64_peak.cu"},
+                "note": ("window is L2-resident (working set << 126 MB L2): FP64-latency bound, see DESIGN.md" if resident else
+                         "float64 arithmetic puts the kernel's floor at the FP64 pipe, not at HBM: see roofline.fp64 and DESIGN.md")}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -314,7 +324,7 @@ def run_b200(args, rank, local_rank, world):
                        f"points sharded over {world} GPUs, NCCL all-reduce of the reduced camera system" if sharded
                        else f"{world} independent windows, one per GPU (replicas)"),
                    "pcg": {"tol": args.pcg_tol, "iterations": pcg_iters} if p.n_cam > 38 else None,
-                   "l2": "flushed between steps (256 MiB write); inside a step the window stays L2-resident by construction",
+                   "l2": "flushed between steps (256 MiB write)" + ("; inside a step the window stays L2-resident by construction" if resident else ""),
                    "schur": args.schur},
         "obs_per_s_residual_jacobian_schur": p.n_obs / (k_ms["linearize_schur"] * 1e-3) * world,
         "shard_observations": p.n_obs,

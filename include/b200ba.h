@@ -99,9 +99,10 @@ typedef struct ba_report {
   float ms_linearize;                   /* profile=1 only: summed device time per kernel class */
   float ms_solve;
   float ms_backsub;
-  float ms_other;                       /* init + finalize (+ collectives when sharded) */
+  float ms_other;                       /* init + finalize */
   int32_t band_width;                   /* BA_SOLVER_BAND: co-visibility bandwidth in keyframes, else -1 */
   int32_t s_blocks;                     /* 6x6 blocks of the reduced camera matrix that are stored / all-reduced */
+  float ms_comm;                        /* profile=1, sharded: NCCL all-reduces (reduced camera system, candidate cost + accept) */
 } ba_report;
 
 typedef struct ba_handle ba_handle;

@@ -101,10 +101,10 @@ struct ba_handle {
   std::vector<cudaEvent_t> prof_ev;
   std::vector<int> prof_tag;
   int prof_n = 0;
-  float prof_ms[4] = {0, 0, 0, 0};
+  float prof_ms[5] = {0, 0, 0, 0, 0};
 };
 
-enum { TAG_LIN = 0, TAG_SOLVE = 1, TAG_BACK = 2, TAG_OTHER = 3 };
+enum { TAG_LIN = 0, TAG_SOLVE = 1, TAG_BACK = 2, TAG_OTHER = 3, TAG_COMM = 4 };
 
 static void prof_mark(ba_handle* h, int tag, cudaStream_t s) {
   if (!h->prm.profile) return;
@@ -120,7 +120,7 @@ static void prof_mark(ba_handle* h, int tag, cudaStream_t s) {
 }
 
 static void prof_collect(ba_handle* h) {
-  for (int i = 0; i < 4; ++i) h->prof_ms[i] = 0.f;
+  for (int i = 0; i < 5; ++i) h->prof_ms[i] = 0.f;
   for (int i = 0; i + 1 < h->prof_n; ++i) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]) == cudaSuccess)
@@ -436,7 +436,7 @@ static int enqueue_lm_loop(ba_handle* h, const Work& w, int schur, cudaStream_t 
     prof_mark(h, TAG_LIN, s);
     launches += launch_linearize(w, schur, h->sm_count, s);
     if (h->world > 1) {
-      prof_mark(h, TAG_OTHER, s);
+      prof_mark(h, TAG_COMM, s);
       int r = g_nccl.allreduce(w.S, w.S, nred, kNcclDouble, kNcclSum, h->comm, s);
       if (r != 0) { h->err = std::string("ncclAllReduce(S): ") + (g_nccl.errstr ? g_nccl.errstr(r) : "?"); return BA_ERR_NCCL; }
     }
@@ -452,7 +452,7 @@ static int enqueue_lm_loop(ba_handle* h, const Work& w, int schur, cudaStream_t 
     prof_mark(h, TAG_BACK, s);
     launches += launch_backsub(w, h->sm_count, s);
     if (h->world > 1) {
-      prof_mark(h, TAG_OTHER, s);
+      prof_mark(h, TAG_COMM, s);
       int r = g_nccl.allreduce(w.cost_cand, w.cost_cand, 1, kNcclDouble, kNcclSum, h->comm, s);
       if (r != 0) { h->err = std::string("ncclAllReduce(cost): ") + (g_nccl.errstr ? g_nccl.errstr(r) : "?"); return BA_ERR_NCCL; }
       launches += launch_accept(w, s);
@@ -501,6 +501,7 @@ static void fill_report(const ba_handle* h, const LmCtl* c, ba_report* rep, int 
   rep->ms_solve = h->prof_ms[TAG_SOLVE];
   rep->ms_backsub = h->prof_ms[TAG_BACK];
   rep->ms_other = h->prof_ms[TAG_OTHER];
+  rep->ms_comm = h->prof_ms[TAG_COMM];
 }
 
 extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t n_obs,

@@ -93,7 +93,7 @@ k_rcs_band(Work w) {
   extern __shared__ double sm[];
   const int nb = w.n_cam, bw = w.band_w, W2 = bw + 2, rowlen = (bw + 1) * 36;
   const int ncell = W2 * (W2 + 1) / 2;
-  const int back_doubles = 2 * kBatch * (rowlen + 36 + 6) + 64 * 6;
+  const int back_doubles = 2 * kBatch * ((bw + 1) * 36 + 36 + 6) + 64 * 6;
   const int a_doubles = max(ncell * kCS, back_doubles);
   double* __restrict__ A = sm;                 // window cells (factorisation) / column batches (backward)
   double* __restrict__ yr = A + a_doubles;     // ring: right-hand side rows of the window
@@ -136,11 +136,6 @@ k_rcs_band(Work w) {
     int rj = ri - d;
     if (rj < 0) rj += W2;
     A[tri_cell(ri, rj) + q] = v;
-  };
-  auto load_rhs = [&](int I, int ri) {       // 6 threads
-    const int r = tid;
-    const size_t at = 6 * (size_t)I + r;
-    yr[ri * 6 + r] = (w.fixed[I] != 0) ? 0.0 : w.b[at];
   };
 
   // ---- initial window: rows 0..min(bw, nb-1) -------------------------------------------------
@@ -186,20 +181,46 @@ k_rcs_band(Work w) {
   if (tid == 0) factor_diag(0);
   __syncthreads();
 
+  // per-thread constants of the row prefetch: block offset d and element q of its kPF band-row elements,
+  // and the diag(U) entry it needs when it holds a diagonal element of the diagonal block
+  int pd[kPF], pq[kPF];
+#pragma unroll
+  for (int u = 0; u < kPF; ++u) {
+    const int e = tid + u * nt;
+    pd[u] = e / 36;
+    pq[u] = e - 36 * pd[u];
+  }
+  const int my_diag = (tid < 36 && tid / 6 == tid % 6) ? tid / 6 : -1;
+
   // ---- factorisation + forward substitution --------------------------------------------------
   int rK = 0;
   for (int K = 0; K < nb; ++K) {
     if (s_fail) break;                            // uniform: written before the last barrier
     const int m = min(bw, nb - 1 - K);
+    const bool tr = (K >= 100 && K < 103);
+    if (tr) dbg_mark(w, 40 + 5 * (K - 100), 500);
     // prefetch the row entering the window
     const int In = K + bw + 1;
     const int rn = (rK == 0) ? W2 - 1 : rK - 1;   // residue of In == residue of K-1
+    // raw loads only (no value-dependent branch, so nothing waits for them before the row is placed):
+    // the band row, the gauge flag of the camera and this thread's diag(U) entry
     double pre[kPF];
+    double pre_du = 0.0, pre_b = 0.0;
+    int pre_fx = 0;
     if (In < nb) {
+      const double* __restrict__ src = Sg + (size_t)In * rowlen;
 #pragma unroll
       for (int u = 0; u < kPF; ++u) {
         const int e = tid + u * nt;
-        pre[u] = (e < rowlen) ? fetch(In, e) : 0.0;
+        pre[u] = (e < rowlen) ? __ldcg(src + e) : 0.0;
+      }
+      pre_fx = w.fixed[In];
+      if (my_diag >= 0) pre_du = __ldcg(w.diagU + 6 * (size_t)In + my_diag);
+      if (tid < 6) pre_b = __ldcg(w.b + 6 * (size_t)In + tid);
+#pragma unroll
+      for (int u = 0; u < kPF; ++u) {
+        const int e = tid + u * nt;
+        if (e < rowlen) Sg[(size_t)In * rowlen + e] = 0.0;      // cleared behind the read for the next LM iteration
       }
     }
     // (2) panel rows and the rhs row:  v <- v * L_KK^-T
@@ -227,7 +248,9 @@ k_rcs_band(Work w) {
         for (int q = 0; q < 6; ++q) v[q] = o[q];
       }
     }
+    if (tr) dbg_mark(w, 41 + 5 * (K - 100), 501);
     __syncthreads();
+    if (tr) dbg_mark(w, 42 + 5 * (K - 100), 502);
     // (3) trailing update; warp 0 owns the next diagonal block and factors it (look-ahead)
     const int nblk_t = m * (m + 1) / 2;
     if (wid == 0) {
@@ -314,37 +337,77 @@ k_rcs_band(Work w) {
         w.band_dinv[6 * (size_t)K + t0] = dinv[rK * 6 + t0];
       }
     }
+    if (tr) dbg_mark(w, 43 + 5 * (K - 100), 503);
     // the new row goes into the cells that step K-1 freed (residue of K-1): nobody reads them now
     if (In < nb) {
+      // damping / gauge rows are applied here, to the diagonal block (d = 0: the first 36 elements)
+      if (tid < 36) {
+        const int r = tid / 6, c = tid - 6 * r;
+        if (pre_fx != 0) pre[0] = (r == c) ? 1.0 : 0.0;
+        else if (r == c) pre[0] += damp(pre_du, lambda);
+      }
 #pragma unroll
       for (int u = 0; u < kPF; ++u) {
         const int e = tid + u * nt;
-        if (e < rowlen) place(In, rn, e, pre[u]);
+        if (e < rowlen) {
+          int rj = rn - pd[u];                       // In - d >= 1 inside the loop: every block of the row exists
+          if (rj < 0) rj += W2;
+          A[tri_cell(rn, rj) + pq[u]] = pre[u];
+        }
       }
-      if (tid < 6) load_rhs(In, rn);
+      if (tid < 6) yr[rn * 6 + tid] = (pre_fx != 0) ? 0.0 : pre_b;
     }
+    if (tr) dbg_mark(w, 44 + 5 * (K - 100), 504);
     __syncthreads();
     rK = wrap(rK + 1, W2);
   }
   __syncthreads();
+  dbg_mark(w, 70, 510);
   const bool fail = s_fail != 0;
   double* __restrict__ x = w.dp;
 
   if (!fail) {
-    // ---- backward substitution L^T x = y, columns in double-buffered batches ------------------
-    const int colsz = rowlen + 36 + 6;                // L column blocks | Linv of the diagonal block | y
-    double* buf[2] = {A, A + kBatch * colsz};
-    double* xr = A + 2 * kBatch * colsz;              // ring of the last 64 solved blocks
+    // ---- backward substitution L^T x = y in the column-oriented (axpy) form -------------------
+    // Row K of L (blocks (K, K-d) = d-th block of column K-d) arrives in double-buffered batches.
+    // Warp 0 walks the rows downwards: x_K = L_KK^-T y_K, then y_J -= L_KJ^T x_K for the rows J < K
+    // inside the band.  Only the update of y_{K-1} is on the critical path of the next step (it is
+    // done first), so a step costs one 6x6 product + one triangular product instead of a reduction
+    // over the whole band column.
+    const int rowsz = (bw + 1) * 36 + 36 + 6;         // blocks (K, K-d) d = 0..bw | Linv of L_KK | pad
+    double* buf[2] = {A, A + kBatch * rowsz};
+    double* yb = A + 2 * kBatch * rowsz;              // ring of 64 right-hand side rows
     const int nbatch = (nb + kBatch - 1) / kBatch;
     auto load_batch = [&](int bi, double* dst, int t0, int wt) {
-      // batch bi covers columns K = nb-1-bi*kBatch-s, s = 0..kBatch-1
-      for (int s = 0; s < kBatch; ++s) {
-        const int K = nb - 1 - bi * kBatch - s;
-        if (K < 0) break;
-        const int m = min(bw, nb - 1 - K);
-        double* c = dst + s * colsz;
-        for (int e = t0; e < (m + 1) * 36; e += wt) c[e] = Lg[(size_t)K * rowlen + e];
-        if (t0 < 6) c[rowlen + 36 + t0] = w.band_y[6 * (size_t)K + t0];
+      // batch bi covers rows K = nb-1-bi*kBatch-s, s = 0..kBatch-1; element e = (s, d, q).
+      // Eight loads are in flight per thread before the first one is stored.
+      const int per_row = (bw + 1) * 36, total = kBatch * per_row;
+      for (int base = t0; base < total; base += 8 * wt) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = base + u * wt;
+          v[u] = 0.0;
+          if (e < total) {
+            const int s = e / per_row, r = e - s * per_row;
+            const int d = r / 36, q = r - 36 * d;
+            const int K = nb - 1 - bi * kBatch - s;
+            if (K - d >= 0) v[u] = __ldcg(Lg + (size_t)(K - d) * rowlen + d * 36 + q);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = base + u * wt;
+          if (e < total) {
+            const int s = e / per_row, r = e - s * per_row;
+            dst[s * rowsz + r] = v[u];
+          }
+        }
+      }
+      // the rows that enter the band below this batch start from the forward-substitution result
+      if (t0 < 6 * kBatch) {
+        const int s = t0 / 6, c = t0 - 6 * s;
+        const int J = nb - 1 - bi * kBatch - s - bw;
+        if (J >= 0) yb[(J & 63) * 6 + c] = __ldcg(w.band_y + 6 * (size_t)J + c);
       }
     };
     auto invert_batch = [&](int bi, double* dst, int t0, int wt) {
@@ -352,63 +415,82 @@ k_rcs_band(Work w) {
         const int s = t / 6, j = t - 6 * s;
         const int K = nb - 1 - bi * kBatch - s;
         if (K < 0) continue;
-        const double* L = dst + s * colsz;            // block d = 0 is L_KK
-        double* Li = dst + s * colsz + rowlen;
+        const double* L = dst + s * rowsz;            // block d = 0 is L_KK
+        double* Li = dst + s * rowsz + (bw + 1) * 36;
+        double di[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) di[i] = __ldcg(w.band_dinv + 6 * (size_t)K + i);
         double col[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
           double a = (i == j) ? 1.0 : 0.0;
 #pragma unroll
           for (int q = 0; q < i; ++q) a = fma(-L[6 * i + q], col[q], a);
-          col[i] = (i < j) ? 0.0 : a * w.band_dinv[6 * (size_t)K + i];
+          col[i] = (i < j) ? 0.0 : a * di[i];
         }
 #pragma unroll
         for (int i = 0; i < 6; ++i) Li[6 * i + j] = col[i];
       }
     };
+    // rows nb-1-bw .. nb-1 start from the forward-substitution result
+    for (int i = tid; i < 6 * min(bw + 1, nb); i += nt) {
+      const int J = nb - 1 - i / 6;
+      yb[(J & 63) * 6 + (i % 6)] = w.band_y[6 * (size_t)J + (i % 6)];
+    }
+    __syncthreads();
     load_batch(0, buf[0], tid, nt);
     __syncthreads();
     invert_batch(0, buf[0], tid, nt);
     __syncthreads();
+    // per-lane constants of the update rounds: pair p = lane + 32 u  ->  (d - 1, column)
+    constexpr int kRounds = (6 * kBandMaxW + 31) / 32;
+    int p_off[kRounds], p_d[kRounds];
+#pragma unroll
+    for (int u = 0; u < kRounds; ++u) {
+      const int pp = lane + 32 * u;
+      p_d[u] = pp / 6;
+      p_off[u] = (p_d[u] + 1) * 36 + (pp - 6 * p_d[u]);
+    }
     for (int bi = 0; bi < nbatch; ++bi) {
       double* cb = buf[bi & 1];
+      if (bi == 10) dbg_mark(w, 75, 520);
       if (wid == 0) {
-        const int g = lane >> 3, c = lane & 7;
         for (int s = 0; s < kBatch; ++s) {
           const int K = nb - 1 - bi * kBatch - s;
           if (K < 0) break;
-          const int m = min(bw, nb - 1 - K);
-          const double* col = cb + s * colsz;
-          double a0 = 0.0, a1 = 0.0;
-          if (c < 6) {
-            for (int d = 1 + g; d <= m; d += 4) {
-              const double* Lb = col + d * 36 + c;
-              const double* xv = xr + ((K + d) & 63) * 6;
-              a0 = fma(Lb[0], xv[0], a0);
-              a1 = fma(Lb[6], xv[1], a1);
-              a0 = fma(Lb[12], xv[2], a0);
-              a1 = fma(Lb[18], xv[3], a1);
-              a0 = fma(Lb[24], xv[4], a0);
-              a1 = fma(Lb[30], xv[5], a1);
-            }
-          }
-          double acc = a0 + a1;
-          acc += __shfl_xor_sync(kFull, acc, 8);
-          acc += __shfl_xor_sync(kFull, acc, 16);
-          const double rhs = (c < 6) ? col[rowlen + 36 + c] - acc : 0.0;
-          // x_c = sum_{r >= c} Linv[r][c] rhs_r
-          const double* Li = col + rowlen;
+          const int mp = min(bw, K);
+          const double* row = cb + s * rowsz;
+          const double* Li = row + (bw + 1) * 36;
+          // x_c = sum_{r >= c} Linv[r][c] y_r   (lanes c < 6), then every lane gets the six x
+          const int c = lane < 6 ? lane : 0;
           double xa = 0.0, xb = 0.0;
 #pragma unroll
           for (int r = 0; r < 6; ++r) {
-            const double rr = __shfl_sync(kFull, rhs, r);
-            const double l = (c < 6 && r >= c) ? Li[6 * r + c] : 0.0;
-            if (r & 1) xb = fma(l, rr, xb); else xa = fma(l, rr, xa);
+            const double l = (r >= c) ? Li[6 * r + c] : 0.0;
+            const double yv = yb[(K & 63) * 6 + r];
+            if (r & 1) xb = fma(l, yv, xb); else xa = fma(l, yv, xa);
           }
           const double xv = xa + xb;
-          if (lane < 6) {
-            xr[(K & 63) * 6 + lane] = xv;
-            x[6 * (size_t)K + lane] = xv;
+          if (lane < 6) x[6 * (size_t)K + lane] = xv;
+          double xk[6];
+#pragma unroll
+          for (int r = 0; r < 6; ++r) xk[r] = __shfl_sync(kFull, xv, r);
+          // y_J -= L_KJ^T x_K; the first six pairs (round 0, lanes 0..5) are row K-1, the only ones the
+          // next step waits for.  All rounds are independent and issued back to back.
+#pragma unroll
+          for (int u = 0; u < kRounds; ++u) {
+            if (p_d[u] < mp) {
+              const double* Lb = row + p_off[u];
+              double* yj = yb + ((K - 1 - p_d[u]) & 63) * 6 + (p_off[u] % 36) % 6;
+              double a0 = *yj, a1 = 0.0;
+              a0 = fma(-Lb[0], xk[0], a0);
+              a1 = fma(-Lb[6], xk[1], a1);
+              a0 = fma(-Lb[12], xk[2], a0);
+              a1 = fma(-Lb[18], xk[3], a1);
+              a0 = fma(-Lb[24], xk[4], a0);
+              a1 = fma(-Lb[30], xk[5], a1);
+              *yj = a0 + a1;
+            }
           }
           __syncwarp();
         }
@@ -418,7 +500,9 @@ k_rcs_band(Work w) {
         asm volatile("bar.sync 1, %0;" ::"r"(nt - 32));
         invert_batch(bi + 1, buf[(bi + 1) & 1], tid - 32, nt - 32);
       }
+      if (bi == 10) dbg_mark(w, 76, 521);
       __syncthreads();
+      if (bi == 10) dbg_mark(w, 77, 522);
     }
   } else {
     for (int c = tid; c < w.n; c += nt) x[c] = 0.0;
@@ -426,6 +510,7 @@ k_rcs_band(Work w) {
     for (size_t i = tid; i < w.s_len; i += nt) Sg[i] = 0.0;
     __syncthreads();
   }
+  dbg_mark(w, 71, 511);
   // clear b / diag(U) / cost for the next iteration
   for (int c = tid; c < w.n; c += nt) { w.b[c] = 0.0; w.diagU[c] = 0.0; }
   if (tid == 0) *w.cost_lin = 0.0;
