@@ -59,6 +59,22 @@ def hbm_peak():
         return 6650.0, "fallback"
 
 
+class _stdout_to_stderr:
+    """Route file descriptor 1 to 2 while a C library that prints banners initialises."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        return False
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -172,7 +188,9 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        with _stdout_to_stderr():          # NCCL prints its version banner on stdout; the contract is ONE JSON line
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
 
     def barrier():
         if world > 1:
@@ -200,7 +218,8 @@ def run_b200(args, rank, local_rank, world):
     lmcfg = dict(max_iter=max_iter, schur=args.schur, pcg_tol=args.pcg_tol, pcg_max_iter=args.pcg_max_iter)
     solver = LocalBASolver(LMConfig(**lmcfg), device=local_rank)
     if sharded and world > 1:
-        badist.init_solver(solver, rank, world, device=dev)
+        with _stdout_to_stderr():
+            badist.init_solver(solver, rank, world, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     if sharded:
         args.steps = min(args.steps, 3)
