@@ -11,6 +11,9 @@
 
 namespace ba {
 
+#ifndef BA_BACKSUB_MIN_CTAS
+#define BA_BACKSUB_MIN_CTAS 2                // resident CTAs per SM the back-substitution kernel is compiled for
+#endif
 static constexpr int kWarps = 8;             // warps per CTA in the per-point kernels
 static constexpr int kThreads = kWarps * 32;
 
@@ -494,10 +497,19 @@ int launch_rcs_cholesky(const Work& w, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------
 // back-substitution, candidate points, candidate cost, accept / reject
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
+// kStaged: the window's current poses, candidate poses and camera steps sit in shared memory (windows of
+// up to kBackCams keyframes), so a point's critical path has no dependent global gathers; the next
+// point's observation range, camera indices and pixels are prefetched while the current one is solved.
+static constexpr int kBackCams = 48;
+
+template <bool kStaged>
+__global__ void __launch_bounds__(kThreads, BA_BACKSUB_MIN_CTAS)
 k_backsub(Work w) {
   __shared__ double s_cost[kWarps];
   __shared__ bool s_last;
+  __shared__ double s_pose[kStaged ? kBackCams * 13 : 1];
+  __shared__ double s_posen[kStaged ? kBackCams * 13 : 1];
+  __shared__ double s_dp[kStaged ? kBackCams * 7 : 1];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   LmCtl* ctl = w.ctl;
   const int cur = ctl->cur;
@@ -511,60 +523,100 @@ k_backsub(Work w) {
 
   const int warp_global = blockIdx.x * kWarps + wid;
   const int warp_total = gridDim.x * kWarps;
-  for (int j = warp_global; j < w.n_pt; j += warp_total) {
-    const int o0 = __ldg(w.pt_off + j);
-    const int k = __ldg(w.pt_off + j + 1) - o0;
-    const double X0 = X[3 * j], X1 = X[3 * j + 1], X2 = X[3 * j + 2];
+  // prefetch pipeline: range of the point after next, observation of the next point
+  int j = warp_global;
+  int o0 = 0, k = -1, o0n = 0, kn = -1;
+  if (j < w.n_pt) { o0 = __ldg(w.pt_off + j); k = __ldg(w.pt_off + j + 1) - o0; }
+  if (j + warp_total < w.n_pt) { o0n = __ldg(w.pt_off + j + warp_total); kn = __ldg(w.pt_off + j + warp_total + 1) - o0n; }
+  ObsIn in;
+  in.cam = 0; in.u = in.v = 0.0;
+  double X0 = 0.0, X1 = 0.0, X2 = 0.0;
+  if (k > 0 && lane < k) in = load_obs(w, o0 + lane);
+  if (k >= 0) { X0 = X[3 * (size_t)j]; X1 = X[3 * (size_t)j + 1]; X2 = X[3 * (size_t)j + 2]; }
+  if (kStaged) {
+    for (int i = threadIdx.x; i < 12 * w.n_cam; i += kThreads) {
+      const int c = i / 12, q = i - 12 * c;
+      s_pose[c * 13 + q] = pose[i];
+      s_posen[c * 13 + q] = posen[i];
+    }
+    for (int i = threadIdx.x; i < 6 * w.n_cam; i += kThreads) {
+      const int c = i / 6, q = i - 6 * c;
+      s_dp[c * 7 + q] = (w.fixed[c] == 0) ? dp[i] : 0.0;
+    }
+    __syncthreads();
+  }
+
+  for (; j < w.n_pt; j += warp_total) {
+    // ---- issue the next point's loads before touching this one -----------------------------------
+    const int jn = j + warp_total;
+    ObsIn nin;
+    nin.cam = 0; nin.u = nin.v = 0.0;
+    double N0x = 0.0, N1x = 0.0, N2x = 0.0;
+    if (kn > 0 && lane < kn) nin = load_obs(w, o0n + lane);
+    if (kn >= 0) { N0x = X[3 * (size_t)jn]; N1x = X[3 * (size_t)jn + 1]; N2x = X[3 * (size_t)jn + 2]; }
+    int o0nn = 0, knn = -1;
+    if (jn + warp_total < w.n_pt) {
+      o0nn = __ldg(w.pt_off + jn + warp_total);
+      knn = __ldg(w.pt_off + jn + warp_total + 1) - o0nn;
+    }
+
     if (k <= 0) {
-      if (lane == 0) { Xn[3 * j] = X0; Xn[3 * j + 1] = X1; Xn[3 * j + 2] = X2; }
-      continue;
-    }
-    double V[6] = {0, 0, 0, 0, 0, 0}, q[3] = {0, 0, 0};
-    for (int base = 0; base < k; base += 32) {
-      int i = base + lane;
-      if (i < k) {
-        ObsIn in = load_obs(w, o0 + i);
-        ObsLin ol;
-        linearize_obs<true>(w.K, pose + 12 * in.cam, pose + 12 * in.cam + 9, X0, X1, X2, in.u,
-                            in.v, delta, ol);
-        double eu = ol.ru, ev = ol.rv;
-        if (w.fixed[in.cam] == 0) {
-          const double* d = dp + 6 * in.cam;
+      if (lane == 0) { Xn[3 * (size_t)j] = X0; Xn[3 * (size_t)j + 1] = X1; Xn[3 * (size_t)j + 2] = X2; }
+    } else {
+      double V[6] = {0, 0, 0, 0, 0, 0}, q[3] = {0, 0, 0};
+      for (int base = 0; base < k; base += 32) {
+        const int i = base + lane;
+        if (i < k) {
+          const ObsIn ob = (base == 0) ? in : load_obs(w, o0 + i);
+          ObsLin ol;
+          const double* P = kStaged ? (s_pose + 13 * ob.cam) : (pose + 12 * (size_t)ob.cam);
+          linearize_obs<true>(w.K, P, P + 9, X0, X1, X2, ob.u, ob.v, delta, ol);
+          double eu = ol.ru, ev = ol.rv;
+          if (kStaged) {
+            const double* d = s_dp + 7 * ob.cam;
 #pragma unroll
-          for (int r = 0; r < 6; ++r) { eu += ol.pu[r] * d[r]; ev += ol.pv[r] * d[r]; }
+            for (int r = 0; r < 6; ++r) { eu += ol.pu[r] * d[r]; ev += ol.pv[r] * d[r]; }
+          } else if (w.fixed[ob.cam] == 0) {
+            const double* d = dp + 6 * (size_t)ob.cam;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { eu += ol.pu[r] * d[r]; ev += ol.pv[r] * d[r]; }
+          }
+          V[0] += ol.wu * ol.lu[0] * ol.lu[0] + ol.wv * ol.lv[0] * ol.lv[0];
+          V[1] += ol.wu * ol.lu[0] * ol.lu[1] + ol.wv * ol.lv[0] * ol.lv[1];
+          V[2] += ol.wu * ol.lu[0] * ol.lu[2] + ol.wv * ol.lv[0] * ol.lv[2];
+          V[3] += ol.wu * ol.lu[1] * ol.lu[1] + ol.wv * ol.lv[1] * ol.lv[1];
+          V[4] += ol.wu * ol.lu[1] * ol.lu[2] + ol.wv * ol.lv[1] * ol.lv[2];
+          V[5] += ol.wu * ol.lu[2] * ol.lu[2] + ol.wv * ol.lv[2] * ol.lv[2];
+          const double au = ol.wu * eu, av = ol.wv * ev;
+#pragma unroll
+          for (int r = 0; r < 3; ++r) q[r] += au * ol.lu[r] + av * ol.lv[r];
         }
-        V[0] += ol.wu * ol.lu[0] * ol.lu[0] + ol.wv * ol.lv[0] * ol.lv[0];
-        V[1] += ol.wu * ol.lu[0] * ol.lu[1] + ol.wv * ol.lv[0] * ol.lv[1];
-        V[2] += ol.wu * ol.lu[0] * ol.lu[2] + ol.wv * ol.lv[0] * ol.lv[2];
-        V[3] += ol.wu * ol.lu[1] * ol.lu[1] + ol.wv * ol.lv[1] * ol.lv[1];
-        V[4] += ol.wu * ol.lu[1] * ol.lu[2] + ol.wv * ol.lv[1] * ol.lv[2];
-        V[5] += ol.wu * ol.lu[2] * ol.lu[2] + ol.wv * ol.lv[2] * ol.lv[2];
-        double au = ol.wu * eu, av = ol.wv * ev;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) q[r] += au * ol.lu[r] + av * ol.lv[r];
+      }
+      warp_sum_6_3(V, q);
+      V[0] += damp(V[0], lambda);
+      V[3] += damp(V[3], lambda);
+      V[5] += damp(V[5], lambda);
+      double Vi[6];
+      sym3_inverse(V, Vi);
+      const double d0 = -(Vi[0] * q[0] + Vi[1] * q[1] + Vi[2] * q[2]);
+      const double d1 = -(Vi[1] * q[0] + Vi[3] * q[1] + Vi[4] * q[2]);
+      const double d2 = -(Vi[2] * q[0] + Vi[4] * q[1] + Vi[5] * q[2]);
+      const double N0 = X0 + d0, N1 = X1 + d1, N2 = X2 + d2;
+      if (lane == 0) { Xn[3 * (size_t)j] = N0; Xn[3 * (size_t)j + 1] = N1; Xn[3 * (size_t)j + 2] = N2; }
+      for (int base = 0; base < k; base += 32) {
+        const int i = base + lane;
+        if (i < k) {
+          const ObsIn ob = (base == 0) ? in : load_obs(w, o0 + i);
+          const double* P = kStaged ? (s_posen + 13 * ob.cam) : (posen + 12 * (size_t)ob.cam);
+          double ru, rv;
+          residual_only(w.K, P, P + 9, N0, N1, N2, ob.u, ob.v, ru, rv);
+          cost += huber_rho(ru, delta) + huber_rho(rv, delta);
+        }
       }
     }
-    warp_sum_6_3(V, q);
-    V[0] += damp(V[0], lambda);
-    V[3] += damp(V[3], lambda);
-    V[5] += damp(V[5], lambda);
-    double Vi[6];
-    sym3_inverse(V, Vi);
-    const double d0 = -(Vi[0] * q[0] + Vi[1] * q[1] + Vi[2] * q[2]);
-    const double d1 = -(Vi[1] * q[0] + Vi[3] * q[1] + Vi[4] * q[2]);
-    const double d2 = -(Vi[2] * q[0] + Vi[4] * q[1] + Vi[5] * q[2]);
-    const double N0 = X0 + d0, N1 = X1 + d1, N2 = X2 + d2;
-    if (lane == 0) { Xn[3 * j] = N0; Xn[3 * j + 1] = N1; Xn[3 * j + 2] = N2; }
-    for (int base = 0; base < k; base += 32) {
-      int i = base + lane;
-      if (i < k) {
-        ObsIn in = load_obs(w, o0 + i);
-        double ru, rv;
-        residual_only(w.K, posen + 12 * in.cam, posen + 12 * in.cam + 9, N0, N1, N2, in.u, in.v,
-                      ru, rv);
-        cost += huber_rho(ru, delta) + huber_rho(rv, delta);
-      }
-    }
+    // rotate the pipeline
+    in = nin; X0 = N0x; X1 = N1x; X2 = N2x;
+    o0 = o0n; k = kn; o0n = o0nn; kn = knn;
   }
   cost = warp_sum(cost);
   if (lane == 0) s_cost[wid] = cost;
@@ -589,10 +641,11 @@ k_backsub(Work w) {
 
 int launch_backsub(const Work& w, int sm_count, cudaStream_t s) {
   int blocks = (w.n_pt + kWarps - 1) / kWarps;
-  int cap = sm_count * 4;
+  int cap = sm_count * BA_BACKSUB_MIN_CTAS;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  k_backsub<<<blocks, kThreads, 0, s>>>(w);
+  if (w.n_cam <= kBackCams) k_backsub<true><<<blocks, kThreads, 0, s>>>(w);
+  else k_backsub<false><<<blocks, kThreads, 0, s>>>(w);
   return 1;
 }
 

@@ -44,8 +44,15 @@ template <int N>
 __device__ __forceinline__ void block_sum(double (&v)[N], double* s_red /* [kPoseWarps][N] */,
                                           double* s_out /* [N] */) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // butterfly with the N sums side by side (independent shuffle/add chains per step)
 #pragma unroll
-  for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
+  for (int o = 16; o > 0; o >>= 1) {
+    double tmp[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) tmp[i] = __shfl_xor_sync(kFull, v[i], o);
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] += tmp[i];
+  }
   if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < N; ++i) s_red[wid * N + i] = v[i];
