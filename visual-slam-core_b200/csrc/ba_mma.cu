@@ -527,26 +527,32 @@ k_linearize_mma(const __grid_constant__ Work w) {
         const double z0 = c00 * gl[0];
         const double z1 = c01 * gl[0] + c11 * gl[1];
         const double z2 = c02 * gl[0] + c12 * gl[1] + c22 * gl[2];
-        // ---- phase 3: pose rows, W = J_p^T w J_l, Y = W C, camera sums ------------------------
-        const double lu0 = ja * P[0] + jc * P[6], lu1 = ja * P[1] + jc * P[7], lu2 = ja * P[2] + jc * P[8];
-        const double lv0 = jb * P[3] + jd * P[6], lv1 = jb * P[4] + jd * P[7], lv2 = jb * P[5] + jd * P[8];
+        // ---- phase 3: pose rows, Y = W C = (w_u p_u) (l_u C) + (w_v p_v) (l_v C), camera sums ----------
+        // (J_l C is formed once per observation: 2 FMAs per entry of Y instead of 5, and neither J_l nor C
+        //  stays live through the row loop)
+        double luC0, luC1, luC2, lvC0, lvC1, lvC2;
+        {
+          const double lu0 = ja * P[0] + jc * P[6], lu1 = ja * P[1] + jc * P[7], lu2 = ja * P[2] + jc * P[8];
+          const double lv0 = jb * P[3] + jd * P[6], lv1 = jb * P[4] + jd * P[7], lv2 = jb * P[5] + jd * P[8];
+          luC0 = lu0 * c00; luC1 = lu0 * c01 + lu1 * c11; luC2 = lu0 * c02 + lu1 * c12 + lu2 * c22;
+          lvC0 = lv0 * c00; lvC1 = lv0 * c01 + lv1 * c11; lvC2 = lv0 * c02 + lv1 * c12 + lv2 * c22;
+        }
+        // b_a: sum_r  p_u[r] (w_u (l_u C).z - w_u r_u) + p_v[r] (w_v (l_v C).z - w_v r_v)
+        const double gu = wu * (luC0 * z0 + luC1 * z1 + luC2 * z2 - ru);
+        const double gv = wv * (lvC0 * z0 + lvC1 * z1 + lvC2 * z2 - rv);
         double pu[6], pv[6];
         pu[0] = jc * Y1;             pu[1] = ja * Y2 - jc * Y0;  pu[2] = -ja * Y1;
         pu[3] = ja;                  pu[4] = 0.0;                pu[5] = jc;
         pv[0] = -jb * Y2 + jd * Y1;  pv[1] = -jd * Y0;           pv[2] = jb * Y0;
         pv[3] = 0.0;                 pv[4] = jb;                 pv[5] = jd;
-        const double au = wu * ru, av = wv * rv;
         int e2 = 0;
         double yp[3];
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
           const double pa = wu * pu[r], pb = wv * pv[r];
-          const double w0 = pa * lu0 + pb * lv0;
-          const double w1 = pa * lu1 + pb * lv1;
-          const double w2 = pa * lu2 + pb * lv2;
-          const double y0 = w0 * c00;
-          const double y1 = w0 * c01 + w1 * c11;
-          const double y2 = w0 * c02 + w1 * c12 + w2 * c22;
+          const double y0 = pa * luC0 + pb * lvC0;
+          const double y1 = pa * luC1 + pb * lvC1;
+          const double y2 = pa * luC2 + pb * lvC2;
           if (r & 1) {
             // panel row d, columns 6 a + r - 1, 6 a + r
             *reinterpret_cast<double2*>(dst + r - 1) = make_double2(yp[0], y0);
@@ -557,7 +563,7 @@ k_linearize_mma(const __grid_constant__ Work w) {
           }
 #pragma unroll
           for (int c2 = 0; c2 <= r; ++c2, ++e2) Ul[e2 * kWin] += pa * pu[c2] + pb * pv[c2];
-          Ul[(21 + r) * kWin] += y0 * z0 + y1 * z1 + y2 * z2 - (au * pu[r] + av * pv[r]);
+          Ul[(21 + r) * kWin] += pu[r] * gu + pv[r] * gv;
         }
       }
     }
