@@ -69,7 +69,11 @@ struct __align__(16) MmaSmem {
   double scr[kScratch];           // scatter_point scratch (one warp at a time, see lock)
   double pose[32 * kPS];
   double red[kSW];
-  float2 suv[kSW][32];
+  // per staging warp: cp.async landing zones of the next point (no registers are spent on the prefetch)
+  float2 puv[kSW][2][32];      // pixels of observations o0 + lane
+  int pcam[kSW][2][32];        // their cameras
+  double pX[kSW][2][4];        // the point
+  int prange[kSW][3][2];       // pt_off[j], pt_off[j + 1] of the points n, n+1, n+2 of the warp (-1: no point)
   int slot[kSW][32];
   PanelFlags pf[3];            // panel n uses pf[n % 3]: written while staging n, read after it, cleared one panel later
   int pbase[2];                // window base the panel in buffer b was staged with
@@ -127,34 +131,17 @@ __device__ __noinline__ void scatter_point_cold(const Work& w, int j, int lane, 
   if (lane == 0) { __threadfence_block(); atomicExch(lock, 0); }
 }
 
-// what a staging warp holds about a point before it linearises it
-struct PointIn {
-  int o0, k;          // observation range (k < 0: no point)
-  int cam;            // camera of observation o0 + lane (kNone past the end)
-  float2 uv;          // its pixel
-  double X0, X1, X2;
-};
-
-__device__ __forceinline__ void load_range(const Work& w, int j, int p_hi, int& o0, int& k) {
-  if (j < p_hi) {
-    o0 = __ldg(w.pt_off + j);
-    k = __ldg(w.pt_off + j + 1) - o0;
-  } else {
-    o0 = 0; k = -1;
-  }
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
 }
-__device__ __forceinline__ void load_point(const Work& w, const double* __restrict__ X, int j, int lane, PointIn& in) {
-  in.cam = kNone;
-  in.uv = make_float2(0.f, 0.f);
-  in.X0 = in.X1 = in.X2 = 0.0;
-  if (in.k >= 0) {
-    if (lane < in.k) {
-      in.cam = __ldg(w.obs_cam + in.o0 + lane);
-      in.uv = __ldg(reinterpret_cast<const float2*>(w.obs_uv) + in.o0 + lane);
-    }
-    in.X0 = X[3 * (size_t)j]; in.X1 = X[3 * (size_t)j + 1]; in.X2 = X[3 * (size_t)j + 2];
-  }
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // clock64 trace of one chosen thread of CTA 0 (compile with -DBA_MMA_TRACE, run with BA_DBG_TIMES=1)
 __device__ __forceinline__ void mark(const Work& w, bool who, int slot, int tag) {
@@ -407,16 +394,35 @@ k_linearize_mma(const __grid_constant__ Work w) {
   load_window();
   mark(w, tid == 0, 31, 301);
 
-  // software pipeline over this warp's points j = p_lo + wid, + kSW, ...: ranges two ahead, data one ahead
-  PointIn in, nx;
-  int o0_2, k_2;
-  {
-    const int j0 = p_lo + wid;
-    load_range(w, j0, p_hi, in.o0, in.k);
-    load_point(w, X, j0, lane, in);
-    load_range(w, j0 + kSW, p_hi, nx.o0, nx.k);
-    load_range(w, j0 + 2 * kSW, p_hi, o0_2, k_2);
-  }
+  // software pipeline over this warp's points j = p_lo + wid, + kSW, ...: the observation range of the
+  // point after next and the cameras / pixels / coordinates of the next point travel with cp.async
+  // straight into shared memory while the current point is linearised
+  auto issue_range = [&](int idx) {              // idx-th point of this warp -> prange[idx % 3]
+    const int jj = p_lo + wid + idx * kSW;
+    int* dst = sm.prange[wid][idx % 3];
+    if (lane < 2) {
+      if (jj < p_hi) cp_async4(dst + lane, w.pt_off + jj + lane);
+      else dst[lane] = -1;
+    }
+  };
+  auto issue_point = [&](int idx) {              // needs prange[idx % 3] to have landed
+    const int jj = p_lo + wid + idx * kSW;
+    const int o0 = sm.prange[wid][idx % 3][0], o1 = sm.prange[wid][idx % 3][1];
+    if (o0 < 0) return;
+    const int k = o1 - o0;
+    if (lane < k) {
+      cp_async4(&sm.pcam[wid][idx & 1][lane], w.obs_cam + o0 + lane);
+      cp_async8(&sm.puv[wid][idx & 1][lane], reinterpret_cast<const float2*>(w.obs_uv) + o0 + lane);
+    }
+    if (lane < 3) cp_async8(&sm.pX[wid][idx & 1][lane], X + 3 * (size_t)jj + lane);
+  };
+  issue_range(0);
+  issue_range(1);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncwarp();
+  issue_point(0);
+  cp_async_commit();
   const double* __restrict__ P = sm.pose + lane * kPS;
 
 #pragma unroll 1
@@ -427,34 +433,40 @@ k_linearize_mma(const __grid_constant__ Work w) {
     double* __restrict__ Y = sm.Yt[b];
     const int slot = wid;
     const int j = p_lo + n * kPts + slot;
-    // ---- prefetch: data of the next point, range of the one after ---------------------------
-    load_point(w, X, j + kSW, lane, nx);
-    int o0_3, k_3;
-    load_range(w, j + 3 * kSW, p_hi, o0_3, k_3);
+    // ---- this point's data has landed; send for the next point and the range after it ------------
+    cp_async_wait_all();
+    __syncwarp();
+    issue_point(n + 1);
+    issue_range(n + 2);
+    cp_async_commit();
+    const int pb = n & 1;
+    const int in_o0 = sm.prange[wid][n % 3][0];
+    const int in_k = (in_o0 < 0) ? -1 : sm.prange[wid][n % 3][1] - in_o0;
+    const int in_cam = (in_k > 0 && lane < min(in_k, 32)) ? sm.pcam[wid][pb][lane] : kNone;
 
     unsigned present = 0u;
-    bool valid = in.k >= 0;
+    bool valid = in_k >= 0;
     int ia = -1;
     float2 uv = make_float2(0.f, 0.f);
     if (valid) {
-      const int k = in.k;
+      const int k = in_k;
       bool ok = k <= 32;
       int rel = -1;
       __syncwarp();
       if (ok && lane < k) {
-        rel = in.cam - base;
+        rel = in_cam - base;
         if (rel < 0 || rel >= kWin) ok = false;
-        else { sm.slot[wid][rel] = lane; sm.suv[wid][rel] = in.uv; }
+        else sm.slot[wid][rel] = lane;
       }
       __syncwarp();
       if (rel >= 0 && rel < kWin && sm.slot[wid][rel] != lane) ok = false;     // repeated (point, keyframe)
       ia = sm.slot[wid][lane];
-      uv = sm.suv[wid][lane];
+      if (ia >= 0) uv = sm.puv[wid][pb][ia];
       ok = __all_sync(kFull, ok);
       __syncwarp();
       sm.slot[wid][lane] = -1;
       if (kSliding && k > 0 && k <= 32) {
-        int c = in.cam;
+        int c = in_cam;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c = min(c, __shfl_xor_sync(kFull, c, o));
         if (lane == 0) { atomicMin(&sm.pf[fs].cmin, c); if (!ok) sm.pf[fs].rebase = 1; }
@@ -475,9 +487,10 @@ k_linearize_mma(const __grid_constant__ Work w) {
       double V[6] = {0, 0, 0, 0, 0, 0}, gl[3] = {0, 0, 0};
       if (seen) {
         const double R0 = P[0], R1 = P[1], R2 = P[2], R3 = P[3], R4 = P[4], R5 = P[5], R6 = P[6], R7 = P[7], R8 = P[8];
-        Y0 = R0 * in.X0 + R1 * in.X1 + R2 * in.X2;
-        Y1 = R3 * in.X0 + R4 * in.X1 + R5 * in.X2;
-        Y2 = R6 * in.X0 + R7 * in.X1 + R8 * in.X2;
+        const double X0 = sm.pX[wid][pb][0], X1 = sm.pX[wid][pb][1], X2 = sm.pX[wid][pb][2];
+        Y0 = R0 * X0 + R1 * X1 + R2 * X2;
+        Y1 = R3 * X0 + R4 * X1 + R5 * X2;
+        Y2 = R6 * X0 + R7 * X1 + R8 * X2;
         const double xc = Y0 + P[9], yc = Y1 + P[10], zc = Y2 + P[11];
         const double iz = 1.0 / (zc + kDepthEps);
         const double xz = xc * iz, yz = yc * iz;
@@ -576,10 +589,6 @@ k_linearize_mma(const __grid_constant__ Work w) {
       }
     }
     if (kSliding && lane == 0) sm.pmask[b][slot] = present;
-    // rotate the pipeline
-    in = nx;
-    nx.o0 = o0_2; nx.k = k_2;
-    o0_2 = o0_3; k_2 = k_3;
 
     if (wid == 0 && lane == 0) sm.pbase[b] = base;
     bool rebase = false;
