@@ -77,7 +77,7 @@ struct ba_handle {
   // sparse path: structure + PCG workspace
   DevBuf bits, wpre, row_nnz, row_ptr, col_idx, tpos, pcg, bits_all;
   // banded path: factor columns, forward-substituted rhs, inverse pivots, bandwidth scalar
-  DevBuf band_L, band_y, band_dinv, band_wbuf;
+  DevBuf band_L, band_y, band_dinv, band_wbuf, bcr;
   int last_solver = BA_SOLVER_CHOLESKY, last_band_w = -1, last_s_blocks = 0;
   int* h_nnzb = nullptr;          // pinned
   // staging for the host-pointer API
@@ -244,7 +244,7 @@ extern "C" int ba_destroy(ba_handle* h) {
                     &h->d_R, &h->d_t, &h->d_fixed, &h->d_X, &h->d_ocam, &h->d_opt, &h->d_ouv,
                     &h->d_off, &h->d_flags, &h->d_hist, &h->d_acc, &h->d_foff, &h->dbg,
                     &h->bits, &h->wpre, &h->row_nnz, &h->row_ptr, &h->col_idx, &h->tpos, &h->pcg,
-                    &h->bits_all, &h->band_L, &h->band_y, &h->band_dinv, &h->band_wbuf};
+                    &h->bits_all, &h->band_L, &h->band_y, &h->band_dinv, &h->band_wbuf, &h->bcr};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
@@ -352,6 +352,13 @@ static int make_work(ba_handle* h, int n_cam, int n_pt, int n_obs, const double 
     w.band_L = (double*)h->band_L.p;
     w.band_y = (double*)h->band_y.p;
     w.band_dinv = (double*)h->band_dinv.p;
+    // cyclic reduction over 15-keyframe super-blocks when the band fits one (BA_BAND=seq keeps the sequential solver)
+    static int band_mode = -1;
+    if (band_mode < 0) { const char* e = getenv("BA_BAND"); band_mode = (e && !strcmp(e, "seq")) ? 1 : 0; }
+    if (band_mode == 0 && bcr_supported(n_cam, bw)) {
+      if ((rc = ensure(h, h->bcr, sizeof(double) * bcr_workspace_doubles(n_cam)))) return rc;
+      w.bcr_ws = (double*)h->bcr.p;
+    }
   } else {
     // symbolic phase: co-visibility bitmap -> block-CSR structure
     const int W = (n_cam + 31) / 32;
@@ -442,7 +449,7 @@ static int enqueue_lm_loop(ba_handle* h, const Work& w, int schur, cudaStream_t 
     }
     prof_mark(h, TAG_SOLVE, s);
     if (w.band_w >= 0) {
-      launches += launch_rcs_band(w, s);
+      launches += w.bcr_ws ? launch_rcs_bcr(w, w.bcr_ws, s) : launch_rcs_band(w, s);
     } else if (sparse) {
       if (launch_rcs_pcg(w, pcg_grid, s) < 0) { h->err = std::string("cooperative PCG launch: ") + cudaGetErrorString(cudaGetLastError()); return BA_ERR_CUDA; }
       launches += 1;
@@ -631,7 +638,7 @@ extern "C" int ba_solve_local_host(ba_handle* h, int32_t n_cam, int32_t n_pt, in
   if (report) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-    int launches = 2 + h->prm.max_iter * (h->world > 1 ? 4 : 3);
+    int launches = 2 + (h->graph_launches > 0 ? h->graph_launches : h->prm.max_iter * (h->world > 1 ? 4 : 3));
     if (h->prm.profile) prof_collect(h);
     fill_report(h, h->h_ctl, report, BA_OK, ms, launches);
   }

@@ -39,6 +39,7 @@ struct Work {
   double* band_L;                     // [n_cam][band_w+1][36] columns of the Cholesky factor
   double* band_y;                     // [n]  L^-1 b
   double* band_dinv;                  // [n]  1 / diag(L)
+  double* bcr_ws;                     // workspace of the cyclic-reduction band solver (null: sequential band solver)
   size_t s_len;                       // doubles in S (dense packed: n_cam(n_cam+1)/2*36, sparse: nnzb*36)
   // block-Jacobi PCG workspace (sparse path)
   double* pcg_r; double* pcg_z; double* pcg_p[2]; double* pcg_Ap; double* pcg_Minv; double* pcg_acc;
@@ -98,6 +99,10 @@ int pcg_grid_size(int n_cam, int sm_count);
 int launch_rcs_pcg(const Work& w, int grid, cudaStream_t s);
 int launch_band_width(const Work& w, int* out, cudaStream_t s);
 int launch_rcs_band(const Work& w, cudaStream_t s);
+bool bcr_supported(int n_cam, int band_w);
+size_t bcr_workspace_doubles(int n_cam);
+int configure_bcr();
+int launch_rcs_bcr(const Work& w, double* ws, cudaStream_t s);
 int configure_band();
 int band_max_w();
 int launch_backsub(const Work& w, int sm_count, cudaStream_t s);

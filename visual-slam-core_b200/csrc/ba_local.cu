@@ -485,6 +485,8 @@ int configure_kernels() {
   if (r != 0) return r;
   r = configure_mma();
   if (r != 0) return r;
+  r = configure_bcr();
+  if (r != 0) return r;
   return configure_tiled();
 }
 
