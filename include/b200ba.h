@@ -54,7 +54,10 @@ enum {
   BA_SOLVER_AUTO = 0,      /* dense Cholesky if the window fits shared memory, else banded, else PCG */
   BA_SOLVER_CHOLESKY = 1,  /* dense in-shared-memory blocked Cholesky (windows up to 38 keyframes) */
   BA_SOLVER_PCG = 2,       /* block-sparse S + block-Jacobi PCG (any co-visibility structure) */
-  BA_SOLVER_BAND = 3       /* block-banded S + direct banded Cholesky (co-visibility bandwidth <= 32 keyframes) */
+  BA_SOLVER_BAND = 3,      /* block-banded S + direct solve (co-visibility bandwidth <= 32 keyframes): block cyclic
+                              reduction over 15-keyframe super-blocks when the bandwidth is <= 15 and the window has
+                              >= 60 keyframes, else the sequential banded Cholesky */
+  BA_SOLVER_BAND_SEQ = 4   /* block-banded S + the sequential banded Cholesky (diagnostics, cross-check) */
 };
 /* schur_kind */
 enum {

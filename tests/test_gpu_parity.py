@@ -124,6 +124,26 @@ def test_large_window_matches_oracle(name, seed, schur, solver_kind):
     print(f"\n[{name} seed {seed} {schur} {solver_kind}] achieved: {info} pcg iterations {res.pcg_iters.tolist()}")
 
 
+@pytest.mark.parametrize("n_cam", [60, 61, 75, 90, 135, 240, 255])
+def test_cyclic_reduction_band_solver_matches_sequential_and_oracle(n_cam):
+    """Block cyclic reduction over 15-keyframe super-blocks (bandwidth <= 15, >= 60 keyframes): 4 ... 17
+    super-blocks, odd and even counts on every level, windows that are and are not a multiple of 15
+    (identity padding), against the sequential banded Cholesky and the oracle's sparse direct solve."""
+    p = synth.make_problem(n_cam=n_cam, n_pt=12 * n_cam, k_mean=5.0, k_max=10, seed=100 + n_cam)
+    out = {}
+    for kind in ("band", "band_seq"):
+        s = LocalBASolver(LMConfig(solver=kind))
+        out[kind] = s.solve_local(p.intr, p.R, p.t, p.fixed, p.X, p.obs_cam, p.obs_pt, p.obs_uv, p.pt_offsets)
+        s.close()
+        assert out[kind].solve_fail.sum() == 0 and out[kind].extra["solver_used"] == "band"
+        assert out[kind].extra["band_width"] <= 15
+    a, b = out["band"], out["band_seq"]
+    np.testing.assert_array_equal(a.accepted, b.accepted)
+    np.testing.assert_allclose(a.cost_hist, b.cost_hist, rtol=1e-7)
+    np.testing.assert_array_equal(a.flags, b.flags)
+    _check(p, a, _oracle(p), gauge_free=n_cam > 100)
+
+
 @pytest.mark.parametrize("name,seed", [("T0", 1), ("T1", 2), ("T2", 3), ("C1", 0)])
 def test_banded_solver_on_small_windows_matches_oracle(name, seed):
     """The banded layout and factorisation forced onto windows the dense solver also handles

@@ -301,7 +301,7 @@ static int pick_mode(ba_handle* h, int n_cam, int n_pt, const int32_t* obs_cam, 
   if (rc) return rc;
   if (wv >= n_cam) wv = n_cam - 1;
   if (wv <= band_max_w()) { *mode = MODE_BAND; *bw = wv; return BA_OK; }
-  if (kind == BA_SOLVER_BAND) {
+  if (kind == BA_SOLVER_BAND || kind == BA_SOLVER_BAND_SEQ) {
     h->err = "co-visibility bandwidth exceeds the banded solver (32 keyframes); use solver auto or pcg";
     return BA_ERR_TOO_LARGE;
   }
@@ -355,7 +355,7 @@ static int make_work(ba_handle* h, int n_cam, int n_pt, int n_obs, const double 
     // cyclic reduction over 15-keyframe super-blocks when the band fits one (BA_BAND=seq keeps the sequential solver)
     static int band_mode = -1;
     if (band_mode < 0) { const char* e = getenv("BA_BAND"); band_mode = (e && !strcmp(e, "seq")) ? 1 : 0; }
-    if (band_mode == 0 && bcr_supported(n_cam, bw)) {
+    if (band_mode == 0 && h->prm.solver_kind != BA_SOLVER_BAND_SEQ && bcr_supported(n_cam, bw)) {
       if ((rc = ensure(h, h->bcr, sizeof(double) * bcr_workspace_doubles(n_cam)))) return rc;
       w.bcr_ws = (double*)h->bcr.p;
     }

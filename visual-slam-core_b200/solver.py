@@ -29,7 +29,7 @@ class LMConfig:
     lambda_max: float = 1e8
     accept_rtol: float = 1e-8
     max_iter: int = 10
-    solver: str = "auto"        # auto | cholesky | pcg | band
+    solver: str = "auto"        # auto | cholesky | pcg | band | band_seq
     schur: str = "auto"         # auto | scatter | tiled | stream | mma
     pcg_max_iter: int = 500
     pcg_tol: float = 1e-10
@@ -43,7 +43,7 @@ class LMConfig:
         p.lambda_min, p.lambda_max = self.lambda_min, self.lambda_max
         p.accept_rtol = self.accept_rtol
         p.max_iter = int(self.max_iter)
-        p.solver_kind = {"auto": 0, "cholesky": 1, "pcg": 2, "band": 3}[self.solver]
+        p.solver_kind = {"auto": 0, "cholesky": 1, "pcg": 2, "band": 3, "band_seq": 4}[self.solver]
         p.schur_kind = {"auto": 0, "scatter": 1, "tiled": 2, "stream": 3, "mma": 4}[self.schur]
         p.pcg_max_iter, p.pcg_tol = int(self.pcg_max_iter), float(self.pcg_tol)
         p.use_graph = 1 if self.use_graph else 0
