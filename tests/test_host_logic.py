@@ -98,3 +98,25 @@ def test_generator_matches_spec():
     assert 0.03 < p.outlier.mean() < 0.07
     q = synth.make_problem("C1", seed=0)
     np.testing.assert_array_equal(p.obs_uv, q.obs_uv)
+
+
+def test_bench_reference_arm_for_pose_only_prints_one_contract_line():
+    """`bench.py --config C3 --impl reference` times the reference's own cv2.solvePnPRansac call on the
+    host (no GPU needed) and prints exactly one JSON line with the contract keys."""
+    import json
+    import os
+    import subprocess
+    import sys
+    pytest.importorskip("cv2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--config", "C3", "--impl", "reference",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "config", "cpu_baseline", "e2e"):
+        assert key in d
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "reference" and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
