@@ -73,7 +73,7 @@ struct ba_handle {
   ba_params prm;
   std::string err;
   // workspace
-  DevBuf pose0, pose1, X0, X1, red, dp, ctl, cand, dbg;
+  DevBuf pose0, pose1, X0, X1, red, dp, ctl, cand, dbg, part;
   // sparse path: structure + PCG workspace
   DevBuf bits, wpre, row_nnz, row_ptr, col_idx, tpos, pcg, bits_all;
   // banded path: factor columns, forward-substituted rhs, inverse pivots, bandwidth scalar
@@ -242,7 +242,7 @@ extern "C" int ba_destroy(ba_handle* h) {
   if (h->graph) cudaGraphExecDestroy(h->graph);
   DevBuf* bufs[] = {&h->pose0, &h->pose1, &h->X0, &h->X1, &h->red, &h->dp, &h->ctl, &h->cand,
                     &h->d_R, &h->d_t, &h->d_fixed, &h->d_X, &h->d_ocam, &h->d_opt, &h->d_ouv,
-                    &h->d_off, &h->d_flags, &h->d_hist, &h->d_acc, &h->d_foff, &h->dbg,
+                    &h->d_off, &h->d_flags, &h->d_hist, &h->d_acc, &h->d_foff, &h->dbg, &h->part,
                     &h->bits, &h->wpre, &h->row_nnz, &h->row_ptr, &h->col_idx, &h->tpos, &h->pcg,
                     &h->bits_all, &h->band_L, &h->band_y, &h->band_dinv, &h->band_wbuf, &h->bcr};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
@@ -334,6 +334,11 @@ static int make_work(ba_handle* h, int n_cam, int n_pt, int n_obs, const double 
   w.dp = (double*)h->dp.p;
   w.ctl = (LmCtl*)h->ctl.p;
   w.world = h->world;
+  if (pt_off != nullptr && n_pt > 0) {
+    w.part_n = mma_grid(n_cam, n_pt, h->sm_count);
+    if ((rc = ensure(h, h->part, sizeof(int) * (size_t)(w.part_n + 1)))) return rc;
+    w.part = (int*)h->part.p;
+  }
   w.dbg = nullptr;
   static int want_dbg = -1;
   if (want_dbg < 0) { const char* e = getenv("BA_DBG_TIMES"); want_dbg = (e && atoi(e)) ? 1 : 0; }

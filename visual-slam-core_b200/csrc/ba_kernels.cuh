@@ -26,6 +26,8 @@ struct Work {
   LmCtl* ctl;
   int world;                          // > 1: accept/reject runs as its own kernel after the all-reduce
   long long* dbg;                     // optional clock64() trace (BA_DBG_TIMES=1), null otherwise
+  int* part;                          // [part_n + 1] first point of every CTA of the mma linearise kernel (equal
+  int part_n;                         // observation shares), written once per solve by k_init; null / 0: none
   // block-sparse reduced camera matrix (large windows); all null / 0 for the dense packed layout
   const unsigned* bsr_bits;           // [n_cam * bsr_W] structure bitmap (symmetric, diagonal set)
   const int* bsr_wpre;                // [n_cam * bsr_W] set bits before each word of its row
@@ -88,6 +90,7 @@ int launch_linearize_stream(const Work& w, int sm_count, cudaStream_t s);
 int configure_stream();
 int launch_linearize_mma(const Work& w, int sm_count, cudaStream_t s);
 int configure_mma();
+int mma_grid(int n_cam, int n_pt, int sm_count);   // CTAs launch_linearize_mma will use
 int mma_window();
 int launch_rcs_cholesky(const Work& w, cudaStream_t s);
 int launch_symbolic(const Work& w, unsigned* bits, int* wpre, int* row_nnz, int* row_ptr, cudaStream_t s);

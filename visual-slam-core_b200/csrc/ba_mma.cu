@@ -219,11 +219,32 @@ __device__ __forceinline__ void cluster_flush(const Work& w, MmaSmem& sm, int ti
 #pragma unroll
   for (int q = 0; q < kCluster; ++q) src[q] = cluster.map_shared_rank(&sm.Sacc[0][0][0], q);
   const int lo = rank * kShare, hi = min(kTotal, lo + kShare);
-  for (int idx = lo + tid; idx < hi; idx += kMT) {
-    double v = 0.0;
+  // every cluster adds into the same entries of S: clusters start at different offsets of their share so that
+  // the L2 does not see all of them on the same addresses at the same time (same-address float64 REDs serialise),
+  // and a thread's remote / local loads are all in flight before its first RED
+  constexpr int kIter = (kShare + kMT - 1) / kMT;
+  const int n_clusters = (int)(gridDim.x / kCluster);
+  const int rot = (int)(((long long)(blockIdx.x / kCluster) * kShare) / (n_clusters > 0 ? n_clusters : 1));
+  double v[kIter];
+  int at[kIter];
 #pragma unroll
-    for (int q = 0; q < kCluster; ++q) v += src[q][idx];
-    if (v == 0.0) continue;
+  for (int u = 0; u < kIter; ++u) {
+    int off = tid + u * kMT;
+    const bool ok = off < hi - lo;
+    off += rot;
+    if (off >= hi - lo) off -= hi - lo;
+    at[u] = ok ? lo + off : -1;
+    double a = 0.0;
+    if (ok) {
+#pragma unroll
+      for (int q = 0; q < kCluster; ++q) a += src[q][lo + off];
+    }
+    v[u] = a;
+  }
+#pragma unroll
+  for (int u = 0; u < kIter; ++u) {
+    if (at[u] < 0 || v[u] == 0.0) continue;
+    const int idx = at[u];
     const int t = idx / 576, e = (idx - 576 * t) >> 5, lane = idx & 31;
     int mI, mJ;
     tile_of(t, mI, mJ);
@@ -232,7 +253,7 @@ __device__ __forceinline__ void cluster_flush(const Work& w, MmaSmem& sm, int ti
     const int m = 24 * mI + 8 * i + (lane >> 2);
     const int n2 = 24 * mJ + 8 * j + 2 * (lane & 3) + h;
     const int a = m / 6, r = m - 6 * a, b = n2 / 6, cc = n2 - 6 * b;
-    if (a > b || (a == b && cc <= r)) atomicAdd(s_block_ptr(w, a, b) + 6 * r + cc, -v);
+    if (a > b || (a == b && cc <= r)) atomicAdd(s_block_ptr(w, a, b) + 6 * r + cc, -v[u]);
   }
   cluster.sync();                                   // nobody leaves while its shared memory is being read
 }
@@ -255,8 +276,14 @@ k_linearize_mma(const __grid_constant__ Work w) {
   const long long nobs = w.n_obs;
   const int t_lo = (int)(nobs * blockIdx.x / gridDim.x);
   const int t_hi = (int)(nobs * (blockIdx.x + 1) / gridDim.x);
-  const int p_lo = (blockIdx.x == 0) ? 0 : lower_bound_off(w.pt_off, w.n_pt, t_lo);
-  const int p_hi = (blockIdx.x == gridDim.x - 1) ? w.n_pt : lower_bound_off(w.pt_off, w.n_pt, t_hi);
+  int p_lo, p_hi;
+  if (w.part != nullptr && w.part_n == (int)gridDim.x) {
+    p_lo = __ldg(w.part + blockIdx.x);
+    p_hi = __ldg(w.part + blockIdx.x + 1);
+  } else {
+    p_lo = (blockIdx.x == 0) ? 0 : lower_bound_off(w.pt_off, w.n_pt, t_lo);
+    p_hi = (blockIdx.x == gridDim.x - 1) ? w.n_pt : lower_bound_off(w.pt_off, w.n_pt, t_hi);
+  }
   const int n_panels = (p_hi - p_lo + kPts - 1) / kPts;
 
   if (wid >= kSW) {
@@ -430,6 +457,7 @@ k_linearize_mma(const __grid_constant__ Work w) {
     const int b = n & 1;
     const int fs = n % 3;
     if (n >= 2) { if (b == 0) bar_sync<kBarEmpty, kMT>(); else bar_sync<kBarEmpty + 1, kMT>(); }
+    if (n == 3) mark(w, tid == 0, 70, 340);
     double* __restrict__ Y = sm.Yt[b];
     const int slot = wid;
     const int j = p_lo + n * kPts + slot;
@@ -439,6 +467,7 @@ k_linearize_mma(const __grid_constant__ Work w) {
     issue_point(n + 1);
     issue_range(n + 2);
     cp_async_commit();
+    if (n == 3) mark(w, tid == 0, 71, 341);
     const int pb = n & 1;
     const int in_o0 = sm.prange[wid][n % 3][0];
     const int in_k = (in_o0 < 0) ? -1 : sm.prange[wid][n % 3][1] - in_o0;
@@ -479,6 +508,7 @@ k_linearize_mma(const __grid_constant__ Work w) {
       }
     }
     const bool seen = valid && ia >= 0;
+    if (n == 3) mark(w, tid == 0, 72, 342);
     const bool act = seen && cam_free;
     double* dst = Y + (size_t)(3 * slot) * kYS + 6 * (lane < kWin ? lane : 0);
     if (valid) {
@@ -516,6 +546,7 @@ k_linearize_mma(const __grid_constant__ Work w) {
         cost += huber_rho(ru, delta) + huber_rho(rv, delta);
       }
       warp_sum_6_3(V, gl);     // butterfly over the lanes, the nine sums side by side
+      if (n == 3) mark(w, tid == 0, 73, 343);
       present = __ballot_sync(kFull, act);
       if (act) {
         // ---- phase 2: C_j with C C^T = (V + lambda diag V)^-1, z = C^T g_l ---------------------
@@ -540,6 +571,7 @@ k_linearize_mma(const __grid_constant__ Work w) {
         const double z0 = c00 * gl[0];
         const double z1 = c01 * gl[0] + c11 * gl[1];
         const double z2 = c02 * gl[0] + c12 * gl[1] + c22 * gl[2];
+        if (n == 3) mark(w, tid == 0, 74, 344);
         // ---- phase 3: pose rows, Y = W C = (w_u p_u) (l_u C) + (w_v p_v) (l_v C), camera sums ----------
         // (J_l C is formed once per observation: 2 FMAs per entry of Y instead of 5, and neither J_l nor C
         //  stays live through the row loop)
@@ -589,6 +621,7 @@ k_linearize_mma(const __grid_constant__ Work w) {
       }
     }
     if (kSliding && lane == 0) sm.pmask[b][slot] = present;
+    if (n == 3) mark(w, tid == 0, 75, 345);
 
     if (wid == 0 && lane == 0) sm.pbase[b] = base;
     bool rebase = false;
@@ -654,13 +687,18 @@ int mma_max_active_clusters(int cluster) {
   return n;
 }
 
-int launch_linearize_mma(const Work& w, int sm_count, cudaStream_t s) {
+int mma_grid(int n_cam, int n_pt, int sm_count) {
   int blocks = sm_count;
-  const int by_pts = (w.n_pt + kPts - 1) / kPts;
+  const int by_pts = (n_pt + kPts - 1) / kPts;
   if (blocks > by_pts) blocks = by_pts;
   if (blocks < 1) blocks = 1;
+  if (n_cam <= kWin) blocks = (blocks + kCluster - 1) / kCluster * kCluster;   // CTAs without points only join the flush
+  return blocks;
+}
+
+int launch_linearize_mma(const Work& w, int sm_count, cudaStream_t s) {
+  const int blocks = mma_grid(w.n_cam, w.n_pt, sm_count);
   if (w.n_cam <= kWin) {
-    blocks = (blocks + kCluster - 1) / kCluster * kCluster;      // CTAs without points only join the flush
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(blocks);
     cfg.blockDim = dim3(kMT);
