@@ -7,7 +7,6 @@
 //   k_backsub       point back-substitution, candidate state, candidate cost, accept/reject
 // All LM control state lives in device memory (LmCtl), so the loop never syncs with the host.
 #include <stdlib.h>
-#include <string.h>
 
 #include "ba_kernels.cuh"
 #include "ba_scatter.cuh"
@@ -125,15 +124,10 @@ int launch_linearize_scatter(const Work& w, int sm_count, cudaStream_t s) {
 // reduced camera system: damping, blocked (6x6) Cholesky in shared memory, camera retraction
 //
 // One CTA.  The matrix sits in shared memory in the same block-packed lower layout the
-// linearise kernels accumulate into, so the load is one coalesced copy.  Per block column K:
-//   (1) one thread factors the 6x6 diagonal block in registers and inverts the factor,
-//   (2) every row below (and the right-hand side, carried as one more row) is multiplied by
-//       L_KK^-T,
-//   (3) the trailing blocks get their rank-6 update, one thread per block row.
-// The forward substitution rides along with the factorisation (rhs row); the backward
-// substitution uses the stored inverse diagonal factors, two barriers per block.
+// linearise kernels accumulate into, so the load is one coalesced copy.  The forward substitution
+// rides along with the factorisation (the right-hand side is carried as one more row); the backward
+// substitution uses the stored inverse diagonal factors.
 // ------------------------------------------------------------------------------------------
-static constexpr int kSolveThreads = 256;
 static constexpr size_t kSolveSmemMax = 227 * 1024 - 1024;   // opt-in limit minus static shared
 
 size_t rcs_cholesky_smem_bytes(int n) {
@@ -205,309 +199,19 @@ __device__ __forceinline__ void tri6_inv_col(const double* __restrict__ L, const
 static constexpr int kBS = 37;
 __device__ __forceinline__ int sblk(int I, int J) { return (I * (I + 1) / 2 + J) * kBS; }
 
-__global__ void __launch_bounds__(kSolveThreads, 1)
-k_rcs_cholesky(Work w) {
-  extern __shared__ double sm[];
-  const int n = w.n, nb = w.n_cam;
-  const int nblk = nb * (nb + 1) / 2;
-  double* __restrict__ A = sm;                        // block-packed lower
-  double* __restrict__ Linv = A + (size_t)nblk * kBS; // inverse diagonal factors
-  double* __restrict__ y = Linv + (size_t)nb * 36;    // right-hand side -> L^-1 b
-  double* x = y + n;                                  // solution
-  __shared__ int s_fail;
-  __shared__ double s_dinv[6];
-  LmCtl* ctl = w.ctl;
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
-  const double lambda = ctl->lambda;
-  const int cur = ctl->cur;
-
-  if (tid == 0) {
-    s_fail = (ctl->solve_fail != 0) ? 1 : 0;      // a linearise kernel may already have flagged the step
-    if (ctl->iter == 0) {
-      double c0 = *w.cost_lin;
-      ctl->cost_cur = c0;
-      ctl->cost_hist[0] = c0;
-    }
-  }
-  dbg_mark(w, 0, 100);
-  // coalesced copy of the accumulated blocks (loads batched 8 deep); the global buffer is zeroed
-  // behind the copy for the next iteration
-  {
-    double* __restrict__ S = w.S;
-    const int total = nblk * 36;
-    for (int base = 0; base < total; base += 8 * nt) {
-      double v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = base + u * nt + tid;
-        v[u] = (i < total) ? S[i] : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = base + u * nt + tid;
-        if (i < total) { A[(i / 36) * kBS + (i % 36)] = v[u]; S[i] = 0.0; }
-      }
-    }
-  }
-  double dU = 0.0;
-  if (tid < n) {
-    y[tid] = (w.fixed[tid / 6] != 0) ? 0.0 : w.b[tid];
-    dU = w.diagU[tid];
-  }
-  for (int c = tid + nt; c < n; c += nt) y[c] = (w.fixed[c / 6] != 0) ? 0.0 : w.b[c];
-  __syncthreads();
-  // damping of the pose blocks; fixed cameras -> identity rows/columns
-  for (int c = tid; c < n; c += nt) {
-    const int cam = c / 6, r = c - 6 * cam;
-    double* D = A + sblk(cam, cam);
-    if (w.fixed[cam] != 0) {
-#pragma unroll
-      for (int q = 0; q < 6; ++q) D[6 * r + q] = (q == r) ? 1.0 : 0.0;
-    } else {
-      D[7 * r] += damp(c < nt ? dU : w.diagU[c], lambda);
-    }
-    w.diagU[c] = 0.0;
-    w.b[c] = 0.0;
-  }
-  if (tid == 0) *w.cost_lin = 0.0;
-  __syncthreads();
-  dbg_mark(w, 1, 101);
-
-  // factor of the first diagonal block; later ones are factored by thread 0 right after it has
-  // updated them inside the trailing phase (look-ahead), off the other threads' critical path
-  double* Dinv = x;                     // x is free until the back substitution: 1/diag(L) lives there
-  auto factor_diag = [&](int K) {
-    double L[36], inv[6];
-    double* D = A + sblk(K, K);
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-      for (int j = 0; j < 6; ++j) L[6 * i + j] = (j <= i) ? D[6 * i + j] : 0.0;
-    if (!chol6(L, inv)) s_fail = 1;
-#pragma unroll
-    for (int q = 0; q < 36; ++q) D[q] = L[q];
-#pragma unroll
-    for (int q = 0; q < 6; ++q) Dinv[6 * K + q] = inv[q];
-  };
-  if (tid == 0) factor_diag(0);
-  __syncthreads();
-
-  for (int K = 0; K < nb; ++K) {
-    if (K < 6) dbg_mark(w, 2 + 3 * K, 110);
-    if (s_fail) break;                    // uniform: written before the last barrier
-    const int m = nb - K - 1;
-    // (2) rows below + rhs row:  v <- v * L_KK^-T  (forward substitution along the row)
-    {
-      const double* __restrict__ Lk = A + sblk(K, K);
-      const double* __restrict__ di = Dinv + 6 * K;
-      for (int row = tid; row < 6 * m + 1; row += nt) {
-        double* v = (row < 6 * m) ? (A + sblk(K + 1 + row / 6, K) + 6 * (row % 6)) : (y + 6 * K);
-        double o[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) o[q] = v[q];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          o[q] *= di[q];
-#pragma unroll
-          for (int c = q + 1; c < 6; ++c) o[c] = fma(-o[q], Lk[6 * c + q], o[c]);
-        }
-#pragma unroll
-        for (int q = 0; q < 6; ++q) v[q] = o[q];
-      }
-    }
-    __syncthreads();
-    if (K < 6) dbg_mark(w, 4 + 3 * K, 112);
-    // (3) trailing update of the blocks (I,J), K < J <= I, and of the rhs blocks
-    const int nblk_t = m * (m + 1) / 2;
-    if (nblk_t >= 48) {
-      // one thread per 6x6 block: 72 shared loads for 216 FMAs
-      for (int t = tid; t < nblk_t + m; t += nt) {
-        if (t < nblk_t) {
-          int I = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-          while (I * (I + 1) / 2 > t) --I;
-          while ((I + 1) * (I + 2) / 2 <= t) ++I;
-          const int J = t - I * (I + 1) / 2;
-          const double* __restrict__ Aik = A + sblk(K + 1 + I, K);
-          const double* __restrict__ Ajk = A + sblk(K + 1 + J, K);
-          double* __restrict__ Aij = A + sblk(K + 1 + I, K + 1 + J);
-          double bj[36];
-#pragma unroll
-          for (int q = 0; q < 36; ++q) bj[q] = Ajk[q];
-          // two block rows at a time: 12 independent accumulators cover the FP64 latency
-#pragma unroll
-          for (int r = 0; r < 6; r += 2) {
-            double a0[6], a1[6], c0[6], c1[6];
-#pragma unroll
-            for (int q = 0; q < 6; ++q) {
-              a0[q] = Aik[6 * r + q];
-              a1[q] = Aik[6 * r + 6 + q];
-              c0[q] = Aij[6 * r + q];
-              c1[q] = Aij[6 * r + 6 + q];
-            }
-#pragma unroll
-            for (int q = 0; q < 6; ++q) {
-#pragma unroll
-              for (int c = 0; c < 6; ++c) {
-                c0[c] = fma(-a0[q], bj[6 * c + q], c0[c]);
-                c1[c] = fma(-a1[q], bj[6 * c + q], c1[c]);
-              }
-            }
-#pragma unroll
-            for (int q = 0; q < 6; ++q) {
-              Aij[6 * r + q] = c0[q];
-              Aij[6 * r + 6 + q] = c1[q];
-            }
-          }
-          if (t == 0) factor_diag(K + 1);     // look-ahead: block (K+1,K+1) is final now
-        } else {
-          const int J = t - nblk_t;
-          const double* __restrict__ Ajk = A + sblk(K + 1 + J, K);
-          const double* yk = y + 6 * K;
-          double* yj = y + 6 * (K + 1 + J);
-#pragma unroll
-          for (int c = 0; c < 6; ++c) {
-            double acc = yj[c];
-#pragma unroll
-            for (int q = 0; q < 6; ++q) acc = fma(-yk[q], Ajk[6 * c + q], acc);
-            yj[c] = acc;
-          }
-        }
-      }
-    } else {
-      // few blocks left: one thread per block row keeps more lanes busy
-      for (int t = tid; t < 6 * nblk_t + m; t += nt) {
-        if (t < 6 * nblk_t) {
-          const int bi = t / 6, r = t - 6 * bi;
-          int I = (int)((sqrtf(8.0f * (float)bi + 1.0f) - 1.0f) * 0.5f);
-          while (I * (I + 1) / 2 > bi) --I;
-          while ((I + 1) * (I + 2) / 2 <= bi) ++I;
-          const int J = bi - I * (I + 1) / 2;
-          const double* __restrict__ Aik = A + sblk(K + 1 + I, K) + 6 * r;
-          const double* __restrict__ Ajk = A + sblk(K + 1 + J, K);
-          double* __restrict__ Aij = A + sblk(K + 1 + I, K + 1 + J) + 6 * r;
-          double a[6], acc[6];
-#pragma unroll
-          for (int q = 0; q < 6; ++q) { a[q] = Aik[q]; acc[q] = Aij[q]; }
-#pragma unroll
-          for (int q = 0; q < 6; ++q) {
-#pragma unroll
-            for (int c = 0; c < 6; ++c) acc[c] = fma(-a[q], Ajk[6 * c + q], acc[c]);
-          }
-#pragma unroll
-          for (int q = 0; q < 6; ++q) Aij[q] = acc[q];
-          if (t < 6) {                        // rows of block (K+1,K+1) = lanes 0..5 of warp 0: look-ahead
-            __syncwarp(0x3fu);
-            if (t == 0) factor_diag(K + 1);
-          }
-        } else {
-          const int J = t - 6 * nblk_t;
-          const double* __restrict__ Ajk = A + sblk(K + 1 + J, K);
-          const double* yk = y + 6 * K;
-          double* yj = y + 6 * (K + 1 + J);
-#pragma unroll
-          for (int c = 0; c < 6; ++c) {
-            double acc = yj[c];
-#pragma unroll
-            for (int q = 0; q < 6; ++q) acc = fma(-yk[q], Ajk[6 * c + q], acc);
-            yj[c] = acc;
-          }
-        }
-      }
-    }
-    __syncthreads();
-  }
-  __syncthreads();
-  dbg_mark(w, 20, 120);
-  const bool fail = s_fail != 0;
-  if (!fail) {
-    // inverse diagonal factors for the back substitution, all blocks in parallel
-    for (int t = tid; t < 6 * nb; t += nt) {
-      const int K = t / 6;
-      tri6_inv_col(A + sblk(K, K), Dinv + 6 * K, t - 6 * K, Linv + K * 36);
-    }
-    __syncthreads();
-    // backward substitution L^T x = y by ONE warp (warp-synchronous, no block barriers):
-    // x_K = L_KK^-T y_K by lanes 0..5, then y_J -= L_KJ^T x_K for J < K spread over the lanes
-    if (tid < 32) {
-      for (int K = nb - 1; K >= 0; --K) {
-        const double* __restrict__ Li = Linv + K * 36;
-        double xv = 0.0;
-        if (lane < 6) {
-          double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-          for (int r = 0; r < 6; ++r) {
-            const double t2 = (r >= lane) ? Li[6 * r + lane] * y[6 * K + r] : 0.0;
-            if (r & 1) a1 += t2; else a0 += t2;
-          }
-          xv = a0 + a1;
-          x[6 * K + lane] = xv;
-        }
-        double xk[6];
-#pragma unroll
-        for (int r = 0; r < 6; ++r) xk[r] = __shfl_sync(kFull, xv, r);
-        for (int t = lane; t < 6 * K; t += 32) {
-          const int J = t / 6, c = t - 6 * J;
-          const double* __restrict__ Akj = A + sblk(K, J);
-          double a0 = y[t], a1 = 0.0;
-#pragma unroll
-          for (int r = 0; r < 6; ++r) {
-            if (r & 1) a1 = fma(-Akj[6 * r + c], xk[r], a1); else a0 = fma(-Akj[6 * r + c], xk[r], a0);
-          }
-          y[t] = a0 + a1;
-        }
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-  } else {
-    for (int c = tid; c < n; c += nt) x[c] = 0.0;
-    __syncthreads();
-  }
-  dbg_mark(w, 21, 130);
-  bool bad = false;
-  for (int c = tid; c < n; c += nt) {
-    double v = x[c];
-    if (!isfinite(v)) { bad = true; v = 0.0; }
-    w.dp[c] = v;
-  }
-  if (bad) s_fail = 1;
-  __syncthreads();
-  if (tid == 0) ctl->solve_fail = s_fail;
-  // candidate camera poses: R <- exp(dw) R, t <- t + dt   (torch_optimizer.py:159, t additive)
-  const double* P = w.pose[cur];
-  double* Pn = w.pose[cur ^ 1];
-  for (int c = tid; c < w.n_cam; c += nt) {
-    double R[9], Rn[9], dw[3], dt[3];
-#pragma unroll
-    for (int q = 0; q < 9; ++q) R[q] = P[12 * c + q];
-    bool upd = (w.fixed[c] == 0) && (s_fail == 0);
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      double a = x[6 * c + q], b2 = x[6 * c + 3 + q];
-      dw[q] = (upd && isfinite(a)) ? a : 0.0;
-      dt[q] = (upd && isfinite(b2)) ? b2 : 0.0;
-    }
-    if (upd) so3_exp_mul(dw, R, Rn);
-#pragma unroll
-    for (int q = 0; q < 9; ++q) Pn[12 * c + q] = upd ? Rn[q] : R[q];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) Pn[12 * c + 9 + q] = P[12 * c + 9 + q] + dt[q];
-  }
-  dbg_mark(w, 22, 140);
-}
-
 // ------------------------------------------------------------------------------------------
-// Same factorisation with the next block column taken off the trailing update's critical path.
+// Right-looking blocked Cholesky with the next block column taken off the trailing update's critical path.
 // 12 warps: a PANEL group (4 warps) and a TRAILING group (8 warps), one CTA-wide barrier per block column.
 // While the trailing group applies column K to the blocks (I,J), J >= K+2, the panel group makes column K+1
 // final: rank-6 update of its blocks and of the rhs block by column K (one thread per block row), Cholesky of
 // the diagonal block by thread 0, forward substitution along the rows below.  The sequential chain per column
-// is (row update -> 6x6 factor -> row solve) instead of (row solve -> barrier -> whole trailing sweep with the
-// factor at its end -> barrier).
+// is (row update -> 6x6 factor -> row solve); measured with the clock64 trace on the C2 window (20 keyframes):
+// 630 + 1 200 + 440 clk plus 250 clk of barriers, against 4 900 clk per column for the earlier single-group
+// kernel (row solve -> barrier -> whole trailing sweep with the factor at its end -> barrier).
 // ------------------------------------------------------------------------------------------
 static constexpr int kPanelThreads = 128;
 static constexpr int kTrailThreads = 256;
-static constexpr int kSolveThreads2 = kPanelThreads + kTrailThreads;
+static constexpr int kSolveThreads = kPanelThreads + kTrailThreads;
 static constexpr int kBarPanel = 1;
 
 __device__ __forceinline__ void panel_bar() {
@@ -545,8 +249,8 @@ __device__ __forceinline__ void row_update6(double* __restrict__ c, const double
   for (int q = 0; q < 6; ++q) c[q] = acc[q];
 }
 
-__global__ void __launch_bounds__(kSolveThreads2, 1)
-k_rcs_cholesky_la(Work w) {
+__global__ void __launch_bounds__(kSolveThreads, 1)
+k_rcs_cholesky(Work w) {
   extern __shared__ double sm[];
   const int n = w.n, nb = w.n_cam;
   const int nblk = nb * (nb + 1) / 2;
@@ -666,16 +370,12 @@ k_rcs_cholesky_la(Work w) {
           row_update6(y + 6 * (K + 1), y + 6 * K, B);
         }
       }
-      if (K == 10) dbg_mark(w, 40, 200);
       if (tid < 32) {
         __syncwarp();
         if (tid == 0) factor_diag(K + 1);
       }
-      if (K == 10) dbg_mark(w, 41, 201);
       panel_bar();
-      if (K == 10) dbg_mark(w, 42, 202);
       solve_column(K + 1, tid, kPanelThreads);
-      if (K == 10) dbg_mark(w, 43, 203);
     } else {
       // ---- trailing blocks (I,J), K+2 <= J <= I, and rhs blocks J >= K+2, by column K -----------------
       const int tt = tid - kPanelThreads;
@@ -743,7 +443,6 @@ k_rcs_cholesky_la(Work w) {
       }
     }
     __syncthreads();
-    if (K == 9 || K == 10) dbg_mark(w, 35 + K, 190 + K);
   }
   __syncthreads();
   dbg_mark(w, 20, 120);
@@ -846,8 +545,6 @@ int configure_kernels() {
   cudaError_t e = cudaFuncSetAttribute(k_rcs_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kSolveSmemMax);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(k_rcs_cholesky_la, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmemMax);
-  if (e != cudaSuccess) return (int)e;
   int r = configure_band();
   if (r != 0) return r;
   r = configure_stream();
@@ -861,10 +558,7 @@ int configure_kernels() {
 
 int launch_rcs_cholesky(const Work& w, cudaStream_t s) {
   size_t smem = rcs_cholesky_smem_bytes(w.n);
-  static int v1 = -1;                   // BA_CHOL=v1: the single-group kernel (two barriers per block column)
-  if (v1 < 0) { const char* e = getenv("BA_CHOL"); v1 = (e && !strcmp(e, "v1")) ? 1 : 0; }
-  if (v1) k_rcs_cholesky<<<1, kSolveThreads, smem, s>>>(w);
-  else k_rcs_cholesky_la<<<1, kSolveThreads2, smem, s>>>(w);
+  k_rcs_cholesky<<<1, kSolveThreads, smem, s>>>(w);
   return 1;
 }
 
