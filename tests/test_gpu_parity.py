@@ -221,6 +221,25 @@ def test_repeated_observations_and_oversized_points(schur):
     _check(p, res, _oracle(p))
 
 
+@pytest.mark.parametrize("schur", ["mma", "auto"])
+def test_observations_in_any_keyframe_order_within_a_point(schur):
+    """`mp.get_observations()` is an insertion-ordered dict (torch_optimizer.py:82): a point's observations
+    need not arrive in increasing keyframe order.  The lane-per-keyframe kernel takes rising order through a
+    table-free path and anything else through its slot table; both must give the oracle's trajectory."""
+    p = synth.make_problem(n_cam=12, n_pt=600, k_mean=7.0, k_max=12, seed=5)
+    rng = np.random.default_rng(17)
+    perm = np.arange(p.n_obs)
+    for j in range(p.n_pt):
+        o0, o1 = p.pt_offsets[j], p.pt_offsets[j + 1]
+        if j % 3:                                     # every third point keeps the rising order
+            perm[o0:o1] = o0 + rng.permutation(o1 - o0)
+    p.obs_cam = np.ascontiguousarray(p.obs_cam[perm]); p.obs_uv = np.ascontiguousarray(p.obs_uv[perm])
+    s = LocalBASolver(LMConfig(schur=schur))
+    res = s.solve_local(p.intr, p.R, p.t, p.fixed, p.X, p.obs_cam, p.obs_pt, p.obs_uv, p.pt_offsets)
+    s.close()
+    _check(p, res, _oracle(p))
+
+
 def test_unsorted_points_use_the_scatter_fallback():
     """Points in random order: chunks span more cameras than the tiled kernel's window and go
     through its per-point scatter fallback; the result must not change."""

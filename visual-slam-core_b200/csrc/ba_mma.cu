@@ -481,19 +481,31 @@ k_linearize_mma(const __grid_constant__ Work w) {
       const int k = in_k;
       bool ok = k <= 32;
       int rel = -1;
-      __syncwarp();
       if (ok && lane < k) {
         rel = in_cam - base;
         if (rel < 0 || rel >= kWin) ok = false;
-        else sm.slot[wid][rel] = lane;
       }
-      __syncwarp();
-      if (rel >= 0 && rel < kWin && sm.slot[wid][rel] != lane) ok = false;     // repeated (point, keyframe)
-      ia = sm.slot[wid][lane];
-      if (ia >= 0) uv = sm.puv[wid][pb][ia];
       ok = __all_sync(kFull, ok);
-      __syncwarp();
-      sm.slot[wid][lane] = -1;
+      // which observation does camera lane `lane` serve?  Observations in strictly increasing keyframe order
+      // (the packer's and the generator's order) need no table: it is the number of observed keyframes below.
+      const int prev = __shfl_up_sync(kFull, rel, 1);
+      const bool rising = __all_sync(kFull, lane == 0 || lane >= k || rel > prev);
+      if (ok && rising) {
+        const unsigned seen_mask = __reduce_or_sync(kFull, (lane < k) ? (1u << rel) : 0u);
+        ia = ((seen_mask >> lane) & 1u) ? __popc(seen_mask & ((1u << lane) - 1u)) : -1;
+        if (ia >= 0) uv = sm.puv[wid][pb][ia];
+      } else if (ok) {
+        // any other order: through a slot table, which also finds repeated (point, keyframe) observations
+        __syncwarp();
+        if (lane < k) sm.slot[wid][rel] = lane;
+        __syncwarp();
+        const bool dup = lane < k && sm.slot[wid][rel] != lane;
+        ia = sm.slot[wid][lane];
+        if (ia >= 0) uv = sm.puv[wid][pb][ia];
+        ok = !__any_sync(kFull, dup);
+        __syncwarp();
+        sm.slot[wid][lane] = -1;
+      }
       if (kSliding && k > 0 && k <= 32) {
         int c = in_cam;
 #pragma unroll
