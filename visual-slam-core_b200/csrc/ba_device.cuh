@@ -187,27 +187,42 @@ __device__ __forceinline__ void linearize_obs(const Intr& K, const double* __res
   }
 }
 
-// accept / reject bookkeeping of one LM iteration (single thread)
-__device__ __forceinline__ void lm_accept(LmCtl* c) {
-  int it = c->iter;
-  double cand = c->cost_cand, cur = c->cost_cur;
-  bool ok = (c->solve_fail == 0) && isfinite(cand) && (cand < cur * (1.0 - c->accept_rtol));
+// accept / reject bookkeeping of one LM iteration (single thread, the tail of every iteration).  Everything it
+// needs is read up front (lm_load, which a kernel can issue before it knows that it is the one to decide): the
+// stores of lm_accept go to the same struct, so loads placed after them would each wait for their own L2 round
+// trip.
+struct LmIn {
+  int iter, solve_fail, pcg_iters_last, n_accepted, cur;
+  double cost_cur, lambda, accept_rtol, lambda_up, lambda_down, lambda_min, lambda_max;
+};
+__device__ __forceinline__ LmIn lm_load(const LmCtl* c) {
+  LmIn in;
+  in.iter = c->iter; in.solve_fail = c->solve_fail; in.pcg_iters_last = c->pcg_iters_last;
+  in.n_accepted = c->n_accepted; in.cur = c->cur;
+  in.cost_cur = c->cost_cur; in.lambda = c->lambda; in.accept_rtol = c->accept_rtol;
+  in.lambda_up = c->lambda_up; in.lambda_down = c->lambda_down;
+  in.lambda_min = c->lambda_min; in.lambda_max = c->lambda_max;
+  return in;
+}
+__device__ __forceinline__ void lm_accept(LmCtl* c, const LmIn& in, double cand) {
+  const int it = in.iter;
+  const bool ok = (in.solve_fail == 0) && isfinite(cand) && (cand < in.cost_cur * (1.0 - in.accept_rtol));
   if (it < 64) {
-    c->lambda_hist[it] = c->lambda;
+    c->lambda_hist[it] = in.lambda;
     c->cand_hist[it] = cand;
     c->accepted[it] = ok ? 1 : 0;
-    c->solve_fail_hist[it] = c->solve_fail;
-    c->pcg_iters_hist[it] = c->pcg_iters_last;
+    c->solve_fail_hist[it] = in.solve_fail;
+    c->pcg_iters_hist[it] = in.pcg_iters_last;
   }
   if (ok) {
-    c->cur ^= 1;
+    c->cur = in.cur ^ 1;
     c->cost_cur = cand;
-    c->n_accepted += 1;
-    c->lambda = fmax(c->lambda * c->lambda_down, c->lambda_min);
+    c->n_accepted = in.n_accepted + 1;
+    c->lambda = fmax(in.lambda * in.lambda_down, in.lambda_min);
   } else {
-    c->lambda = fmin(c->lambda * c->lambda_up, c->lambda_max);
+    c->lambda = fmin(in.lambda * in.lambda_up, in.lambda_max);
   }
-  if (it + 1 < 65) c->cost_hist[it + 1] = c->cost_cur;
+  if (it + 1 < 65) c->cost_hist[it + 1] = ok ? cand : in.cost_cur;
   c->iter = it + 1;
   c->cost_cand = 0.0;
   c->cost_lin = 0.0;

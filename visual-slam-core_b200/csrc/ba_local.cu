@@ -592,7 +592,6 @@ template <bool kStaged, int kG>
 __global__ void __launch_bounds__(kThreads, BA_BACKSUB_MIN_CTAS)
 k_backsub(Work w) {
   __shared__ double s_cost[kWarps];
-  __shared__ bool s_last;
   __shared__ double s_pose[kStaged ? kBackCams * 13 : 1];
   __shared__ double s_posen[kStaged ? kBackCams * 13 : 1];
   __shared__ double s_dp[kStaged ? kBackCams * 7 : 1];
@@ -716,16 +715,17 @@ k_backsub(Work w) {
 #pragma unroll
     for (int i = 0; i < kWarps; ++i) c += s_cost[i];
     atomicAdd(w.cost_cand, c);
+    // the LM state the decision needs does not change during this kernel: requested now, so that the last CTA
+    // has it by the time its ticket comes back
+    const LmIn in = lm_load(ctl);
     __threadfence();
-    unsigned t = atomicAdd(&ctl->ticket, 1u);
-    s_last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (s_last && threadIdx.x == 0 && w.world == 1) {
-    __threadfence();
-    ctl->cost_cand = *((volatile double*)w.cost_cand);
-    *w.cost_cand = 0.0;
-    lm_accept(ctl);
+    const unsigned t = atomicAdd(&ctl->ticket, 1u);
+    if (t == gridDim.x - 1 && w.world == 1) {
+      __threadfence();
+      const double cand = *((volatile double*)w.cost_cand);
+      *w.cost_cand = 0.0;
+      lm_accept(ctl, in, cand);
+    }
   }
 }
 
@@ -769,9 +769,10 @@ int launch_backsub(const Work& w, int sm_count, cudaStream_t s) {
 // accept / reject as its own kernel (multi-GPU: runs after the candidate-cost all-reduce)
 __global__ void k_accept(Work w) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    w.ctl->cost_cand = *w.cost_cand;
+    const LmIn in = lm_load(w.ctl);
+    const double cand = *w.cost_cand;
     *w.cost_cand = 0.0;
-    lm_accept(w.ctl);
+    lm_accept(w.ctl, in, cand);
   }
 }
 int launch_accept(const Work& w, cudaStream_t s) {
