@@ -293,8 +293,16 @@ def run_pose_only(args, rank, local_rank, world):
     value = world * args.steps * nF * max_iter / (ms_max / 1e3)
 
     # end to end: host buffers through ba_solve_pose_only_host (H2D / D2H inside)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a).copy()).pin_memory().numpy()
+    hR, ht, hX, huv, hfo = pin(pp.R), pin(pp.t), pin(pp.X), pin(pp.uv), pin(pp.frame_offsets)
+    hflags = pin(np.zeros(nM, dtype=np.uint8))
+    hhist = pin(np.zeros((nF, max_iter + 1), dtype=np.float64))
+    hacc = pin(np.zeros((nF, max(max_iter, 1)), dtype=np.uint8))
+
     def e2e_step():
-        return solver.solve_pose_only(pp.intr, pp.R, pp.t, pp.X, pp.uv, pp.frame_offsets)
+        np.copyto(hR, pp.R); np.copyto(ht, pp.t)
+        return solver.solve_pose_only(pp.intr, hR, ht, hX, huv, hfo, inplace=True, flags=hflags,
+                                      cost_hist=hhist, accepted=hacc)
 
     for _ in range(max(args.warmup, 3)):
         out = e2e_step()
@@ -327,7 +335,7 @@ def run_pose_only(args, rank, local_rank, world):
                          "note": f"the matches are read once from HBM and then {2 * max_iter} times from L2 / L1 (linearise + candidate "
                                  f"cost per LM iteration): the kernel is bound by FP64 latency, not by HBM"},
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": "LocalBASolver.solve_pose_only -> ba_solve_pose_only_host"},
+                    "api": "LocalBASolver.solve_pose_only(inplace, pinned host buffers) -> ba_solve_pose_only_host"},
             "gpu_launches": args.steps, "clocks": clocks}
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import lm_oracle as O

@@ -39,3 +39,25 @@ def test_pose_only_full_size_properties():
                            np.zeros((0, 2), np.float32), np.zeros(1, np.int32))
     assert r["R"].shape == (0, 3, 3)
     s2.close()
+
+
+def test_pose_only_inplace_with_caller_buffers_equals_the_copying_call():
+    """`inplace=True` refines the caller's R / t and fills the caller's flags / cost_hist / accepted (the
+    pinned-buffer path bench.py times end to end); results are those of the default call, bit for bit."""
+    pp = synth.make_pose_only(n_frames=9, n_match=200, seed=4, ragged=True)
+    s = LocalBASolver(LMConfig())
+    a = s.solve_pose_only(pp.intr, pp.R, pp.t, pp.X, pp.uv, pp.frame_offsets)
+    R, t = pp.R.copy(), pp.t.copy()
+    nM, nF, mi = pp.X.shape[0], pp.R.shape[0], LMConfig().max_iter
+    flags = np.full(nM, 7, np.uint8); hist = np.zeros((nF, mi + 1)); acc = np.zeros((nF, mi), np.uint8)
+    b = s.solve_pose_only(pp.intr, R, t, pp.X, pp.uv, pp.frame_offsets, inplace=True, flags=flags,
+                          cost_hist=hist, accepted=acc)
+    assert b["R"].base is R or b["R"] is R
+    np.testing.assert_array_equal(R, a["R"]); np.testing.assert_array_equal(t, a["t"])
+    np.testing.assert_array_equal(flags, a["flags"]); np.testing.assert_array_equal(hist, a["cost_hist"])
+    np.testing.assert_array_equal(acc, a["accepted"])
+    with pytest.raises(ValueError):
+        s.solve_pose_only(pp.intr, R.astype(np.float32), t, pp.X, pp.uv, pp.frame_offsets, inplace=True)
+    with pytest.raises(ValueError):
+        s.solve_pose_only(pp.intr, R, t, pp.X, pp.uv, pp.frame_offsets, flags=np.zeros(3, np.uint8))
+    s.close()

@@ -203,10 +203,24 @@ class LocalBASolver:
         return rep
 
     # ------------------------------------------------------------------ pose-only
-    def solve_pose_only(self, intr, R, t, X, uv, frame_offsets, want_hist: bool = True):
+    def solve_pose_only(self, intr, R, t, X, uv, frame_offsets, want_hist: bool = True, inplace: bool = False,
+                        flags=None, cost_hist=None, accepted=None):
+        """Batched motion-only LM (one free pose per frame, points fixed).
+
+        `inplace=True` refines the caller's float64 C-contiguous `R` (n,3,3) / `t` (n,3) where they are;
+        `flags` (uint8 [n_match]), `cost_hist` (float64 [n, max_iter+1]) and `accepted` (uint8 [n, max_iter])
+        may be passed in to be filled.  With all of them (and X, uv, frame_offsets) in pinned host memory the
+        host<->device copies inside the call are plain DMA transfers."""
         intr = np.ascontiguousarray(intr, dtype=np.float64)
-        R = np.array(R, dtype=np.float64, order="C").reshape(-1, 3, 3)
-        t = np.array(t, dtype=np.float64, order="C").reshape(-1, 3)
+        if inplace:
+            for name, a in (("R", R), ("t", t)):
+                if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+                    raise ValueError(f"{name} must be C-contiguous float64 for inplace=True")
+            R = R.reshape(-1, 3, 3)
+            t = t.reshape(-1, 3)
+        else:
+            R = np.array(R, dtype=np.float64, order="C").reshape(-1, 3, 3)
+            t = np.array(t, dtype=np.float64, order="C").reshape(-1, 3)
         X = np.ascontiguousarray(X, dtype=np.float32).reshape(-1, 3)
         uv = np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 2)
         fo = np.ascontiguousarray(frame_offsets, dtype=np.int32)
@@ -214,17 +228,26 @@ class LocalBASolver:
         if fo.shape[0] != nF + 1 or uv.shape[0] != nM or (nF and int(fo[-1]) != nM):
             raise ValueError("inconsistent array sizes")
         mi = self.cfg.max_iter
-        flags = np.zeros(nM, dtype=np.uint8)
-        hist = np.zeros((nF, mi + 1), dtype=np.float64) if want_hist else None
-        acc = np.zeros((nF, max(mi, 1)), dtype=np.uint8) if want_hist else None
+
+        def _out(a, shape, name):
+            if a is None:
+                return np.zeros(shape, dtype=np.float64 if name == "cost_hist" else np.uint8)
+            want = np.float64 if name == "cost_hist" else np.uint8
+            if a.dtype != want or not a.flags["C_CONTIGUOUS"] or a.size != int(np.prod(shape)):
+                raise ValueError(f"{name} must be a C-contiguous {np.dtype(want).name} array of shape {shape}")
+            return a
+
+        flags = _out(flags, (nM,), "flags")
+        hist = _out(cost_hist, (nF, mi + 1), "cost_hist") if (want_hist or cost_hist is not None) else None
+        acc = _out(accepted, (nF, max(mi, 1)), "accepted") if (want_hist or accepted is not None) else None
         ms = C.c_float(0.0)
         with self._lock:
             rc = self.lib.ba_solve_pose_only_host(
                 self._h, nF, nM, _dptr(intr), _ptr(R), _ptr(t), _ptr(X), _ptr(uv), _ptr(fo),
                 _ptr(flags), _ptr(hist), _ptr(acc), C.byref(ms))
             _lib.check(self.lib, self._h, rc, "ba_solve_pose_only_host")
-        return dict(R=R, t=t, flags=flags, cost_hist=hist,
-                    accepted=None if acc is None else acc[:, :mi], gpu_ms=float(ms.value))
+        return dict(R=R, t=t, flags=flags, cost_hist=None if hist is None else hist.reshape(nF, mi + 1),
+                    accepted=None if acc is None else acc.reshape(nF, max(mi, 1))[:, :mi], gpu_ms=float(ms.value))
 
     # ------------------------------------------------------------------ inspection (tests)
     def debug_linearize(self, intr, R, t, fixed, X, obs_cam, obs_pt, obs_uv, pt_offsets, lam):
