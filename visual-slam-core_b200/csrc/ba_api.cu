@@ -233,6 +233,8 @@ extern "C" int ba_create(const ba_params* params, int device, ba_handle** out) {
 extern "C" int ba_set_params(ba_handle* h, const ba_params* params) {
   if (!h || check_params(params) != BA_OK) return BA_ERR_INVALID;
   h->prm = *params;
+  // the captured LM loop depends on the solver / Schur kind and the iteration count
+  if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; h->graph_key = ba_handle::GraphKey(); }
   return BA_OK;
 }
 
@@ -446,7 +448,11 @@ static int enqueue_lm_loop(ba_handle* h, const Work& w, int schur, cudaStream_t 
   const int pcg_grid = sparse ? pcg_grid_size(w.n_cam, h->sm_count) : 0;
   for (int it = 0; it < h->prm.max_iter; ++it) {
     prof_mark(h, TAG_LIN, s);
-    launches += launch_linearize(w, schur, h->sm_count, s);
+    {
+      const int nl = launch_linearize(w, schur, h->sm_count, s);
+      if (nl < 0) { h->err = std::string("linearise launch: ") + cudaGetErrorString(cudaGetLastError()); return BA_ERR_CUDA; }
+      launches += nl;
+    }
     if (h->world > 1) {
       prof_mark(h, TAG_COMM, s);
       int r = g_nccl.allreduce(w.S, w.S, nred, kNcclDouble, kNcclSum, h->comm, s);
