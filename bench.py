@@ -481,7 +481,7 @@ def run_b200(args, rank, local_rank, world):
     e2e_value = n_windows * args.steps * max_iter / float(te.item())
     import ctypes as C
     from visual_slam_core_b200 import _lib
-    h2d = sum(a.nbytes for a in (hR, ht, hfixed, hX, hoc, hop, huv, hoff))
+    h2d = sum(a.nbytes for a in (hR, ht, hfixed, hX, hoc, huv, hoff))   # obs_pt is expanded from pt_offsets on the device
     d2h = hR.nbytes + ht.nbytes + hX.nbytes + hflags.nbytes + 2240   # + LM control block (report)
     final_cost = float(res.cost_hist[-1])
 

@@ -130,7 +130,9 @@ int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t n_obs,
                    const int32_t* pt_offsets,
                    uint8_t* flags, void* stream, ba_report* report);
 
-/* Same, HOST pointers; H2D and D2H copies are inside the call. */
+/* Same, HOST pointers; H2D and D2H copies are inside the call.  obs_pt is NOT uploaded: the device copy is
+ * expanded from pt_offsets (the two describe the same thing; the argument may be NULL here).  The small pose
+ * arrays travel as one copy each way through a pinned staging buffer of the handle. */
 int ba_solve_local_host(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t n_obs,
                         const double intr[4],
                         double* cam_R, double* cam_t, const uint8_t* cam_fixed,

@@ -83,6 +83,9 @@ struct ba_handle {
   // staging for the host-pointer API
   DevBuf d_R, d_t, d_fixed, d_X, d_ocam, d_opt, d_ouv, d_off, d_flags, d_hist, d_acc, d_foff;
   LmCtl* h_ctl = nullptr;         // pinned
+  double* h_small = nullptr;      // pinned staging of R | t | fixed for the host-pointer API
+  size_t h_small_cap = 0;         // bytes
+  DevBuf d_small;
   cudaStream_t stream = nullptr;  // used by the host API
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // CUDA graph cache of the LM loop
@@ -251,6 +254,8 @@ extern "C" int ba_destroy(ba_handle* h) {
   if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  if (h->h_small) cudaFreeHost(h->h_small);
+  if (h->d_small.p) cudaFree(h->d_small.p);
   if (h->h_nnzb) cudaFreeHost(h->h_nnzb);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -606,45 +611,57 @@ extern "C" int ba_solve_local_host(ba_handle* h, int32_t n_cam, int32_t n_pt, in
                                    const uint8_t* cam_fixed, double* X, const int32_t* obs_cam,
                                    const int32_t* obs_pt, const float* obs_uv,
                                    const int32_t* pt_offsets, uint8_t* flags, ba_report* report) {
+  (void)obs_pt;                    // expanded from pt_offsets on the device
   if (!h) return BA_ERR_INVALID;
   if (n_cam <= 0 || n_pt < 0 || n_obs < 0 || !intr || !cam_R || !cam_t || !cam_fixed ||
-      (n_pt > 0 && (!X || !pt_offsets)) || (n_obs > 0 && (!obs_cam || !obs_pt || !obs_uv)))
+      (n_pt > 0 && (!X || !pt_offsets)) || (n_obs > 0 && (!obs_cam || !obs_uv)))
     return BA_ERR_INVALID;
   CK(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
   int rc;
-  if ((rc = ensure(h, h->d_R, sizeof(double) * 9 * (size_t)n_cam))) return rc;
-  if ((rc = ensure(h, h->d_t, sizeof(double) * 3 * (size_t)n_cam))) return rc;
-  if ((rc = ensure(h, h->d_fixed, (size_t)n_cam))) return rc;
+  // R | t | fixed in one pinned staging record: one copy up, one copy (R | t) down
+  const size_t nR = 9 * (size_t)n_cam, nT = 3 * (size_t)n_cam;
+  const size_t small_bytes = sizeof(double) * (nR + nT) + (size_t)n_cam;
+  if (small_bytes > h->h_small_cap) {
+    if (h->h_small) { cudaFreeHost(h->h_small); h->h_small = nullptr; h->h_small_cap = 0; }
+    const size_t cap = small_bytes + small_bytes / 4 + 256;
+    CK(cudaMallocHost((void**)&h->h_small, cap));
+    h->h_small_cap = cap;
+  }
+  if ((rc = ensure(h, h->d_small, small_bytes))) return rc;
   if ((rc = ensure(h, h->d_X, sizeof(double) * 3 * (size_t)(n_pt + 1)))) return rc;
   if ((rc = ensure(h, h->d_ocam, sizeof(int32_t) * (size_t)(n_obs + 1)))) return rc;
   if ((rc = ensure(h, h->d_opt, sizeof(int32_t) * (size_t)(n_obs + 1)))) return rc;
   if ((rc = ensure(h, h->d_ouv, sizeof(float) * 2 * (size_t)(n_obs + 1)))) return rc;
   if ((rc = ensure(h, h->d_off, sizeof(int32_t) * (size_t)(n_pt + 1)))) return rc;
   if ((rc = ensure(h, h->d_flags, (size_t)(n_obs + 1)))) return rc;
-  CK(cudaMemcpyAsync(h->d_R.p, cam_R, sizeof(double) * 9 * (size_t)n_cam, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(h->d_t.p, cam_t, sizeof(double) * 3 * (size_t)n_cam, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(h->d_fixed.p, cam_fixed, (size_t)n_cam, cudaMemcpyHostToDevice, s));
+  memcpy(h->h_small, cam_R, sizeof(double) * nR);
+  memcpy(h->h_small + nR, cam_t, sizeof(double) * nT);
+  memcpy(h->h_small + nR + nT, cam_fixed, (size_t)n_cam);
+  double* d_R = (double*)h->d_small.p;
+  double* d_t = d_R + nR;
+  const uint8_t* d_fixed = (const uint8_t*)(d_t + nT);
+  CK(cudaMemcpyAsync(h->d_small.p, h->h_small, small_bytes, cudaMemcpyHostToDevice, s));
   if (n_pt > 0) {
-    CK(cudaMemcpyAsync(h->d_X.p, X, sizeof(double) * 3 * (size_t)n_pt, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(h->d_off.p, pt_offsets, sizeof(int32_t) * (size_t)(n_pt + 1), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_X.p, X, sizeof(double) * 3 * (size_t)n_pt, cudaMemcpyHostToDevice, s));
+    if (n_obs > 0) launch_expand_obs_pt((const int*)h->d_off.p, n_pt, (int*)h->d_opt.p, s);
   }
   if (n_obs > 0) {
     CK(cudaMemcpyAsync(h->d_ocam.p, obs_cam, sizeof(int32_t) * (size_t)n_obs, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_opt.p, obs_pt, sizeof(int32_t) * (size_t)n_obs, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(h->d_ouv.p, obs_uv, sizeof(float) * 2 * (size_t)n_obs, cudaMemcpyHostToDevice, s));
   }
-  rc = ba_solve_local(h, n_cam, n_pt, n_obs, intr, (double*)h->d_R.p, (double*)h->d_t.p,
-                      (const uint8_t*)h->d_fixed.p, (double*)h->d_X.p, (const int32_t*)h->d_ocam.p,
-                      (const int32_t*)h->d_opt.p, (const float*)h->d_ouv.p,
+  rc = ba_solve_local(h, n_cam, n_pt, n_obs, intr, d_R, d_t, d_fixed, (double*)h->d_X.p,
+                      (const int32_t*)h->d_ocam.p, (const int32_t*)h->d_opt.p, (const float*)h->d_ouv.p,
                       (const int32_t*)h->d_off.p, flags ? (uint8_t*)h->d_flags.p : nullptr, s, nullptr);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(cam_R, h->d_R.p, sizeof(double) * 9 * (size_t)n_cam, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(cam_t, h->d_t.p, sizeof(double) * 3 * (size_t)n_cam, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h->h_small, h->d_small.p, sizeof(double) * (nR + nT), cudaMemcpyDeviceToHost, s));
   if (n_pt > 0) CK(cudaMemcpyAsync(X, h->d_X.p, sizeof(double) * 3 * (size_t)n_pt, cudaMemcpyDeviceToHost, s));
   if (flags && n_obs > 0) CK(cudaMemcpyAsync(flags, h->d_flags.p, (size_t)n_obs, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(h->h_ctl, h->ctl.p, sizeof(LmCtl), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  memcpy(cam_R, h->h_small, sizeof(double) * nR);
+  memcpy(cam_t, h->h_small + nR, sizeof(double) * nT);
   dump_dbg(h);
   if (report) {
     float ms = 0.f;

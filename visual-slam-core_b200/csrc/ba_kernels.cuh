@@ -112,6 +112,7 @@ int launch_backsub(const Work& w, int sm_count, cudaStream_t s);
 int launch_accept(const Work& w, cudaStream_t s);
 int launch_finalize(const Work& w, double* R_out, double* t_out, double* X_out,
                     unsigned char* flags, cudaStream_t s);
+int launch_expand_obs_pt(const int* pt_off, int n_pt, int* obs_pt, cudaStream_t s);   // CSR offsets -> point of every observation
 int launch_eval_cost(const Work& w, const double* pose, const double* X, double* out,
                      double delta, cudaStream_t s);
 int configure_tiled();

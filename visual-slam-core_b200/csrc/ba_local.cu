@@ -766,6 +766,24 @@ int launch_backsub(const Work& w, int sm_count, cudaStream_t s) {
   return 1;
 }
 
+// point index of every observation from the CSR offsets (host-pointer API: 4 bytes per observation that need not
+// cross PCIe); a warp per point, so long observation lists are written coalesced
+__global__ void k_expand_obs_pt(const int* __restrict__ pt_off, int n_pt, int* __restrict__ obs_pt) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+  for (int j = warp; j < n_pt; j += nwarp) {
+    const int o0 = __ldg(pt_off + j), o1 = __ldg(pt_off + j + 1);
+    for (int o = o0 + lane; o < o1; o += 32) obs_pt[o] = j;
+  }
+}
+int launch_expand_obs_pt(const int* pt_off, int n_pt, int* obs_pt, cudaStream_t s) {
+  if (n_pt <= 0) return 0;
+  int blocks = (n_pt + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_expand_obs_pt<<<blocks, 256, 0, s>>>(pt_off, n_pt, obs_pt);
+  return 1;
+}
+
 // accept / reject as its own kernel (multi-GPU: runs after the candidate-cost all-reduce)
 __global__ void k_accept(Work w) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
