@@ -15,6 +15,7 @@ The outer loop is over points, so the list is already sorted by point: `pt_offse
 """
 from __future__ import annotations
 
+import operator
 from dataclasses import dataclass
 from typing import Any, List
 
@@ -161,6 +162,24 @@ def pack_initial(keyframes: List[Any], map_points: List[Any]) -> PackedInitial:
 # ---------------------------------------------------------------------------------------------
 # fast path: an incremental structure-of-arrays mirror of the observation graph
 # ---------------------------------------------------------------------------------------------
+_ID_OF = operator.attrgetter("id")
+
+
+def _stable_order_by(keys: np.ndarray, n_keys: int) -> np.ndarray:
+    """argsort(keys, kind="stable") for small non-negative integer keys: a counting sort through scipy's
+    COO -> CSR conversion when scipy is there (it keeps the input order inside a row)."""
+    try:
+        from scipy.sparse import coo_matrix
+        n = keys.shape[0]
+        csr = coo_matrix((np.arange(1, n + 1, dtype=np.int32), (keys, np.arange(n, dtype=np.int32))),
+                         shape=(max(n_keys, 1), max(n, 1))).tocsr()
+        if csr.nnz == n:
+            return csr.indices.astype(np.int64)
+    except Exception:                                   # no scipy: numpy's merge sort
+        pass
+    return np.argsort(keys, kind="stable")
+
+
 class ObservationTable:
     """Append-only SoA mirror of `KeyFrame.add_map_point` / `MapPoint.add_observation`
     (`map/keyframe.py:82-86`, `map/map_point.py:37-39`): one row (keyframe_id, point id, cam_id,
@@ -249,6 +268,33 @@ class ObservationTable:
         if orig_remove is not None:
             cls.remove_map_point = orig_remove
 
+    @staticmethod
+    def _lookup(window_keys: np.ndarray, row_keys: np.ndarray, last_wins: bool) -> np.ndarray:
+        """Window position of every table row's key (int32, -1: not in the window)."""
+        m = window_keys.shape[0]
+        out = np.full(row_keys.shape[0], -1, dtype=np.int32)
+        if m == 0 or row_keys.shape[0] == 0:
+            return out
+        lo, hi = int(window_keys.min()), int(window_keys.max())
+        if lo >= 0 and hi < 8 * (m + row_keys.shape[0]) + (1 << 20):
+            lut = np.full(hi + 2, -1, dtype=np.int32)
+            pos = np.arange(m, dtype=np.int32)
+            if last_wins:
+                lut[window_keys] = pos                  # duplicate ids: the later assignment stays
+            else:
+                lut[window_keys[::-1]] = pos[::-1]      # duplicate ids: the first occurrence stays
+            inside = (row_keys >= 0) & (row_keys <= hi)
+            return lut[np.where(inside, row_keys, hi + 1)]          # lut[hi + 1] is -1
+        order = np.argsort(window_keys, kind="stable")
+        skeys = window_keys[order]
+        pos = np.searchsorted(skeys, row_keys, side="right" if last_wins else "left")
+        if last_wins:
+            pos -= 1
+        ok = (pos >= 0) & (pos < m)
+        ok &= skeys[np.clip(pos, 0, m - 1)] == row_keys
+        out[ok] = order[pos[ok]]
+        return out
+
     def pack(self, keyframes: List[Any], map_points: List[Any]) -> PackedWindow:
         """Same result as `pack_window(keyframes, map_points)` for a graph that was built through the
         hooked `add_map_point` (observation order inside a point = insertion order, as
@@ -266,26 +312,33 @@ class ObservationTable:
             t[i] = np.asarray(kf.t_w2c, dtype=np.float32).reshape(3)
             fixed[i] = 1 if kf is kf_fixed else 0
             kf_ids[i] = kf.keyframe_id
-        X = (np.array([mp.position for mp in map_points], dtype=np.float32).reshape(n_pt, 3).astype(np.float64)
-             if n_pt else np.zeros((0, 3), dtype=np.float64))
-        mp_keys = np.fromiter((self.point_key(mp) for mp in map_points), dtype=np.int64, count=n_pt)
+        if n_pt:
+            try:                                        # positions are (3,) arrays: one concatenation, one rounding
+                X = np.concatenate([mp.position for mp in map_points]).astype(np.float32).astype(np.float64).reshape(n_pt, 3)
+            except ValueError:                          # a position that is not a flat array of three
+                X = np.array([mp.position for mp in map_points], dtype=np.float32).reshape(n_pt, 3).astype(np.float64)
+        else:
+            X = np.zeros((0, 3), dtype=np.float64)
+        try:
+            mp_keys = np.fromiter(map(_ID_OF, map_points), dtype=np.int64, count=n_pt)
+        except AttributeError:                          # points without an `id`: the object identity is the key
+            mp_keys = np.fromiter((self.point_key(mp) for mp in map_points), dtype=np.int64, count=n_pt)
 
         n = self._n
-        rows = np.flatnonzero(self._alive[:n])
-        # keyframe_id -> window row (a later duplicate id wins, as the dict at :61 does)
-        order_kf = np.argsort(kf_ids, kind="stable")
-        skf = kf_ids[order_kf]
-        pos = np.searchsorted(skf, self._kf[rows], side="right") - 1
-        hit = (pos >= 0) & (skf[np.clip(pos, 0, None)] == self._kf[rows])
-        rows, cam_row = rows[hit], order_kf[pos[hit]]
-        order_mp = np.argsort(mp_keys, kind="stable")
-        smp = mp_keys[order_mp]
-        posm = np.searchsorted(smp, self._mp[rows], side="left")
-        hitm = (posm < n_pt) & (smp[np.clip(posm, 0, max(n_pt - 1, 0))] == self._mp[rows]) if n_pt else np.zeros(0, bool)
-        rows, cam_row, pt_row = rows[hitm], cam_row[hitm], order_mp[posm[hitm]]
-        # group by point; inside a point by keyframe in first-insertion order, then by insertion
-        # (= the nested dict iteration of the reference's packing loop, :80-95)
-        o = np.lexsort((rows, self._grp[rows], pt_row))
+        alive = self._alive[:n]
+        # key -> window row through a lookup table when the ids are small integers (the reference's global
+        # counters), through a sorted search otherwise (object identities)
+        cam_of = self._lookup(kf_ids, self._kf[:n], last_wins=True)      # a later duplicate id wins, as the dict at :61 does
+        pt_of = self._lookup(mp_keys, self._mp[:n], last_wins=False)
+        rows = np.flatnonzero(alive & (cam_of >= 0) & (pt_of >= 0))
+        cam_row, pt_row = cam_of[rows], pt_of[rows]
+        # group by point; inside a point by keyframe in first-insertion order, then by insertion (= the nested
+        # dict iteration of the reference's packing loop, :80-95).  Rows are in insertion order already, so
+        # when no (keyframe, point) pair was observed twice a stable counting sort by point is all it takes.
+        if np.array_equal(self._grp[rows], rows):
+            o = _stable_order_by(pt_row, n_pt)
+        else:
+            o = np.lexsort((rows, self._grp[rows], pt_row))
         rows, cam_row, pt_row = rows[o], cam_row[o], pt_row[o]
         pt_offsets = np.zeros(n_pt + 1, dtype=np.int32)
         np.cumsum(np.bincount(pt_row, minlength=n_pt), out=pt_offsets[1:])
