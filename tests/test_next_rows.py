@@ -57,6 +57,36 @@ def test_observation_table_multi_sensor_order_and_removal():
         table.uninstall()
 
 
+def test_observation_table_key_lookup_paths_and_empty_windows():
+    """Small integer ids go through look-up tables, huge ids (object identities, sparse counters) through a
+    sorted search; an empty point list and a window without recorded observations pack to nothing."""
+    cam = refgraph.Camera(1280, 720, 700, 700, 640, 360)
+
+    class Point:                                        # no `id`: the object identity is the key
+        def __init__(self, x):
+            self.position = np.asarray(x, dtype=np.float64)
+
+        def get_observations(self):
+            return self.obs
+
+    kps = [refgraph.KeyPoint(1.0, 2.0), refgraph.KeyPoint(3.0, 4.0)]
+    kfs = [refgraph.KeyFrame(cam, [list(kps)], np.eye(3), np.zeros(3)) for _ in range(2)]
+    kfs[1].keyframe_id = 900_000_000_000                # far outside any look-up table
+    pts = [Point([0, 0, 1]), Point([1, 0, 2])]
+    table = packing.ObservationTable()
+    table.add(kfs[0], 0, 0, pts[0]); table.add(kfs[1], 0, 1, pts[0]); table.add(kfs[1], 0, 0, pts[1])
+    pts[0].obs = {kfs[0].keyframe_id: {0: 0}, kfs[1].keyframe_id: {0: 1}}
+    pts[1].obs = {kfs[1].keyframe_id: {0: 0}}
+    pw = table.pack(kfs, pts)
+    _assert_same_window(pw, packing.pack_window(kfs, pts))
+    np.testing.assert_array_equal(pw.obs_cam, [0, 1, 1])
+    np.testing.assert_array_equal(pw.pt_offsets, [0, 2, 3])
+    assert table.pack(kfs, []).n_obs == 0
+    stranger = [refgraph.KeyFrame(cam, [[]], np.eye(3), np.zeros(3))]
+    empty = table.pack(stranger, pts)
+    assert empty.n_obs == 0 and empty.pt_offsets.tolist() == [0, 0, 0]
+
+
 def test_fast_path_is_faster_on_a_real_window():
     import time
     p = synth.make_problem("T2", seed=3)
