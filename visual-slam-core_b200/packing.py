@@ -64,35 +64,42 @@ def pack_window(keyframes: List[Any], map_points: List[Any]) -> PackedWindow:
     else:
         X = np.zeros((0, 3), dtype=np.float64)
 
+    # the reference's nested loop (:74-95), kept loop for loop; what can leave the interpreter does: the point
+    # index of an observation comes from the per-point counts, the appends are bound once
     obs_cam: List[int] = []
-    obs_pt: List[int] = []
     obs_cid: List[int] = []
     obs_uv: List[Any] = []
-    counts = np.zeros(n_pt, dtype=np.int64)
+    counts: List[int] = []
+    add_cam, add_cid, add_uv, add_count = obs_cam.append, obs_cid.append, obs_uv.append, counts.append
     kps_of = [keyframes[i].keypoints for i in range(n_cam)]
-    for j, mp in enumerate(map_points):
+    index_of = pose_index.get
+    for mp in map_points:
         c0 = len(obs_cam)
         for kf_id, cams in mp.get_observations().items():
-            i = pose_index.get(kf_id)
+            i = index_of(kf_id)
             if i is None:
                 continue
             kps = kps_of[i]
+            n_sensors = len(kps)
             for cam_id, kp_idx in cams.items():
-                if cam_id >= len(kps):
+                if cam_id >= n_sensors:
                     continue
-                if kp_idx >= len(kps[cam_id]):
+                kp = kps[cam_id]
+                if kp_idx >= len(kp):
                     continue
-                obs_uv.append(kps[cam_id][kp_idx].pt)
-                obs_cam.append(i)
-                obs_pt.append(j)
-                obs_cid.append(cam_id)
-        counts[j] = len(obs_cam) - c0
+                add_uv(kp[kp_idx].pt)
+                add_cam(i)
+                add_cid(cam_id)
+        add_count(len(obs_cam) - c0)
 
     pt_offsets = np.zeros(n_pt + 1, dtype=np.int32)
-    np.cumsum(counts, out=pt_offsets[1:])
+    if n_pt:
+        np.cumsum(np.asarray(counts, dtype=np.int64), out=pt_offsets[1:])
+    obs_pt = np.repeat(np.arange(n_pt, dtype=np.int32), np.asarray(counts, dtype=np.int64)) if n_pt \
+        else np.zeros(0, dtype=np.int32)
     return PackedWindow(
         intr=intr, R=R, t=t, fixed=fixed, X=X,
-        obs_cam=np.asarray(obs_cam, dtype=np.int32), obs_pt=np.asarray(obs_pt, dtype=np.int32),
+        obs_cam=np.asarray(obs_cam, dtype=np.int32), obs_pt=obs_pt,
         obs_uv=np.asarray(obs_uv, dtype=np.float32).reshape(-1, 2),
         obs_cam_id=np.asarray(obs_cid, dtype=np.int32), pt_offsets=pt_offsets)
 
