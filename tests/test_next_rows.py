@@ -87,6 +87,59 @@ def test_observation_table_key_lookup_paths_and_empty_windows():
     assert empty.n_obs == 0 and empty.pt_offsets.tolist() == [0, 0, 0]
 
 
+def test_c_packer_loop_equals_the_python_loop(monkeypatch):
+    """`csrc/fastpack.c` walks the object graph exactly as `pack_window`'s Python loop does (iteration order,
+    the two skip rules, negative indices as Python indexes them); containers that are not exact dicts / lists
+    send the call back to the Python loop."""
+    from visual_slam_core_b200 import _build
+    try:
+        _build.build_fastpack()
+    except RuntimeError as e:                              # no compiler / no Python.h on this machine
+        pytest.skip(str(e))
+    fp = packing._load_fastpack()
+    assert fp is not None
+
+    def both(kfs, pts):
+        monkeypatch.setattr(packing, "_fastpack", fp)
+        a = packing.pack_window(kfs, pts)
+        monkeypatch.setattr(packing, "_fastpack", None)
+        b = packing.pack_window(kfs, pts)
+        _assert_same_window(a, b)
+        for f in ("obs_cam", "obs_pt", "obs_uv", "obs_cam_id", "pt_offsets"):
+            assert getattr(a, f).dtype == getattr(b, f).dtype and getattr(a, f).flags["WRITEABLE"]
+        return a
+
+    for name in ("a", "b", "c"):
+        g = load_golden(name)
+        cam, kfs, mps = graph_from_golden(g)
+        window = kfs[: int(g["n_kf"])]
+        both(window, window_points(window))
+        both(kfs[1:], window_points(kfs[1:]))              # keyframes outside the window are skipped
+    # two sensors, out-of-range sensor / keypoint indices (skipped), a negative keypoint index (last keypoint)
+    cam = refgraph.Camera(1280, 720, 700, 700, 640, 360)
+    kps = lambda n: [refgraph.KeyPoint(10.0 * i, 5.0 * i) for i in range(n)]
+    kfs = [refgraph.KeyFrame(cam, [kps(4), kps(3)], np.eye(3), np.zeros(3)) for _ in range(3)]
+    mps = [refgraph.MapPoint([0.1 * j, 0.0, 5.0]) for j in range(3)]
+    mps[0].add_observation(kfs[0].keyframe_id, 0, 1); mps[0].add_observation(kfs[1].keyframe_id, 1, 2)
+    mps[0].add_observation(kfs[0].keyframe_id, 1, 0)
+    mps[1].add_observation(kfs[2].keyframe_id, 2, 0)        # sensor 2 does not exist
+    mps[1].add_observation(kfs[2].keyframe_id, 1, 3)        # keypoint 3 of sensor 1 does not exist
+    mps[1].add_observation(kfs[1].keyframe_id, 0, -1)       # Python indexes from the end
+    mps[2].add_observation(12345678, 0, 0)                  # a keyframe that is not in the window
+    pw = both(kfs, mps)
+    assert pw.n_obs == 4 and pw.pt_offsets.tolist() == [0, 3, 4, 4]
+    np.testing.assert_array_equal(pw.obs_uv[3], [30.0, 15.0])
+
+    class Observed(dict):                                   # not an exact dict: the C loop declines
+        pass
+
+    orig = mps[0].get_observations
+    mps[0].get_observations = lambda: Observed(orig())
+    assert fp.pack_observations(mps, {kf.keyframe_id: i for i, kf in enumerate(kfs)}, [kf.keypoints for kf in kfs]) is None
+    both(kfs, mps)
+    assert both(kfs, []).n_obs == 0
+
+
 def test_fast_path_is_faster_on_a_real_window():
     import time
     p = synth.make_problem("T2", seed=3)

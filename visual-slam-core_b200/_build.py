@@ -30,7 +30,7 @@ def _stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps: List[str] = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps: List[str] = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
     deps.append(os.path.join(os.path.dirname(HERE), "include", "b200ba.h"))
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
@@ -66,3 +66,32 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print("\n".join(log))
     return LIB_PATH
+
+
+# ---------------------------------------------------------------------------------------------
+# host-side helper: the packer's observation loop as a CPython extension (no CUDA; optional)
+# ---------------------------------------------------------------------------------------------
+FASTPACK_SRC = os.path.join(CSRC, "fastpack.c")
+
+
+def fastpack_path() -> str:
+    import sysconfig
+    return os.path.join(HERE, "_fastpack" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_fastpack(force: bool = False) -> str:
+    """gcc -shared of csrc/fastpack.c next to this file.  Raises when there is no compiler or no Python.h;
+    packing.py treats the extension as optional and keeps its Python loop."""
+    import sysconfig
+    out = fastpack_path()
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(FASTPACK_SRC):
+        return out
+    cc = os.environ.get("CC") or shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        raise RuntimeError("no C compiler for the packer extension")
+    inc = sysconfig.get_paths()["include"]
+    cmd = [cc, "-O2", "-fPIC", "-shared", "-Wall", "-I", inc, FASTPACK_SRC, "-o", out]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"packer extension failed to build:\n{r.stdout}")
+    return out

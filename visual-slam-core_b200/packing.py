@@ -24,6 +24,27 @@ import numpy as np
 MIN_OBSERVATIONS = 10   # torch_optimizer.py:99-101
 
 
+def _load_fastpack():
+    """The observation loop as a CPython extension (csrc/fastpack.c), built in-tree by `_build.build_fastpack`
+    (`__graft_entry__.build()` does it).  Optional: without it the Python loop below does the same work."""
+    import importlib.util
+    import os
+    try:
+        from . import _build
+        path = _build.fastpack_path()
+        if not os.path.exists(path):
+            return None
+        spec = importlib.util.spec_from_file_location("_fastpack", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    except Exception:
+        return None
+
+
+_fastpack = _load_fastpack()
+
+
 @dataclass
 class PackedWindow:
     intr: np.ndarray        # (4,) f64 (float32-valued)
@@ -64,6 +85,24 @@ def pack_window(keyframes: List[Any], map_points: List[Any]) -> PackedWindow:
     else:
         X = np.zeros((0, 3), dtype=np.float64)
 
+    kps_of = [keyframes[i].keypoints for i in range(n_cam)]
+    packed = None
+    if _fastpack is not None and isinstance(map_points, list):
+        # the same loop in C; None when a container is not an exact dict / list (then the loop below runs)
+        packed = _fastpack.pack_observations(map_points, pose_index, kps_of)
+    if packed is not None:
+        cam_b, cid_b, uv_b, counts_b = packed
+        counts_a = np.frombuffer(counts_b, dtype=np.int64)
+        pt_offsets = np.zeros(n_pt + 1, dtype=np.int32)
+        if n_pt:
+            np.cumsum(counts_a, out=pt_offsets[1:])
+        return PackedWindow(
+            intr=intr, R=R, t=t, fixed=fixed, X=X,
+            obs_cam=np.frombuffer(cam_b, dtype=np.int32).copy(),
+            obs_pt=np.repeat(np.arange(n_pt, dtype=np.int32), counts_a) if n_pt else np.zeros(0, dtype=np.int32),
+            obs_uv=np.frombuffer(uv_b, dtype=np.float32).reshape(-1, 2).copy(),
+            obs_cam_id=np.frombuffer(cid_b, dtype=np.int32).copy(), pt_offsets=pt_offsets)
+
     # the reference's nested loop (:74-95), kept loop for loop; what can leave the interpreter does: the point
     # index of an observation comes from the per-point counts, the appends are bound once
     obs_cam: List[int] = []
@@ -71,7 +110,6 @@ def pack_window(keyframes: List[Any], map_points: List[Any]) -> PackedWindow:
     obs_uv: List[Any] = []
     counts: List[int] = []
     add_cam, add_cid, add_uv, add_count = obs_cam.append, obs_cid.append, obs_uv.append, counts.append
-    kps_of = [keyframes[i].keypoints for i in range(n_cam)]
     index_of = pose_index.get
     for mp in map_points:
         c0 = len(obs_cam)
