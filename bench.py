@@ -172,6 +172,46 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def plugin_leg(p, device_index, max_iter, reps=3):
+    """What a user of the reference sees after swapping the optimizer: `Map.optimize_local(B200Optimizer, window)`
+    on the window as an object graph (KeyFrame / MapPoint stand-ins of refgraph.py), i.e. window collection +
+    packing + the CUDA solve through the host API + write-back, in wall-clock milliseconds.  Informational: the
+    contract's `e2e` is the C-ABI call on host buffers."""
+    import tempfile
+    from visual_slam_core_b200 import B200Optimizer, handlers, packing, refgraph
+    cam, kfs, mps = refgraph.graph_from_problem(p)
+
+    class _Opt:
+        lm_max_iter = max_iter
+    class _Cfg:
+        optimization = _Opt()
+    opt = B200Optimizer(_Cfg(), log_dir=tempfile.mkdtemp(prefix="b200ba_bench_"), device=f"cuda:{device_index}")
+    m = refgraph.Map()
+    R0 = [np.array(kf.R_w2c, dtype=np.float64) for kf in kfs]
+    t0 = [np.array(kf.t_w2c, dtype=np.float64).reshape(3, 1) for kf in kfs]
+    X0 = [np.array(mp.position, dtype=np.float64) for mp in mps]
+    total, ok = [], True
+    for _ in range(reps + 1):                               # the first call creates the solver and captures the graph
+        for kf, R, t in zip(kfs, R0, t0):
+            kf.set_pose_Rt(R.copy(), t.copy())
+        for mp, x in zip(mps, X0):
+            mp.update_position(x.copy())
+        t_a = time.perf_counter()
+        ok = bool(m.optimize_local(opt, kfs)) and ok
+        total.append(1e3 * (time.perf_counter() - t_a))
+    t_a = time.perf_counter()
+    pts = handlers.collect_window_points(kfs)
+    t_b = time.perf_counter()
+    pw = packing.pack_window(kfs, pts)
+    t_c = time.perf_counter()
+    packing.write_back(kfs, pts, pw.R, pw.t, pw.X)
+    t_d = time.perf_counter()
+    return {"optimize_local_ms": min(total[1:]), "ok": ok, "collect_ms": 1e3 * (t_b - t_a),
+            "pack_window_ms": 1e3 * (t_c - t_b), "write_back_ms": 1e3 * (t_d - t_c),
+            "packer_loop": "C (csrc/fastpack.c)" if packing._fastpack is not None else "Python",
+            "api": "refgraph.Map.optimize_local -> B200Optimizer.optimize_local (object graph in, objects mutated)"}
+
+
 def reference_pnp(pts3d, pts2d, K):
     """The reference's pose estimate for one frame, call for call
     (`visual_slam/utils/motion_estimation.py:100-131`: cv2.solvePnPRansac, SOLVEPNP_ITERATIVE,
@@ -568,6 +608,11 @@ def run_b200(args, rank, local_rank, world):
         line["parity_vs_oracle"] = {"max_rel_cost_diff": rel,
                                     "accept_sequence_equal": bool(np.array_equal(res.accepted, ref.accepted)),
                                     "flags_equal": bool(np.array_equal(res.flags, ref.flags))}
+    if rank == 0 and world == 1 and not args.no_cpu and p.n_obs <= 400_000:
+        try:
+            line["plugin"] = plugin_leg(p, local_rank, max_iter)
+        except Exception as e:                              # informational leg: never costs the bench line
+            line["plugin"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
