@@ -130,6 +130,15 @@ def test_c_packer_loop_equals_the_python_loop(monkeypatch):
     assert pw.n_obs == 4 and pw.pt_offsets.tolist() == [0, 3, 4, 4]
     np.testing.assert_array_equal(pw.obs_uv[3], [30.0, 15.0])
 
+    class Broken(refgraph.MapPoint):                         # an exception inside the walk surfaces unchanged
+        def get_observations(self):
+            raise KeyError("lost")
+
+    for impl in (fp, None):
+        monkeypatch.setattr(packing, "_fastpack", impl)
+        with pytest.raises(KeyError):
+            packing.pack_window(kfs, mps + [Broken([0.0, 0.0, 1.0])])
+
     class Observed(dict):                                   # not an exact dict: the C loop declines
         pass
 
