@@ -149,7 +149,9 @@ def test_c_packer_loop_equals_the_python_loop(monkeypatch):
     assert both(kfs, []).n_obs == 0
 
 
-def test_fast_path_is_faster_on_a_real_window():
+def test_fast_path_is_faster_on_a_real_window(monkeypatch):
+    """The table beats the interpreter's walk of the object graph (best of three after one warm-up call each,
+    so that first-use imports are not what is timed)."""
     import time
     p = synth.make_problem("T2", seed=3)
     table = packing.ObservationTable()
@@ -159,10 +161,18 @@ def test_fast_path_is_faster_on_a_real_window():
     finally:
         table.uninstall()
     pts = window_points(kfs)
-    t0 = time.perf_counter(); a = packing.pack_window(kfs, pts); t1 = time.perf_counter()
-    b = table.pack(kfs, pts); t2 = time.perf_counter()
+    monkeypatch.setattr(packing, "_fastpack", None)          # the Python loop
+
+    def best(fn):
+        out, t_best = fn(), float("inf")
+        for _ in range(3):
+            t0 = time.perf_counter(); out = fn(); t_best = min(t_best, time.perf_counter() - t0)
+        return out, t_best
+
+    a, t_loop = best(lambda: packing.pack_window(kfs, pts))
+    b, t_table = best(lambda: table.pack(kfs, pts))
     _assert_same_window(b, a)
-    assert (t2 - t1) < (t1 - t0)
+    assert t_table < t_loop
 
 
 # ---------------------------------------------------------------------------------------- N2
