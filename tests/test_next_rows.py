@@ -92,10 +92,14 @@ def test_c_packer_loop_equals_the_python_loop(monkeypatch):
     the two skip rules, negative indices as Python indexes them); containers that are not exact dicts / lists
     send the call back to the Python loop."""
     from visual_slam_core_b200 import _build
+    path = _build.fastpack_path()
+    before = os.path.getmtime(path) if os.path.exists(path) else None
     try:
         _build.build_fastpack()
     except RuntimeError as e:                              # no compiler / no Python.h on this machine
         pytest.skip(str(e))
+    if packing._fastpack is not None and os.path.getmtime(path) != before:
+        pytest.skip("packer extension rebuilt from newer sources; this process still holds the old one - re-run")
     fp = packing._load_fastpack()
     assert fp is not None
 
@@ -129,6 +133,18 @@ def test_c_packer_loop_equals_the_python_loop(monkeypatch):
     pw = both(kfs, mps)
     assert pw.n_obs == 4 and pw.pt_offsets.tolist() == [0, 3, 4, 4]
     np.testing.assert_array_equal(pw.obs_uv[3], [30.0, 15.0])
+
+    # cv2's detectors return TUPLES of cv2.KeyPoint (feature/feature.py:33,47): same path, same result
+    cv2 = pytest.importorskip("cv2")
+    real = lambda n: tuple(cv2.KeyPoint(10.5 * i, 5.25 * i, 1.0) for i in range(n))
+    kfs_cv = [refgraph.KeyFrame(cam, [real(4), real(3)], np.eye(3), np.zeros(3)) for _ in range(3)]
+    mps_cv = [refgraph.MapPoint([0.1 * j, 0.0, 5.0]) for j in range(2)]
+    mps_cv[0].add_observation(kfs_cv[0].keyframe_id, 0, 1); mps_cv[0].add_observation(kfs_cv[2].keyframe_id, 1, -1)
+    mps_cv[1].add_observation(kfs_cv[1].keyframe_id, 1, 5); mps_cv[1].add_observation(kfs_cv[1].keyframe_id, 0, 3)
+    index = {kf.keyframe_id: i for i, kf in enumerate(kfs_cv)}
+    assert fp.pack_observations(mps_cv, index, [kf.keypoints for kf in kfs_cv]) is not None
+    pw_cv = both(kfs_cv, mps_cv)
+    np.testing.assert_array_equal(pw_cv.obs_uv, np.array([[10.5, 5.25], [21.0, 10.5], [31.5, 15.75]], np.float32))
 
     class Broken(refgraph.MapPoint):                         # an exception inside the walk surfaces unchanged
         def get_observations(self):

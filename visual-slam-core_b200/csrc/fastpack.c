@@ -10,8 +10,8 @@
  *               uv = kf.keypoints[cam_id][kp_idx].pt                                     (:94)
  *
  * The interpreter spends ~1.5 us per observation on this loop; the solve it feeds takes a millisecond.
- * Only exact dict / list containers take this path; anything else makes the function return None and the
- * caller runs the Python loop.  Host-side helper: no CUDA here, and nothing of the product depends on it being
+ * Only exact dict containers and exact list / tuple keypoint sequences take this path; anything else makes the
+ * function return None and the caller runs the Python loop.  Host-side helper: no CUDA here, and nothing of the product depends on it being
  * built (packing.py falls back to the Python loop).
  */
 #define PY_SSIZE_T_CLEAN
@@ -55,15 +55,19 @@ static void rows_free(Rows* r) {
   free(r->uv);
 }
 
-/* list[index] with Python's rules for negative indices; NULL + IndexError when out of range (borrowed ref) */
-static PyObject* list_item(PyObject* list, Py_ssize_t idx) {
-  const Py_ssize_t n = PyList_GET_SIZE(list);
+/* exact list (1) or exact tuple (2) -- cv2's detectors hand out tuples of KeyPoint -- anything else 0 */
+static int seq_kind(PyObject* o) { return PyList_CheckExact(o) ? 1 : (PyTuple_CheckExact(o) ? 2 : 0); }
+static Py_ssize_t seq_len(PyObject* o, int kind) { return kind == 1 ? PyList_GET_SIZE(o) : PyTuple_GET_SIZE(o); }
+
+/* seq[index] with Python's rules for negative indices; NULL + IndexError when out of range (borrowed ref) */
+static PyObject* seq_item(PyObject* o, int kind, Py_ssize_t idx) {
+  const Py_ssize_t n = seq_len(o, kind);
   if (idx < 0) idx += n;
   if (idx < 0 || idx >= n) {
-    PyErr_SetString(PyExc_IndexError, "list index out of range");
+    PyErr_SetString(PyExc_IndexError, kind == 1 ? "list index out of range" : "tuple index out of range");
     return NULL;
   }
-  return PyList_GET_ITEM(list, idx);
+  return kind == 1 ? PyList_GET_ITEM(o, idx) : PyTuple_GET_ITEM(o, idx);
 }
 
 /* pack_observations(map_points, pose_index, keypoints_of) -> (cam, cam_id, uv, counts) as bytes, or None */
@@ -102,21 +106,23 @@ static PyObject* pack_observations(PyObject* self, PyObject* args) {
       if (i == -1 && PyErr_Occurred()) goto fail;
       if (i < 0 || i >= PyList_GET_SIZE(kps_of)) { PyErr_SetString(PyExc_IndexError, "pose index out of range"); goto fail; }
       PyObject* kps = PyList_GET_ITEM(kps_of, i);
-      if (!PyDict_CheckExact(cams) || !PyList_CheckExact(kps)) { unsupported = 1; break; }
-      const Py_ssize_t n_sensors = PyList_GET_SIZE(kps);
+      const int kps_kind = seq_kind(kps);
+      if (!PyDict_CheckExact(cams) || !kps_kind) { unsupported = 1; break; }
+      const Py_ssize_t n_sensors = seq_len(kps, kps_kind);
       Py_ssize_t p2 = 0;
       PyObject *cam_id_o, *kp_idx_o;
       while (PyDict_Next(cams, &p2, &cam_id_o, &kp_idx_o)) {
         const Py_ssize_t cam_id = PyLong_AsSsize_t(cam_id_o);
         if (cam_id == -1 && PyErr_Occurred()) { PyErr_Clear(); unsupported = 1; break; }
         if (cam_id >= n_sensors) continue;
-        PyObject* kp_list = list_item(kps, cam_id);
+        PyObject* kp_list = seq_item(kps, kps_kind, cam_id);
         if (!kp_list) goto fail;
-        if (!PyList_CheckExact(kp_list)) { unsupported = 1; break; }
+        const int kp_kind = seq_kind(kp_list);
+        if (!kp_kind) { unsupported = 1; break; }
         const Py_ssize_t kp_idx = PyLong_AsSsize_t(kp_idx_o);
         if (kp_idx == -1 && PyErr_Occurred()) { PyErr_Clear(); unsupported = 1; break; }
-        if (kp_idx >= PyList_GET_SIZE(kp_list)) continue;
-        PyObject* kp = list_item(kp_list, kp_idx);
+        if (kp_idx >= seq_len(kp_list, kp_kind)) continue;
+        PyObject* kp = seq_item(kp_list, kp_kind, kp_idx);
         if (!kp) goto fail;
         PyObject* pt = PyObject_GetAttr(kp, s_pt);
         if (!pt) goto fail;
