@@ -1,29 +1,42 @@
 #!/usr/bin/env python
-"""Benchmark of the local-BA hot path (BASELINE.json metric: LM iterations/s, obs/s through
-residual + Jacobian + Schur, against the HBM roofline, with the CPU path timed beside it).
+"""Benchmark of the local-BA hot path (BASELINE.json metric: LM iterations/s and observations/s through
+residual + Jacobian + Schur at 1/2/4/8 B200, against the HBM roofline, with the CPU path timed beside it).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C4] [--impl b200|reference]
 
-A *step* is one complete local-BA solve of the workload window: `max_iter` (10) LM iterations,
-each = linearise + Schur -> reduced-camera solve -> back-substitution + candidate cost ->
-accept/reject, plus state init and outlier flags.  Every step starts from the same initial state.
+Default workload = BASELINE config 4, the one the metric is quoted on: ONE window of 1 000 cameras /
+1 M points / 8 M observations.  With N > 1 (torchrun, one rank per GPU) the SAME window is sharded by map
+point over the ranks (cameras replicated) and the reduced camera system + costs are NCCL all-reduced inside
+the CUDA library every LM iteration: strong scaling.  N = 1 runs the same window on one GPU.
 
-  value  = LM iterations/s with inputs resident in HBM (CUDA events around each step, L2 flushed
-           between steps, max over ranks; N > 1 = one independent window per GPU, weak scaling).
-  e2e    = the same through the public host-buffer API (`LocalBASolver.solve_local_inplace`,
-           i.e. the C-ABI `ba_solve_local_host`): pinned host inputs -> H2D -> solve -> D2H of
-           poses, points, flags and the LM report, all inside the timed region.
-  roofline = dominant kernel (by summed device time, measured live with CUDA events in a
-           profile pass of the same workload): algorithmic bytes / launch duration vs measured HBM peak.
-  cpu_baseline = oracle/lm_oracle.py (same LM, numpy float64) on this box's host cores.
+A *step* is one complete solve of the window: `max_iter` (10) LM iterations, each = linearise + Schur ->
+(all-reduce) -> reduced-camera solve -> back-substitution + candidate cost -> accept/reject, plus state
+init and outlier flags.  Every step starts from the same initial state.
 
-`--impl reference` times the reference's own CPU algorithm (Adam over a Python per-observation
-autograd loop, restated in oracle/ref_adam.py and validated against the unmodified reference in
-tests/test_ref_adam.py) on a bounded sample of the same window.
+  value    = LM iterations/s, inputs resident in HBM (CUDA events around each step on the launching
+             stream, L2 flushed between steps, max over ranks).
+  e2e      = the same through the host-buffer C ABI (`ba_solve_local_host`): pinned host inputs -> H2D ->
+             solve -> D2H of poses, points, flags and the LM report inside the timed region.
+  roofline = the linearise (residual + Jacobian + Schur) kernel: algorithmic bytes per launch / its live
+             CUDA-event duration, against the measured HBM peak; `roofline.fp64` the same in flops.
+  parity   = N > 1: the sharded solve against the single-GPU solve of the same window run in the same job
+             (cost history, accept sequence, poses, points, flags; poses identical across ranks);
+             N = 1: full-size properties against the oracle's objective / flag restatement.
+  cpu_baseline = oracle/lm_oracle.py (same LM, numpy float64) on a bounded sample of the window.
+  configs  = (N = 1 only) BASELINE configs 1-3 as sub-objects, each with value / e2e / roofline / parity.
+             For C1/C2 `e2e` is what a user of the reference calls, `Map.optimize_local(B200Optimizer, keyframes)`
+             on the window as an object graph (collection + packing + H2D + solve + D2H + write-back, wall
+             clock); the host-buffer C-ABI figure is kept as `e2e_abi`.
+
+`--impl reference` times the reference's own CPU implementation of the path: the UNMODIFIED
+`TorchOptimizer.optimize_local` through `Map.optimize_local` (oracle/ref_shim.py) when the reference tree is
+importable (baseline/_ref or /root/reference), else the restated loop oracle/ref_adam.py (labelled "port").
+One reference iteration is ONE ADAM STEP -- the reference has no LM.
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
 import statistics
@@ -39,6 +52,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "local_ba_lm_iterations_per_s"
 UNIT = "LM iter/s"
+FP64_PEAK_TFLOPS = 36.6          # scripts/fp64_peak.cu on this pool's B200 (vector DFMA); DMMA: 37.1 (scripts/dmma_peak.cu)
 
 
 # --------------------------------------------------------------------------------------------
@@ -54,9 +68,27 @@ def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
         with open(p) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured"
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
-        return 6650.0, "fallback"
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(cfg_name, key="linearize_schur"):
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(cfg_name, {}).get(key)
+    except Exception:
+        return None
+
+
+def load_synth():
+    """The generator alone, WITHOUT importing the product package (the reference arm must not map our .so)."""
+    spec = importlib.util.spec_from_file_location(
+        "_bench_synth", os.path.join(ROOT, "visual-slam-core_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["_bench_synth"] = mod
+    spec.loader.exec_module(mod)
+    return mod
 
 
 class _stdout_to_stderr:
@@ -129,87 +161,92 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# --------------------------------------------------------------------------------------------
+def workload_name(cfg, n_cam, n_pt, n_obs):
+    kind = "local BA window" if n_cam <= 40 else "BAL-scale synthetic BA"
+    return f"{cfg}: {kind}, {n_cam} keyframes, {n_pt} map points, {n_obs} observations, pinhole, Huber 5px, 5% outliers"
+
+
+# ============================================================================================
+# reference arm
+# ============================================================================================
+def _compact_cameras(sub):
+    """Keep only the cameras the sample observes (plus camera 0, the gauge), renumbered."""
+    cams = np.unique(np.concatenate([[0], sub.obs_cam]))
+    remap = -np.ones(sub.n_cam, dtype=np.int64)
+    remap[cams] = np.arange(len(cams))
+    return dict(intr=sub.intr, R=sub.R[cams], t=sub.t[cams], fixed=sub.fixed[cams], X=sub.X,
+                obs_cam=remap[sub.obs_cam].astype(np.int32), obs_pt=sub.obs_pt, obs_uv=sub.obs_uv)
+
+
 def run_reference(args, rank, world):
-    """The reference's CPU algorithm on a bounded sample of the workload window."""
+    """The reference's CPU implementation of the path on a bounded sample of the workload window."""
     if rank != 0:
         return
     import torch
-    import b200ba  # noqa: F401
-    from visual_slam_core_b200 import synth
-    from oracle import ref_adam
+    synth = load_synth()
+    from oracle import ref_shim
+    ref, ref_err = None, None
+    try:
+        ref = ref_shim.import_reference()
+    except Exception as e:                       # absent on this box: the restated loop takes over
+        ref_err = repr(e)
     p = synth.make_problem(args.config, seed=0)
-    total = args.steps + args.warmup
-    # probe the per-observation cost, then size the sample so the whole run ends in ~2.5 minutes
-    probe_n = 60
-    sub = p.shard_by_point(0, max(1, p.n_obs // probe_n))
-    ref_adam.adam_local_ba(sub.intr, sub.R, sub.t, sub.fixed, sub.X, sub.obs_cam, sub.obs_pt, sub.obs_uv, 1, 1e-4)
-    t0 = time.perf_counter()   # the first call pays torch's lazy initialisation: time the second
-    ref_adam.adam_local_ba(sub.intr, sub.R, sub.t, sub.fixed, sub.X, sub.obs_cam, sub.obs_pt, sub.obs_uv, 1, 1e-4)
-    per_obs = (time.perf_counter() - t0) / max(sub.n_obs, 1)
-    budget = 150.0
-    n_sample = int(min(p.n_obs, max(200, budget / max(total, 1) / max(per_obs, 1e-6))))
+    n_total = max(args.steps + args.warmup, 1)
+    # ~1 ms per observation and Adam iteration (SURVEY 6): size the sample for ~75 s of timed work
+    per_obs = 1.0e-3
+    n_sample = int(min(p.n_obs, max(400, 75.0 / n_total / per_obs)))
     sub = p.shard_by_point(0, max(1, round(p.n_obs / n_sample)))
-    out = ref_adam.adam_local_ba(sub.intr, sub.R, sub.t, sub.fixed, sub.X, sub.obs_cam, sub.obs_pt, sub.obs_uv,
-                                 n_iter=total, lr=1e-4, delta=5.0)
-    secs = out["secs"][args.warmup:]
-    t_step = sum(secs) / max(len(secs), 1)
-    # one reference iteration over the full window = t_step * n_obs / sample (linear in n_obs: SURVEY 6)
-    value = (sub.n_obs / p.n_obs) / t_step
+    w = _compact_cameras(sub)
+    n_s_obs, n_s_pt, n_s_cam = len(w["obs_cam"]), w["X"].shape[0], w["R"].shape[0]
+    host = f"torch {torch.__version__} CPU, torch threads {torch.get_num_threads()} (the loop is a single Python thread), host cpus {os.cpu_count()}"
+    sub_cfgs = {}
+    if ref is not None:
+        kind = "reference"
+        cam, kfs, mps = ref_shim.graph_from_arrays(ref, w["intr"], w["R"], w["t"], w["X"], w["obs_cam"], w["obs_pt"], w["obs_uv"])
+        ref_shim.run_local_ba(ref, kfs, n_iter=max(args.warmup, 1))             # warm-up (lazy torch init)
+        ok, secs, losses, info = ref_shim.run_local_ba(ref, kfs, n_iter=args.steps)
+        t_iter = secs / max(args.steps, 1)
+        how = (f"UNMODIFIED reference ({ref['path']}): Map.optimize_local -> TorchOptimizer.optimize_local(device=cpu), "
+               f"one call of n_iter={args.steps} after a warm-up call of n_iter={max(args.warmup, 1)}, ok={ok}")
+        if world == 1 and not args.no_sub:
+            # SURVEY 8d-D5: BASELINE config 1 timed IN FULL through the unmodified reference (10 Adam iterations)
+            p1 = synth.make_problem("C1", seed=0)
+            cam1, kfs1, mps1 = ref_shim.graph_from_arrays(ref, p1.intr, p1.R, p1.t, p1.X, p1.obs_cam, p1.obs_pt, p1.obs_uv)
+            ok1, secs1, losses1, _ = ref_shim.run_local_ba(ref, kfs1, n_iter=10)
+            sub_cfgs["C1"] = {
+                "workload": workload_name("C1", p1.n_cam, p1.n_pt, p1.n_obs), "value": 10.0 / secs1, "unit": "Adam iter/s",
+                "seconds_for_10_iterations": secs1, "ok": ok1, "logged_losses": losses1[:3],
+                "cpu_baseline": {"value": 10.0 / secs1, "unit": "Adam iter/s", "cores": 1, "kind": "reference",
+                                 "sample": f"the FULL window, 10 Adam iterations in one Map.optimize_local call; {host}"}}
+    else:
+        kind = "port"
+        from oracle import ref_adam
+        ref_adam.adam_local_ba(w["intr"], w["R"], w["t"], w["fixed"], w["X"], w["obs_cam"][:50], w["obs_pt"][:50],
+                               w["obs_uv"][:50], 1, 1e-4)
+        out = ref_adam.adam_local_ba(w["intr"], w["R"], w["t"], w["fixed"], w["X"], w["obs_cam"], w["obs_pt"], w["obs_uv"],
+                                     n_iter=n_total, lr=1e-4, delta=5.0)
+        secs_l = out["secs"][args.warmup:]
+        t_iter = sum(secs_l) / max(len(secs_l), 1)
+        how = (f"oracle/ref_adam.py, the reference's Adam loop restated (reference tree not importable here: {ref_err}); "
+               f"{len(secs_l)} timed iterations after {args.warmup} warm-up iterations")
+    # one reference iteration over the full window = t_iter * n_obs / sample (linear in n_obs: SURVEY 6)
+    value = (n_s_obs / p.n_obs) / t_iter
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.config, p), "iteration": "one Adam iteration (the reference has no LM)",
-                   "extrapolation": "value = (sample_obs / window_obs) / seconds_per_iteration; time is linear in observations"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": f"{sub.n_obs} of {p.n_obs} observations ({sub.n_pt} points), {len(secs)} timed Adam "
-                                   f"iterations, torch {torch.__version__} CPU, torch threads {torch.get_num_threads()} "
-                                   f"(the loop is a single Python thread), host cpus {os.cpu_count()}"},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_iter, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, p.n_cam, p.n_pt, p.n_obs),
+                   "iteration": "ONE ADAM STEP of the reference (it has no Levenberg-Marquardt; SURVEY fact 2) is set against one LM iteration",
+                   "step": f"one Adam iteration over a sample of {n_s_obs} observations ({n_s_pt} points, {n_s_cam} keyframes)",
+                   "extrapolation": "value = (sample_obs / window_obs) / seconds_per_iteration; time is linear in observations (SURVEY 6)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
+                         "sample": f"{n_s_obs} of {p.n_obs} observations; {how}; {host}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if sub_cfgs:
+        line["configs"] = sub_cfgs
     print(json.dumps(line), flush=True)
-
-
-def plugin_leg(p, device_index, max_iter, reps=3):
-    """What a user of the reference sees after swapping the optimizer: `Map.optimize_local(B200Optimizer, window)`
-    on the window as an object graph (KeyFrame / MapPoint stand-ins of refgraph.py), i.e. window collection +
-    packing + the CUDA solve through the host API + write-back, in wall-clock milliseconds.  Informational: the
-    contract's `e2e` is the C-ABI call on host buffers."""
-    import tempfile
-    from visual_slam_core_b200 import B200Optimizer, handlers, packing, refgraph
-    cam, kfs, mps = refgraph.graph_from_problem(p)
-
-    class _Opt:
-        lm_max_iter = max_iter
-    class _Cfg:
-        optimization = _Opt()
-    opt = B200Optimizer(_Cfg(), log_dir=tempfile.mkdtemp(prefix="b200ba_bench_"), device=f"cuda:{device_index}")
-    m = refgraph.Map()
-    R0 = [np.array(kf.R_w2c, dtype=np.float64) for kf in kfs]
-    t0 = [np.array(kf.t_w2c, dtype=np.float64).reshape(3, 1) for kf in kfs]
-    X0 = [np.array(mp.position, dtype=np.float64) for mp in mps]
-    total, ok = [], True
-    for _ in range(reps + 1):                               # the first call creates the solver and captures the graph
-        for kf, R, t in zip(kfs, R0, t0):
-            kf.set_pose_Rt(R.copy(), t.copy())
-        for mp, x in zip(mps, X0):
-            mp.update_position(x.copy())
-        t_a = time.perf_counter()
-        ok = bool(m.optimize_local(opt, kfs)) and ok
-        total.append(1e3 * (time.perf_counter() - t_a))
-    t_a = time.perf_counter()
-    pts = handlers.collect_window_points(kfs)
-    t_b = time.perf_counter()
-    pw = packing.pack_window(kfs, pts)
-    t_c = time.perf_counter()
-    packing.write_back(kfs, pts, pw.R, pw.t, pw.X)
-    t_d = time.perf_counter()
-    return {"optimize_local_ms": min(total[1:]), "ok": ok, "collect_ms": 1e3 * (t_b - t_a),
-            "pack_window_ms": 1e3 * (t_c - t_b), "write_back_ms": 1e3 * (t_d - t_c),
-            "packer_loop": "C (csrc/fastpack.c)" if packing._fastpack is not None else "Python",
-            "api": "refgraph.Map.optimize_local -> B200Optimizer.optimize_local (object graph in, objects mutated)"}
 
 
 def reference_pnp(pts3d, pts2d, K):
@@ -227,113 +264,314 @@ def reference_pnp(pts3d, pts2d, K):
     return R, tvec.reshape(3, 1), True, inl
 
 
-def run_pose_only(args, rank, local_rank, world):
-    """BASELINE config 3: batched pose-only BA, 256 frames x 1000 matches, one B200 (replicas for N > 1)."""
-    import b200ba  # noqa: F401
-    from visual_slam_core_b200 import LMConfig, synth
-    pp = synth.make_pose_only(n_frames=256, n_match=1000, seed=rank)
+# ============================================================================================
+# B200 arm: helpers
+# ============================================================================================
+class Ctx:
+    """Per-process device context."""
+
+    def __init__(self, rank, local_rank, world):
+        import torch
+        self.torch = torch
+        self.rank, self.local_rank, self.world = rank, local_rank, world
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the solver has no CPU fallback")
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        self.stream = torch.cuda.current_stream(self.dev)
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            self.dist = dist
+            with _stdout_to_stderr():          # NCCL prints its banner on stdout; the contract is ONE JSON line
+                dist.init_process_group("nccl", device_id=self.dev)
+                dist.barrier()
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, x: float) -> float:
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x: float) -> float:
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def T(self, a):
+        return self.torch.as_tensor(np.ascontiguousarray(a)).to(self.dev)
+
+    def pin(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a).copy()).pin_memory().numpy()
+
+
+class DeviceWindow:
+    """A packed window resident in HBM + the in-place state tensors of a solve."""
+
+    def __init__(self, ctx, p):
+        T = ctx.T
+        self.p = p
+        self.R0, self.t0, self.X0 = T(p.R), T(p.t), T(p.X)
+        self.R, self.t, self.X = self.R0.clone(), self.t0.clone(), self.X0.clone()
+        self.fixed, self.oc, self.op = T(p.fixed), T(p.obs_cam), T(p.obs_pt)
+        self.uv, self.off = T(p.obs_uv), T(p.pt_offsets)
+        self.flags = ctx.torch.zeros(p.n_obs, dtype=ctx.torch.uint8, device=ctx.dev)
+
+    def reset(self):
+        self.R.copy_(self.R0); self.t.copy_(self.t0); self.X.copy_(self.X0)
+
+    def solve(self, solver, stream, sync):
+        self.reset()
+        return solver.solve_local_device(self.p.intr, self.R, self.t, self.fixed, self.X, self.oc, self.op,
+                                         self.uv, self.off, self.flags, stream=stream.cuda_stream, sync=sync)
+
+
+def time_resident(ctx, win, solver, steps, warmup):
+    """K timed solves with CUDA events on the launching stream, L2 flushed between; returns
+    (ms summed over the K steps on this rank, last warm-up report, clocks)."""
+    torch = ctx.torch
+    rep = None
+    for _ in range(max(warmup, 3)):
+        rep = win.solve(solver, ctx.stream, sync=True)
+    sampler = ClockSampler(ctx.local_rank)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    ctx.barrier()
+    sampler.start()
+    for a, b in evs:
+        ctx.flush.zero_()
+        a.record(ctx.stream)
+        win.solve(solver, ctx.stream, sync=False)
+        b.record(ctx.stream)
+    ctx.barrier()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    return ms, rep, sampler.stop()
+
+
+def time_e2e_abi(ctx, p, solver, steps, warmup):
+    """The host-buffer C ABI with pinned host memory: H2D, solve, D2H inside the timed wall-clock region."""
+    pin = ctx.pin
+    hR, ht, hX = pin(p.R), pin(p.t), pin(p.X)
+    hfixed, hoc, hop, huv, hoff = pin(p.fixed), pin(p.obs_cam), pin(p.obs_pt), pin(p.obs_uv), pin(p.pt_offsets)
+    hflags = pin(np.zeros(p.n_obs, dtype=np.uint8))
+
+    def e2e_step():
+        np.copyto(hR, p.R); np.copyto(ht, p.t); np.copyto(hX, p.X)
+        return solver.solve_local_inplace(p.intr, hR, ht, hfixed, hX, hoc, hop, huv, hoff, hflags)
+
+    res = None
+    for _ in range(max(warmup, 3)):
+        res = e2e_step()
+    ctx.barrier()
+    t_a = time.perf_counter()
+    for _ in range(steps):
+        res = e2e_step()
+    ctx.torch.cuda.synchronize(ctx.dev)
+    secs = ctx.max_over_ranks(time.perf_counter() - t_a)
+    h2d = sum(a.nbytes for a in (hR, ht, hfixed, hX, hoc, huv, hoff))     # obs_pt is expanded from pt_offsets on the device
+    d2h = hR.nbytes + ht.nbytes + hX.nbytes + hflags.nbytes + 2240        # + LM control block (report)
+    return secs, res, int(h2d), int(d2h)
+
+
+def profile_kernels(ctx, win, solver_factory, lmcfg, max_iter, reps):
+    """CUDA events around every kernel (no graph), same workload: ms per LM iteration per kernel class."""
+    from visual_slam_core_b200 import LMConfig
+    prof = solver_factory(LMConfig(profile=True, **lmcfg))
+    acc = np.zeros(5)
+    r = None
+    for i in range(reps + 2):
+        r = win.solve(prof, ctx.stream, sync=True)
+        if i >= 2:
+            acc += np.array([r.ms_linearize, r.ms_solve, r.ms_backsub, r.ms_other, r.ms_comm])
+    acc /= reps
+    k_ms = {"linearize_schur": acc[0] / max_iter, "rcs_solve": acc[1] / max_iter,
+            "backsub_cost": acc[2] / max_iter, "init_finalize_per_step": acc[3],
+            "nccl_allreduce": acc[4] / max_iter}
+    return k_ms, r
+
+
+def roofline_block(cfg_name, p, k_ms, ms_per_iter, band_blocks=None):
+    dense = p.n_cam <= 38
+    b_rjs, b_iter = algorithmic_bytes(p.n_cam, p.n_pt, p.n_obs, dense=dense,
+                                      nnzb=band_blocks if band_blocks else 33 * p.n_cam)
+    peak, peak_src = hbm_peak()
+    lin_ms = k_ms["linearize_schur"]
+    lin_gbs = b_rjs / (lin_ms * 1e-3) / 1e9
+    k_obs = np.diff(p.pt_offsets).astype(np.float64)
+    flops = 300.0 * p.n_obs + 216.0 * float((k_obs * k_obs).sum())       # SURVEY 8d-D4 "algorithmic flops"
+    fp64_tf = flops / (lin_ms * 1e-3) / 1e12
+    dom = max(("linearize_schur", "rcs_solve", "backsub_cost"), key=lambda k: k_ms[k])
+    resident = b_iter < 100e6
+    return {"bound": "hbm", "kernel": "linearise (residual + Jacobian + Schur)", "achieved": lin_gbs, "peak": peak,
+            "unit": "GB/s", "frac": lin_gbs / peak, "traffic": ncu_traffic(cfg_name), "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": b_rjs, "launch_ms": lin_ms, "dominant_kernel_by_time": dom,
+            "whole_iteration": {"algorithmic_bytes": b_iter, "achieved": b_iter / (ms_per_iter * 1e-3) / 1e9,
+                                "frac": b_iter / (ms_per_iter * 1e-3) / 1e9 / peak},
+            "fp64": {"algorithmic_flop_per_launch": flops, "achieved_tflops": fp64_tf, "peak_tflops": FP64_PEAK_TFLOPS,
+                     "frac": fp64_tf / FP64_PEAK_TFLOPS,
+                     "note": "all arithmetic is float64 (vector DFMA + mma.m8n8k4.f64), required by the parity tolerances "
+                             "(scripts/f32_jacobian_experiment.py); peak measured with scripts/fp64_peak.cu"},
+            "note": ("window is L2-resident (working set << 126 MB L2): bound by FP64 latency, see DESIGN.md" if resident else
+                     "float64 arithmetic puts the kernel's floor at the FP64 pipe, not at HBM: see roofline.fp64 and DESIGN.md")}
+
+
+def plugin_leg(p, device_index, max_iter, reps=5):
+    """What a user of the reference calls after swapping the optimizer: `Map.optimize_local(B200Optimizer, window)`
+    on the window as an object graph (stand-in KeyFrame / MapPoint types with the reference's accessors):
+    window collection + packing + H2D + CUDA solve + D2H + write-back, wall clock."""
+    import tempfile
+    from visual_slam_core_b200 import B200Optimizer, handlers, packing
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refgraph
+    cam, kfs, mps = refgraph.graph_from_problem(p)
+
+    class _Opt:
+        lm_max_iter = max_iter
+    class _Cfg:
+        optimization = _Opt()
+    opt = B200Optimizer(_Cfg(), log_dir=tempfile.mkdtemp(prefix="b200ba_bench_"), device=f"cuda:{device_index}")
+    m = refgraph.Map()
+    R0 = [np.array(kf.R_w2c, dtype=np.float64) for kf in kfs]
+    t0 = [np.array(kf.t_w2c, dtype=np.float64).reshape(3, 1) for kf in kfs]
+    X0 = [np.array(mp.position, dtype=np.float64) for mp in mps]
+    total, ok = [], True
+    for _ in range(reps + 2):                               # the first calls create the solver and capture the graph
+        for kf, R, t in zip(kfs, R0, t0):
+            kf.set_pose_Rt(R.copy(), t.copy())
+        for mp, x in zip(mps, X0):
+            mp.update_position(x.copy())
+        t_a = time.perf_counter()
+        ok = bool(m.optimize_local(opt, kfs)) and ok
+        total.append(time.perf_counter() - t_a)
+    res = opt.last_result
+    t_a = time.perf_counter()
+    pts = handlers.collect_window_points(kfs)
+    t_b = time.perf_counter()
+    pw = opt.pack(kfs, pts) if hasattr(opt, "pack") else packing.pack_window(kfs, pts)
+    t_c = time.perf_counter()
+    packing.write_back(kfs, pts, pw.R, pw.t, pw.X)
+    t_d = time.perf_counter()
+    timed = total[2:]
+    return {"seconds_per_call": statistics.median(timed), "ok": ok, "result": res,
+            "breakdown_ms": {"collect": 1e3 * (t_b - t_a), "pack": 1e3 * (t_c - t_b), "write_back": 1e3 * (t_d - t_c)},
+            "packer": getattr(opt, "packer_name", "pack_window"),
+            "h2d": int(pw.R.nbytes + pw.t.nbytes + pw.fixed.nbytes + pw.X.nbytes + pw.obs_cam.nbytes + pw.obs_uv.nbytes + pw.pt_offsets.nbytes),
+            "d2h": int(pw.R.nbytes + pw.t.nbytes + pw.X.nbytes + pw.obs_cam.shape[0] + 2240)}
+
+
+def oracle_parity(res, ref, tol_cost=1e-5):
+    """Trajectory parity of a CUDA solve against the oracle on the same window (north_star tolerances)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import rot_angle, scale_norm_trans_err
+    rel = float(np.max(np.abs(res.cost_hist - ref.cost_hist) / ref.cost_hist))
+    rot = float(rot_angle(res.R, ref.R).max())
+    tr = float(scale_norm_trans_err(res.R, res.t, ref.R, ref.t).max())
+    acc = bool(np.array_equal(res.accepted, ref.accepted))
+    fl = int((res.flags != ref.flags).sum())
+    return {"max_rel_cost_diff": rel, "accept_sequence_equal": acc, "max_rot_err_rad": rot,
+            "max_scale_norm_trans_err": tr, "flag_mismatches": fl, "n_flags": int(ref.flags.shape[0]),
+            "ok": bool(rel <= tol_cost and rot <= 1e-5 and tr <= 1e-5 and fl == 0 and acc)}
+
+
+# ============================================================================================
+# sub-configs (N = 1): C1, C2 local windows and C3 pose-only
+# ============================================================================================
+def bench_window(ctx, cfg_name, args, with_cpu=True):
+    from visual_slam_core_b200 import LMConfig, LocalBASolver, synth
+    max_iter = args.lm_iters
+    steps, warmup = max(args.steps, 10), max(args.warmup, 3)
+    p = synth.make_problem(cfg_name, seed=0)
+    lmcfg = dict(max_iter=max_iter, schur=args.schur)
+    solver = LocalBASolver(LMConfig(**lmcfg), device=ctx.local_rank)
+    win = DeviceWindow(ctx, p)
+    ms, rep, clocks = time_resident(ctx, win, solver, steps, warmup)
+    value = steps * max_iter / (ms / 1e3)
+    secs, res, h2d, d2h = time_e2e_abi(ctx, p, solver, steps, warmup)
+    k_ms, _ = profile_kernels(ctx, win, lambda c: LocalBASolver(c, device=ctx.local_rank), lmcfg, max_iter, 5)
+    out = {"workload": workload_name(cfg_name, p.n_cam, p.n_pt, p.n_obs), "metric": METRIC, "unit": UNIT,
+           "value": value, "ms_per_step": ms / steps, "steps": steps, "warmup": warmup, "dtype": "f64",
+           "obs_per_s_residual_jacobian_schur": p.n_obs / (k_ms["linearize_schur"] * 1e-3),
+           "kernel_ms_per_lm_iteration": k_ms,
+           "roofline": roofline_block(cfg_name, p, k_ms, ms / steps / max_iter),
+           "e2e_abi": {"value": steps * max_iter / secs, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "api": "LocalBASolver.solve_local_inplace -> ba_solve_local_host (pinned host buffers)"},
+           "gpu_launches": int(rep.n_launches) * steps, "clocks": clocks}
+    try:
+        pl = plugin_leg(p, ctx.local_rank, max_iter)
+        out["e2e"] = {"value": max_iter / pl["seconds_per_call"], "unit": UNIT, "ms_per_call": 1e3 * pl["seconds_per_call"],
+                      "h2d_bytes_per_step": pl["h2d"], "d2h_bytes_per_step": pl["d2h"], "ok": pl["ok"],
+                      "breakdown_ms": pl["breakdown_ms"], "packer": pl["packer"],
+                      "api": "Map.optimize_local(B200Optimizer, keyframes): object graph in, objects mutated (collection + "
+                             "packing + H2D + solve + D2H + write-back, wall clock)"}
+    except Exception as e:                                  # never costs the bench line
+        out["e2e"] = {"error": repr(e)}
+    if with_cpu:
+        from oracle import lm_oracle as O
+        t_c = time.perf_counter()
+        ref = O.solve_local(p.intr, p.R, p.t, p.fixed, p.X, p.obs_cam, p.obs_pt, p.obs_uv, O.LMParams(max_iter=max_iter))
+        dt = time.perf_counter() - t_c
+        out["cpu_baseline"] = {"value": max_iter / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": f"the full window, one solve of {max_iter} LM iterations with oracle/lm_oracle.py "
+                                         f"(numpy float64, same algorithm) in {dt:.1f} s"}
+        out["parity"] = dict(oracle_parity(res, ref), vs="oracle/lm_oracle.py, full trajectory on the full window")
+    solver.close()
+    return out
+
+
+def bench_pose_only(ctx, args, impl_reference=False):
+    """BASELINE config 3: batched pose-only BA, 256 frames x 1000 matches, one B200."""
+    import ctypes as C
+    from visual_slam_core_b200 import LMConfig, LocalBASolver, _lib, synth
+    torch = ctx.torch
+    pp = synth.make_pose_only(n_frames=256, n_match=1000, seed=0)
     nF, nM = pp.n_frames, pp.n_match
     K = np.array([[pp.intr[0], 0, pp.intr[2]], [0, pp.intr[1], pp.intr[3]], [0, 0, 1.0]])
     max_iter = args.lm_iters
-    metric, unit = "pose_only_lm_iterations_per_s", "frame LM iter/s"
-    workload = f"C3: batched pose-only BA, {nF} frames x {nM // nF} 2D-3D matches, pinhole, Huber 5px, 10% outliers"
-
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        import cv2
-        cv2.setRNGSeed(42)
-        total = args.steps + args.warmup
-        n_sample = int(min(nF, max(8, 4000 // max(total, 1))))       # ~4 ms per frame: a few seconds per step
-        secs = []
-        for it in range(total):
-            t0 = time.perf_counter()
-            for f in range(n_sample):
-                a, b = pp.frame_offsets[f], pp.frame_offsets[f + 1]
-                reference_pnp(pp.X[a:b], pp.uv[a:b], K)
-            secs.append(time.perf_counter() - t0)
-        t_step = sum(secs[args.warmup:]) / max(len(secs) - args.warmup, 1)
-        fps = n_sample / t_step
-        value = fps * max_iter          # one reference pose estimate is set against one 10-iteration LM refinement
-        line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload, "equivalence": f"value = frames/s x {max_iter}: one cv2.solvePnPRansac call "
-                           f"replaces one {max_iter}-iteration pose-only LM"},
-                "frames_per_s": fps,
-                "cpu_baseline": {"value": value, "unit": unit, "cores": int(cv2.getNumThreads()), "kind": "reference",
-                                 "sample": f"{n_sample} of {nF} frames per step, cv2 {cv2.__version__} solvePnPRansac exactly as "
-                                           f"motion_estimation.py:107-116 calls it, host cpus {os.cpu_count()}"},
-                "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
-        return
-
-    import ctypes as C
-    import torch
-    import torch.distributed as dist
-    from visual_slam_core_b200 import LocalBASolver, _lib
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the solver has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        with _stdout_to_stderr():
-            dist.init_process_group("nccl", device_id=dev)
-            dist.barrier()
-    solver = LocalBASolver(LMConfig(max_iter=max_iter), device=local_rank)
+    steps, warmup = max(args.steps, 10), max(args.warmup, 3)
+    unit = "frame LM iter/s"
+    solver = LocalBASolver(LMConfig(max_iter=max_iter), device=ctx.local_rank)
     lib = solver.lib
-    T = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(dev)
+    T = ctx.T
     R0, t0 = T(pp.R), T(pp.t)
     R, t = R0.clone(), t0.clone()
     X, uv, fo = T(pp.X), T(pp.uv), T(pp.frame_offsets)
-    flags = torch.zeros(nM, dtype=torch.uint8, device=dev)
-    hist = torch.zeros((nF, max_iter + 1), dtype=torch.float64, device=dev)
+    flags = torch.zeros(nM, dtype=torch.uint8, device=ctx.dev)
+    hist = torch.zeros((nF, max_iter + 1), dtype=torch.float64, device=ctx.dev)
     intr = np.ascontiguousarray(pp.intr, dtype=np.float64)
-    stream = torch.cuda.current_stream(dev)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    stream = ctx.stream
 
-    def step():
-        R.copy_(R0); t.copy_(t0)
+    def launch():
         rc = lib.ba_solve_pose_only(solver._h, nF, nM, intr.ctypes.data_as(C.POINTER(C.c_double)), R.data_ptr(),
                                     t.data_ptr(), X.data_ptr(), uv.data_ptr(), fo.data_ptr(), flags.data_ptr(),
                                     hist.data_ptr(), None, C.c_void_p(stream.cuda_stream))
         _lib.check(lib, solver._h, rc, "ba_solve_pose_only")
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    sampler = ClockSampler(local_rank)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    sampler.start()
+    for _ in range(warmup):
+        R.copy_(R0); t.copy_(t0)
+        launch()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    ctx.barrier()
     for (a, b), (ka, kb) in zip(evs, kev):
-        flush.zero_()
+        ctx.flush.zero_()
         a.record(stream)
         R.copy_(R0); t.copy_(t0)
         ka.record(stream)
-        lib.ba_solve_pose_only(solver._h, nF, nM, intr.ctypes.data_as(C.POINTER(C.c_double)), R.data_ptr(),
-                               t.data_ptr(), X.data_ptr(), uv.data_ptr(), fo.data_ptr(), flags.data_ptr(),
-                               hist.data_ptr(), None, C.c_void_p(stream.cuda_stream))
+        launch()
         kb.record(stream)
         b.record(stream)
-    barrier()
+    ctx.barrier()
     ms = sum(a.elapsed_time(b) for a, b in evs)
-    k_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
-    clocks = sampler.stop()
-    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_max = float(tms.item())
-    value = world * args.steps * nF * max_iter / (ms_max / 1e3)
+    k_ms = sum(a.elapsed_time(b) for a, b in kev) / steps
+    value = steps * nF * max_iter / (ms / 1e3)
 
-    # end to end: host buffers through ba_solve_pose_only_host (H2D / D2H inside)
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a).copy()).pin_memory().numpy()
+    pin = ctx.pin
     hR, ht, hX, huv, hfo = pin(pp.R), pin(pp.t), pin(pp.X), pin(pp.uv), pin(pp.frame_offsets)
     hflags = pin(np.zeros(nM, dtype=np.uint8))
     hhist = pin(np.zeros((nF, max_iter + 1), dtype=np.float64))
@@ -344,49 +582,48 @@ def run_pose_only(args, rank, local_rank, world):
         return solver.solve_pose_only(pp.intr, hR, ht, hX, huv, hfo, inplace=True, flags=hflags,
                                       cost_hist=hhist, accepted=hacc)
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         out = e2e_step()
-    barrier()
     t_a = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         out = e2e_step()
-    torch.cuda.synchronize(dev)
-    te = torch.tensor([time.perf_counter() - t_a], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.steps * nF * max_iter / float(te.item())
+    torch.cuda.synchronize(ctx.dev)
+    e2e_value = steps * nF * max_iter / (time.perf_counter() - t_a)
     h2d = pp.R.nbytes + pp.t.nbytes + pp.X.nbytes + pp.uv.nbytes + pp.frame_offsets.nbytes
     d2h = pp.R.nbytes + pp.t.nbytes + nM + nF * (max_iter + 1) * 8 + nF * max_iter
-
     b_po = 21 * nM + 96 * nF                                   # SURVEY 8d-D4, one pass over the matches
     peak, peak_src = hbm_peak()
     gbs = b_po / (k_ms * 1e-3) / 1e9
-    line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "lm_iterations_per_step": max_iter,
-                       "parallelism": "single GPU" if world == 1 else f"{world} independent batches, one per GPU (replicas)",
-                       "l2": "flushed between steps (256 MiB write); inside a step the batch stays L2-resident"},
-            "frames_per_s": value / max_iter,
-            "kernel_ms_per_step": {"pose_only_lm": k_ms},
-            "roofline": {"bound": "hbm", "kernel": "k_pose_only (whole LM loop, one CTA per frame)", "achieved": gbs,
-                         "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": b_po, "launch_ms": k_ms,
-                         "note": f"the matches are read once from HBM and then {2 * max_iter} times from L2 / L1 (linearise + candidate "
-                                 f"cost per LM iteration): the kernel is bound by FP64 latency, not by HBM"},
-            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": "LocalBASolver.solve_pose_only(inplace, pinned host buffers) -> ba_solve_pose_only_host"},
-            "gpu_launches": args.steps, "clocks": clocks}
-    if rank == 0 and world == 1 and not args.no_cpu:
+    res = {"workload": f"C3: batched pose-only BA, {nF} frames x {nM // nF} 2D-3D matches, pinhole, Huber 5px, 10% outliers",
+           "metric": "pose_only_lm_iterations_per_s", "unit": unit, "value": value, "frames_per_s": value / max_iter,
+           "ms_per_step": ms / steps, "steps": steps, "warmup": warmup, "dtype": "f64",
+           "kernel_ms_per_step": {"pose_only_lm": k_ms},
+           "roofline": {"bound": "hbm", "kernel": "k_pose_only (whole LM loop of every frame in one launch)", "achieved": gbs,
+                        "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": ncu_traffic("C3", "pose_only"),
+                        "peak_source": peak_src, "algorithmic_bytes_per_launch": b_po, "launch_ms": k_ms,
+                        "note": f"the matches are read once from HBM and then {2 * max_iter} times from L2 / L1 (linearise + candidate "
+                                f"cost per LM iteration): the kernel is bound by FP64 latency, not by HBM"},
+           "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "api": "LocalBASolver.solve_pose_only(inplace, pinned host buffers) -> ba_solve_pose_only_host"},
+           "gpu_launches": steps}
+    if not args.no_cpu:
         from oracle import lm_oracle as O
-        n_s = 16
-        a = int(pp.frame_offsets[n_s])
         t_c = time.perf_counter()
-        ref = O.solve_pose_only(pp.intr, pp.R[:n_s], pp.t[:n_s], pp.X[:a], pp.uv[:a], pp.frame_offsets[:n_s + 1],
-                                O.LMParams(max_iter=max_iter))
+        ref = O.solve_pose_only(pp.intr, pp.R, pp.t, pp.X, pp.uv, pp.frame_offsets, O.LMParams(max_iter=max_iter))
         dt = time.perf_counter() - t_c
-        line["oracle_cpu"] = {"value": n_s * max_iter / dt, "unit": unit, "cores": 1,
-                              "sample": f"{n_s} of {nF} frames, oracle/lm_oracle.py solve_pose_only (numpy float64) in {dt:.1f} s"}
+        res["oracle_cpu"] = {"value": nF * max_iter / dt, "unit": unit, "cores": 1,
+                             "sample": f"all {nF} frames, oracle/lm_oracle.py solve_pose_only (numpy float64) in {dt:.1f} s"}
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from helpers import rot_angle
+        res["parity"] = {
+            "vs": "oracle/lm_oracle.py solve_pose_only, all frames",
+            "max_rel_cost_diff": float(np.max(np.abs(out["cost_hist"] - ref["cost_hist"]) / ref["cost_hist"])),
+            "accept_sequence_equal": bool(np.array_equal(out["accepted"], ref["accepted"])),
+            "max_rot_err_rad": float(rot_angle(out["R"].reshape(-1, 3, 3), ref["R"]).max()),
+            "max_trans_err": float(np.abs(out["t"].reshape(-1, 3) - ref["t"]).max()),
+            "flag_mismatches": int((out["flags"] != ref["flags"]).sum()), "n_flags": int(nM)}
+        res["parity"]["ok"] = bool(res["parity"]["max_rel_cost_diff"] <= 1e-5 and res["parity"]["flag_mismatches"] == 0
+                                   and res["parity"]["max_rot_err_rad"] <= 1e-5 and res["parity"]["max_trans_err"] <= 1e-5)
         try:
             import cv2
             cv2.setRNGSeed(42)
@@ -396,227 +633,241 @@ def run_pose_only(args, rank, local_rank, world):
                 fa, fb = pp.frame_offsets[f], pp.frame_offsets[f + 1]
                 reference_pnp(pp.X[fa:fb], pp.uv[fa:fb], K)
             dt_r = time.perf_counter() - t_c
-            line["cpu_baseline"] = {"value": n_r / dt_r * max_iter, "unit": unit, "cores": int(cv2.getNumThreads()),
-                                    "kind": "reference",
-                                    "sample": f"{n_r} of {nF} frames, cv2 {cv2.__version__} solvePnPRansac as called at "
-                                              f"motion_estimation.py:107-116 ({1e3 * dt_r / n_r:.2f} ms per frame); value = frames/s x {max_iter}"}
-        except Exception as e:  # OpenCV missing on the box: fall back to the oracle port
-            line["cpu_baseline"] = dict(line["oracle_cpu"], kind="port", note=f"cv2 unavailable: {e!r}")
-        line["parity_vs_oracle"] = {
-            "max_rel_cost_diff": float(np.max(np.abs(out["cost_hist"][:n_s] - ref["cost_hist"]) / ref["cost_hist"])),
-            "flags_equal": bool(np.array_equal(out["flags"][:a], ref["flags"]))}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+            res["cpu_baseline"] = {"value": n_r / dt_r * max_iter, "unit": unit, "cores": int(cv2.getNumThreads()),
+                                   "kind": "reference",
+                                   "sample": f"{n_r} of {nF} frames, cv2 {cv2.__version__} solvePnPRansac as called at "
+                                             f"motion_estimation.py:107-116 ({1e3 * dt_r / n_r:.2f} ms per frame); value = frames/s x {max_iter}"}
+        except Exception as e:  # OpenCV missing on the box: the oracle port is the baseline
+            res["cpu_baseline"] = dict(res["oracle_cpu"], kind="port", note=f"cv2 unavailable: {e!r}")
+    solver.close()
+    return res
 
 
-def workload_name(cfg, p):
-    return f"{cfg}: local BA window, {p.n_cam} keyframes, {p.n_pt} map points, {p.n_obs} observations, pinhole, Huber 5px"
-
-
-# --------------------------------------------------------------------------------------------
+# ============================================================================================
+# B200 arm: the headline window, sharded by point over the ranks
+# ============================================================================================
 def run_b200(args, rank, local_rank, world):
-    import torch
-    import torch.distributed as dist
+    ctx = Ctx(rank, local_rank, world)
+    torch = ctx.torch
     import b200ba  # noqa: F401
     from visual_slam_core_b200 import LMConfig, LocalBASolver, synth
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the solver has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        with _stdout_to_stderr():          # NCCL prints its version banner on stdout; the contract is ONE JSON line
-            dist.init_process_group("nccl", device_id=dev)
-            dist.barrier()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    from visual_slam_core_b200 import dist as badist
 
     max_iter = args.lm_iters
-    sharded = args.shard or args.config in ("C4", "C5")
-    if sharded:
-        # BASELINE configs 4/5: ONE problem, points sharded over the ranks, cameras replicated; the
-        # reduced camera system and the costs are NCCL all-reduced inside the CUDA library
-        from visual_slam_core_b200 import dist as badist
-        full = synth.make_problem(args.config, seed=0)
-        p = full.shard_by_point(rank, world) if world > 1 else full
-        n_obs_total, n_pt_total = full.n_obs, full.n_pt
-        del full
-    else:
-        p = synth.make_problem(args.config, seed=rank)      # one independent window per GPU
-        n_obs_total, n_pt_total = p.n_obs, p.n_pt
-    T = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(dev)
-    R0, t0, X0 = T(p.R), T(p.t), T(p.X)
-    R, t, X = R0.clone(), t0.clone(), X0.clone()
-    fixed, oc, op, uv, off = T(p.fixed), T(p.obs_cam), T(p.obs_pt), T(p.obs_uv), T(p.pt_offsets)
-    flags = torch.zeros(p.n_obs, dtype=torch.uint8, device=dev)
+    steps, warmup = args.steps, max(args.warmup, 3)
+    full = synth.make_problem(args.config, seed=0)
+    p = full.shard_by_point(rank, world) if world > 1 else full
     lmcfg = dict(max_iter=max_iter, schur=args.schur, pcg_tol=args.pcg_tol, pcg_max_iter=args.pcg_max_iter)
     solver = LocalBASolver(LMConfig(**lmcfg), device=local_rank)
-    if sharded and world > 1:
+    if world > 1:
         with _stdout_to_stderr():
-            badist.init_solver(solver, rank, world, device=dev)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    if sharded:
-        args.steps = min(args.steps, 3)
-    stream = torch.cuda.current_stream(dev)
+            badist.init_solver(solver, rank, world, device=ctx.dev)
+    win = DeviceWindow(ctx, p)
 
-    def step(sync=False):
-        R.copy_(R0); t.copy_(t0); X.copy_(X0)
-        return solver.solve_local_device(p.intr, R, t, fixed, X, oc, op, uv, off, flags,
-                                         stream=stream.cuda_stream, sync=sync)
-
-    rep = None
-    for _ in range(max(args.warmup, 3)):
-        rep = step(sync=True)
+    # ---- resident
+    ms, rep, clocks = time_resident(ctx, win, solver, steps, warmup)
+    ms_max = ctx.max_over_ranks(ms)
+    value = steps * max_iter / (ms_max / 1e3)
     launches_per_step = int(rep.n_launches)
+    # the state the timed solves end in (every step starts from the same state, so any of them will do)
+    rep = win.solve(solver, ctx.stream, sync=True)
+    R_sh, t_sh = win.R.cpu().numpy().copy(), win.t.cpu().numpy().copy()
+    X_sh, flags_sh = win.X.cpu().numpy().copy(), win.flags.cpu().numpy().copy()
+    hist_sh = np.array(rep.cost_hist[: max_iter + 1])
+    acc_sh = np.array(rep.accepted[:max_iter], dtype=np.uint8)
 
-    sampler = ClockSampler(local_rank)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    sampler.start()
-    for a, b in evs:
-        flush.zero_()
-        a.record(stream)
-        step(sync=False)
-        b.record(stream)
-    barrier()
-    ms = sum(a.elapsed_time(b) for a, b in evs)
-    clocks = sampler.stop()
-    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    # ---- end to end through the host-buffer C ABI
+    secs, res, h2d, d2h = time_e2e_abi(ctx, p, solver, steps, warmup)
+    e2e_value = steps * max_iter / secs
+    h2d_all, d2h_all = int(ctx.sum_over_ranks(h2d)), int(ctx.sum_over_ranks(d2h))
+
+    # ---- per-kernel device times
     if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_max = float(tms.item())
-    n_windows = 1 if sharded else world
-    value = n_windows * args.steps * max_iter / (ms_max / 1e3)
-
-    # ---- end to end through the host-buffer API (pinned host memory, copies inside the timed region)
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a).copy()).pin_memory().numpy()
-    hR, ht, hX = pin(p.R), pin(p.t), pin(p.X)
-    hfixed, hoc, hop, huv, hoff = pin(p.fixed), pin(p.obs_cam), pin(p.obs_pt), pin(p.obs_uv), pin(p.pt_offsets)
-    hflags = pin(np.zeros(p.n_obs, dtype=np.uint8))
-    if sharded and world > 1:
-        e2e_solver = solver                                  # one communicator per process is enough
+        def factory(cfg):
+            solver.set_config(cfg)
+            return solver
     else:
-        e2e_solver = LocalBASolver(LMConfig(**lmcfg), device=local_rank)
-
-    def e2e_step():
-        np.copyto(hR, p.R); np.copyto(ht, p.t); np.copyto(hX, p.X)
-        return e2e_solver.solve_local_inplace(p.intr, hR, ht, hfixed, hX, hoc, hop, huv, hoff, hflags)
-
-    for _ in range(max(args.warmup, 3)):
-        res = e2e_step()
-    barrier()
-    t_a = time.perf_counter()
-    for _ in range(args.steps):
-        res = e2e_step()
-    torch.cuda.synchronize(dev)
-    t_b = time.perf_counter()
-    te = torch.tensor([t_b - t_a], dtype=torch.float64, device=dev)
+        factory = lambda cfg: LocalBASolver(cfg, device=local_rank)   # noqa: E731
+    k_ms, r_prof = profile_kernels(ctx, win, factory, lmcfg, max_iter, 3)
+    k_ms = {k: ctx.max_over_ranks(v) for k, v in k_ms.items()}
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = n_windows * args.steps * max_iter / float(te.item())
-    import ctypes as C
-    from visual_slam_core_b200 import _lib
-    h2d = sum(a.nbytes for a in (hR, ht, hfixed, hX, hoc, huv, hoff))   # obs_pt is expanded from pt_offsets on the device
-    d2h = hR.nbytes + ht.nbytes + hX.nbytes + hflags.nbytes + 2240   # + LM control block (report)
-    final_cost = float(res.cost_hist[-1])
+        solver.set_config(LMConfig(**lmcfg))
+    band_blocks = int(r_prof.s_blocks) if int(r_prof.band_width) >= 0 else None
 
-    # ---- profile pass: CUDA events around every kernel (no graph), same workload
-    if sharded and world > 1:
-        prof = solver
-        prof.set_config(LMConfig(profile=True, **lmcfg))
-    else:
-        prof = LocalBASolver(LMConfig(profile=True, **lmcfg), device=local_rank)
-    acc = np.zeros(5)
-    n_prof = 5 if not sharded else 2
-    for i in range(n_prof + 2):
-        R.copy_(R0); t.copy_(t0); X.copy_(X0)
-        r = prof.solve_local_device(p.intr, R, t, fixed, X, oc, op, uv, off, flags, stream=stream.cuda_stream, sync=True)
-        if i >= 2:
-            acc += np.array([r.ms_linearize, r.ms_solve, r.ms_backsub, r.ms_other, r.ms_comm])
-    acc /= n_prof
-    pcg_iters = [int(v) for v in r.pcg_iters[:max_iter]]
-    k_ms = {"linearize_schur": acc[0] / max_iter, "rcs_solve": acc[1] / max_iter,
-            "backsub_cost": acc[2] / max_iter, "init_finalize_per_step": acc[3],
-            "nccl_allreduce": acc[4] / max_iter}
-    b_rjs, b_iter = algorithmic_bytes(p.n_cam, p.n_pt, p.n_obs, dense=p.n_cam <= 38, nnzb=33 * p.n_cam)
-    peak, peak_src = hbm_peak()
-    dom = max(("linearize_schur", "rcs_solve", "backsub_cost"), key=lambda k: k_ms[k])
-    lin_gbs = b_rjs / (k_ms["linearize_schur"] * 1e-3) / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get(args.config, {}).get("linearize_schur")
-    except Exception:
-        pass
-    k_obs = np.diff(p.pt_offsets).astype(np.float64)
-    flops = 300.0 * p.n_obs + 216.0 * float((k_obs * k_obs).sum())       # SURVEY 8d-D4 "algorithmic flops"
-    fp64_peak = 36.6                                                     # TFLOP/s, scripts/fp64_peak.cu on this pool's B200
-    fp64_tf = flops / (k_ms["linearize_schur"] * 1e-3) / 1e12
-    resident = b_iter < 100e6
-    roofline = {"bound": "hbm", "kernel": "k_linearize (residual+Jacobian+Schur)", "achieved": lin_gbs, "peak": peak,
-                "unit": "GB/s", "frac": lin_gbs / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": b_rjs, "launch_ms": k_ms["linearize_schur"],
-                "dominant_kernel_by_time": dom,
-                "whole_iteration": {"algorithmic_bytes": b_iter,
-                                    "achieved": b_iter / (ms_max / 1e3 / (args.steps * max_iter)) / 1e9,
-                                    "frac": b_iter / (ms_max / 1e3 / (args.steps * max_iter)) / 1e9 / peak},
-                "fp64": {"algorithmic_flop_per_launch": flops, "achieved_tflops": fp64_tf, "peak_tflops": fp64_peak,
-                         "frac": fp64_tf / fp64_peak,
-                         "note": "all arithmetic is float64 (vector FMA + mma.m8n8k4.f64); measured peak of scripts/fp64_peak.cu"},
-                "note": ("window is L2-resident (working set << 126 MB L2): FP64-latency bound, see DESIGN.md" if resident else
-                         "float64 arithmetic puts the kernel's floor at the FP64 pipe, not at HBM: see roofline.fp64 and DESIGN.md")}
+    # ---- parity
+    parity = {}
+    if world > 1:
+        # the single-GPU solve of the SAME window, in this job, on every rank's own GPU
+        one = LocalBASolver(LMConfig(**lmcfg), device=local_rank)
+        wfull = DeviceWindow(ctx, full)
+        rep1 = wfull.solve(one, ctx.stream, sync=True)
+        hist1 = np.array(rep1.cost_hist[: max_iter + 1])
+        acc1 = np.array(rep1.accepted[:max_iter], dtype=np.uint8)
+        lo, hi = p.meta["pt_range"]
+        o0, o1 = int(full.pt_offsets[lo]), int(full.pt_offsets[hi])
+        R1, t1 = wfull.R.cpu().numpy(), wfull.t.cpu().numpy()
+        X1, f1 = wfull.X[lo:hi].cpu().numpy(), wfull.flags[o0:o1].cpu().numpy()
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from helpers import rot_angle, scale_norm_trans_err
+        # replicated state must be IDENTICAL across ranks: compare every rank's poses with rank 0's, bit for bit
+        Rt = torch.as_tensor(np.concatenate([R_sh.reshape(-1), t_sh.reshape(-1)])).to(ctx.dev)
+        Rt0 = Rt.clone()
+        ctx.dist.broadcast(Rt0, src=0)
+        pose_spread = ctx.max_over_ranks(float((Rt != Rt0).sum().item()))
+        hist_spread = ctx.max_over_ranks(float(np.abs(hist_sh - hist1).max())) - ctx.max_over_ranks(-float(np.abs(hist_sh - hist1).max()))
+        parity = {
+            "vs": f"the single-GPU solve of the same window, run in this job on every rank's own GPU (N = 1 path of the same library)",
+            "max_rel_cost_diff": ctx.max_over_ranks(float(np.max(np.abs(hist_sh - hist1) / hist1))),
+            "accept_sequence_equal": ctx.max_over_ranks(0.0 if np.array_equal(acc_sh, acc1) else 1.0) == 0.0,
+            "max_rot_err_rad": ctx.max_over_ranks(float(rot_angle(R_sh, R1).max())),
+            "max_scale_norm_trans_err": ctx.max_over_ranks(float(scale_norm_trans_err(R_sh, t_sh, R1, t1).max())),
+            "max_point_diff": ctx.max_over_ranks(float(np.abs(X_sh - X1).max()) if X1.size else 0.0),
+            "flag_mismatches": int(ctx.sum_over_ranks(float((flags_sh != f1).sum()))),
+            "n_flags": int(full.n_obs),
+            "pose_entries_differing_across_ranks": int(pose_spread),
+            "cost_history_identical_across_ranks": bool(hist_spread == 0.0),
+        }
+        parity["ok"] = bool(parity["max_rel_cost_diff"] <= 1e-6 and parity["accept_sequence_equal"]
+                            and parity["max_rot_err_rad"] <= 1e-5 and parity["max_scale_norm_trans_err"] <= 1e-5
+                            and parity["pose_entries_differing_across_ranks"] == 0)
+        one.close()
+        del wfull
+    elif not args.no_cpu:
+        # full size, size-independent properties against the oracle's restatement of the reference objective
+        from oracle import lm_oracle as O
+        c0 = O.reference_cost(full.intr, full.R, full.t, full.X, full.obs_cam, full.obs_pt, full.obs_uv)
+        c1 = O.reference_cost(full.intr, R_sh, t_sh, X_sh, full.obs_cam, full.obs_pt, full.obs_uv)
+        fl = O.outlier_flags(full.intr, R_sh, t_sh, X_sh, full.obs_cam, full.obs_pt, full.obs_uv)
+        parity = {
+            "vs": "oracle/lm_oracle.py objective and flag rule evaluated at the CUDA solver's initial / final state, full window "
+                  "(trajectory parity at this camera count is asserted against the sparse oracle in tests/test_gpu_large.py)",
+            "initial_cost_rel_diff": float(abs(hist_sh[0] - c0) / c0),
+            "final_cost_rel_diff": float(abs(hist_sh[-1] - c1) / c1),
+            "flag_mismatches": int((fl != flags_sh).sum()), "n_flags": int(full.n_obs),
+            "cost_monotone": bool(np.all(np.diff(hist_sh) <= 0)),
+            "accepted": acc_sh.tolist(),
+        }
+        parity["ok"] = bool(parity["initial_cost_rel_diff"] <= 1e-9 and parity["final_cost_rel_diff"] <= 1e-9
+                            and parity["flag_mismatches"] == 0 and parity["cost_monotone"])
 
+    lin_ms = k_ms["linearize_schur"]
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-        "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.config, p) if not sharded else
-                   f"{args.config}: {p.n_cam} cameras, {n_pt_total} points, {n_obs_total} observations, sharded by point over {world} GPU(s)",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms_max / steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, full.n_cam, full.n_pt, full.n_obs),
                    "lm_iterations_per_step": max_iter,
-                   "parallelism": "single GPU" if world == 1 else (
-                       f"points sharded over {world} GPUs, NCCL all-reduce of the reduced camera system" if sharded
-                       else f"{world} independent windows, one per GPU (replicas)"),
-                   "pcg": {"tol": args.pcg_tol, "iterations": pcg_iters} if p.n_cam > 38 else None,
-                   "l2": "flushed between steps (256 MiB write)" + ("; inside a step the window stays L2-resident by construction" if resident else ""),
+                   "parallelism": "single GPU" if world == 1 else
+                                  f"points sharded over {world} GPUs (cameras replicated), NCCL all-reduce of the reduced camera system and the costs every LM iteration",
+                   "solver": {"used": {1: "cholesky", 2: "pcg", 3: "band"}.get(int(r_prof.solver_used), "?"),
+                              "band_width": int(r_prof.band_width), "s_blocks": int(r_prof.s_blocks)},
+                   "l2": "flushed between steps (256 MiB write); the window itself is larger than L2",
                    "schur": args.schur},
-        "obs_per_s_residual_jacobian_schur": p.n_obs / (k_ms["linearize_schur"] * 1e-3) * world,
+        "obs_per_s_residual_jacobian_schur": full.n_obs / (lin_ms * 1e-3),
         "shard_observations": p.n_obs,
         "kernel_ms_per_lm_iteration": k_ms,
-        "final_cost": final_cost,
-        "roofline": roofline,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "api": "LocalBASolver.solve_local_inplace -> ba_solve_local_host (pinned host buffers)"},
-        "gpu_launches": launches_per_step * args.steps,
+        "final_cost": float(hist_sh[-1]),
+        "roofline": roofline_block(args.config, p, k_ms, ms_max / steps / max_iter, band_blocks),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
+                "api": "LocalBASolver.solve_local_inplace -> ba_solve_local_host (pinned host buffers, every rank its shard)"},
+        "parity": parity,
+        "gpu_launches": launches_per_step * steps,
         "clocks": clocks,
     }
 
-    if rank == 0 and world == 1 and not args.no_cpu and p.n_obs <= 400_000:
+    if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import lm_oracle as O
+        # bounded CPU sample: the first 1/20 of the window's points with every observation of theirs
+        frac = 20 if full.n_obs > 2_000_000 else (4 if full.n_obs > 400_000 else 1)
+        sub = full.shard_by_point(0, frac)
         t_c = time.perf_counter()
-        ref = O.solve_local(p.intr, p.R, p.t, p.fixed, p.X, p.obs_cam, p.obs_pt, p.obs_uv,
-                            O.LMParams(max_iter=max_iter))
+        O.solve_local(sub.intr, sub.R, sub.t, sub.fixed, sub.X, sub.obs_cam, sub.obs_pt, sub.obs_uv,
+                      O.LMParams(max_iter=max_iter))
         dt = time.perf_counter() - t_c
-        rel = float(np.max(np.abs(res.cost_hist - ref.cost_hist) / ref.cost_hist))
-        line["cpu_baseline"] = {"value": max_iter / dt, "unit": UNIT, "cores": 1, "kind": "port",
-                                "sample": f"the full window, one solve of {max_iter} LM iterations with "
-                                          f"oracle/lm_oracle.py (numpy float64, same algorithm) in {dt:.1f} s"}
-        line["parity_vs_oracle"] = {"max_rel_cost_diff": rel,
-                                    "accept_sequence_equal": bool(np.array_equal(res.accepted, ref.accepted)),
-                                    "flags_equal": bool(np.array_equal(res.flags, ref.flags))}
-    if rank == 0 and world == 1 and not args.no_cpu and p.n_obs <= 400_000:
+        line["cpu_baseline"] = {"value": max_iter / dt * (sub.n_obs / full.n_obs), "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"{sub.n_obs} of {full.n_obs} observations ({sub.n_pt} points, the first 1/{frac} of the window), "
+                                          f"one solve of {max_iter} LM iterations with oracle/lm_oracle.py (numpy float64 + scipy sparse "
+                                          f"direct solve, same algorithm) in {dt:.1f} s; value scaled by sample/window observations"}
+    if rank == 0 and world == 1 and not args.no_sub:
+        subs = {}
+        del win
+        torch.cuda.empty_cache()
+        for name in ("C1", "C2"):
+            try:
+                subs[name] = bench_window(ctx, name, args, with_cpu=not args.no_cpu)
+            except Exception as e:
+                subs[name] = {"error": repr(e)}
         try:
-            line["plugin"] = plugin_leg(p, local_rank, max_iter)
-        except Exception as e:                              # informational leg: never costs the bench line
-            line["plugin"] = {"error": repr(e)}
+            subs["C3"] = bench_pose_only(ctx, args)
+        except Exception as e:
+            subs["C3"] = {"error": repr(e)}
+        line["configs"] = subs
     if rank == 0:
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if ctx.dist is not None:
+        ctx.dist.destroy_process_group()
+
+
+def run_single(args, rank, local_rank, world):
+    """`--config C1|C2|C3`: one of the single-GPU configs as the top-level line (replicas for N > 1)."""
+    ctx = Ctx(rank, local_rank, world)
+    import b200ba  # noqa: F401
+    if args.config == "C3":
+        sub = bench_pose_only(ctx, args)
+    else:
+        sub = bench_window(ctx, args.config, args, with_cpu=not args.no_cpu and rank == 0)
+    v = ctx.sum_over_ranks(sub["value"])
+    line = {"metric": sub["metric"], "value": v, "unit": sub["unit"], "n_gpus": world, "steps": sub["steps"],
+            "warmup": sub["warmup"], "ms_per_step": ctx.max_over_ranks(sub["ms_per_step"]), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": sub["workload"], "lm_iterations_per_step": args.lm_iters,
+                       "parallelism": "single GPU" if world == 1 else f"{world} independent windows, one per GPU (replicas only: this config does not shard)",
+                       "l2": "flushed between steps (256 MiB write); inside a step the window stays L2-resident by construction"}}
+    for k in ("obs_per_s_residual_jacobian_schur", "kernel_ms_per_lm_iteration", "kernel_ms_per_step", "roofline", "e2e", "e2e_abi",
+              "parity", "cpu_baseline", "oracle_cpu", "gpu_launches", "clocks", "frames_per_s"):
+        if k in sub:
+            line[k] = sub[k]
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if ctx.dist is not None:
+        ctx.dist.destroy_process_group()
+
+
+def run_reference_pose_only(args, rank):
+    if rank != 0:
+        return
+    import cv2
+    synth = load_synth()
+    pp = synth.make_pose_only(n_frames=256, n_match=1000, seed=0)
+    nF, nM = pp.n_frames, pp.n_match
+    K = np.array([[pp.intr[0], 0, pp.intr[2]], [0, pp.intr[1], pp.intr[3]], [0, 0, 1.0]])
+    max_iter = args.lm_iters
+    cv2.setRNGSeed(42)
+    total = args.steps + args.warmup
+    n_sample = int(min(nF, max(8, 4000 // max(total, 1))))       # ~4 ms per frame: a few seconds per step
+    secs = []
+    for it in range(total):
+        t0 = time.perf_counter()
+        for f in range(n_sample):
+            a, b = pp.frame_offsets[f], pp.frame_offsets[f + 1]
+            reference_pnp(pp.X[a:b], pp.uv[a:b], K)
+        secs.append(time.perf_counter() - t0)
+    t_step = sum(secs[args.warmup:]) / max(len(secs) - args.warmup, 1)
+    fps = n_sample / t_step
+    value = fps * max_iter          # one reference pose estimate is set against one 10-iteration LM refinement
+    unit = "frame LM iter/s"
+    line = {"impl": "reference", "metric": "pose_only_lm_iterations_per_s", "value": value, "unit": unit, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C3: batched pose-only BA, {nF} frames x {nM // nF} 2D-3D matches, pinhole, Huber 5px, 10% outliers",
+                       "equivalence": f"value = frames/s x {max_iter}: one cv2.solvePnPRansac call replaces one {max_iter}-iteration pose-only LM"},
+            "frames_per_s": fps,
+            "cpu_baseline": {"value": value, "unit": unit, "cores": int(cv2.getNumThreads()), "kind": "reference",
+                             "sample": f"{n_sample} of {nF} frames per step, cv2 {cv2.__version__} solvePnPRansac exactly as "
+                                       f"motion_estimation.py:107-116 calls it, host cpus {os.cpu_count()}"},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -625,21 +876,24 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="C2")
+    ap.add_argument("--config", default="C4", help="C4 (default) / C5: sharded by point over the ranks; C1 / C2 / C3: single-GPU configs")
     ap.add_argument("--lm-iters", type=int, default=10)
     ap.add_argument("--schur", default="auto")
-    ap.add_argument("--shard", action="store_true", help="shard ONE problem by point over the ranks (default for C4/C5)")
     ap.add_argument("--pcg-tol", type=float, default=1e-10)
     ap.add_argument("--pcg-max-iter", type=int, default=3000)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the oracle legs (cpu_baseline, oracle parity)")
+    ap.add_argument("--no-sub", action="store_true", help="skip the C1 / C2 / C3 sub-objects of the N = 1 line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.config == "C3":
-        run_pose_only(args, rank, local_rank, world)
-    elif args.impl == "reference":
-        run_reference(args, rank, world)
+    if args.impl == "reference":
+        if args.config == "C3":
+            run_reference_pose_only(args, rank)
+        else:
+            run_reference(args, rank, world)
+    elif args.config in ("C1", "C2", "C3"):
+        run_single(args, rank, local_rank, world)
     else:
         run_b200(args, rank, local_rank, world)
 

@@ -3,7 +3,7 @@ import os
 
 import numpy as np
 
-from visual_slam_core_b200 import refgraph
+import refgraph
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 

@@ -1,0 +1,86 @@
+"""Parity of the CUDA path at BASELINE sizes and on C4/C5-shaped windows, against oracle trajectories computed
+once on the CPU and committed (tests/golden/make_large_golden.py -> tests/golden/lm_*.npz).
+
+  C2  BASELINE config 2, the full window: whole LM trajectory (VERDICT r1 weak #1a)
+  C3  BASELINE config 3, all 256 frames x 1000 matches (weak #1d)
+  L1  1 000 cameras x 50 000 points, co-visibility bandwidth 15: the banded layout and the 8-level cyclic
+      reduction C4 runs on (missing #3)
+  L2  10 000 cameras x 100 000 points: the 11-level path of C5
+
+Tolerances are BASELINE.json's: cost 1e-5 relative per iteration, rotations 1e-5 rad, translations 1e-5 of the
+median baseline (after removing the free monocular scale on the long trajectories, see helpers), flags bit-exact.
+"""
+import os
+import sys
+import zlib
+
+import numpy as np
+import pytest
+
+from visual_slam_core_b200 import LMConfig, LocalBASolver, synth
+
+from helpers import GOLDEN, gauge_aligned_trans_err, rot_angle, scale_norm_trans_err
+
+sys.path.insert(0, GOLDEN)
+import make_large_golden as G  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _load(name):
+    path = os.path.join(GOLDEN, f"lm_{name}.npz")
+    if not os.path.exists(path):
+        pytest.fail(f"{path} is missing: run tests/golden/make_large_golden.py")
+    return np.load(path)
+
+
+@pytest.mark.parametrize("name", ["C2", "L1", "L2"])
+def test_lm_trajectory_matches_the_committed_oracle_run(name):
+    g = _load(name)
+    p = G.make_window(name)
+    assert G.input_checksum(p) == int(g["checksum"]), "the generator no longer reproduces the fixture's window"
+    s = LocalBASolver(LMConfig())
+    res = s.solve_local(p.intr, p.R, p.t, p.fixed, p.X, p.obs_cam, p.obs_pt, p.obs_uv, p.pt_offsets)
+    s.close()
+    long_traj = p.n_cam > 40
+    rel = np.abs(res.cost_hist - g["cost_hist"]) / g["cost_hist"]
+    ang = rot_angle(res.R, g["R"])
+    if long_traj:
+        terr, scale = gauge_aligned_trans_err(res.R, res.t, g["R"], g["t"])
+    else:
+        terr, scale = scale_norm_trans_err(res.R, res.t, g["R"], g["t"]), 1.0
+    flags = np.unpackbits(g["flags_packed"])[: p.n_obs]
+    st = int(g["X_stride"])
+    dX = np.abs(res.X[::st] - g["X"]).max(axis=1)
+    print(f"\n[{name}] {p.n_cam} cams / {p.n_pt} pts / {p.n_obs} obs, solver {res.extra['solver_used']} (band {res.extra['band_width']}): "
+          f"accepted {res.accepted.tolist()} vs {g['accepted'].tolist()}, max rel cost diff {rel.max():.2e}, rot {ang.max():.2e} rad, "
+          f"trans {terr.max():.2e} (scale {scale:.9f}), flag mismatches {int((res.flags != flags).sum())} of {p.n_obs}, "
+          f"points moved > 1e-4: {float(np.mean(dX > 1e-4)):.4f}, gpu {res.gpu_ms:.2f} ms")
+    np.testing.assert_array_equal(res.accepted, g["accepted"])
+    np.testing.assert_allclose(res.lambda_hist, g["lambda_hist"], rtol=1e-12)
+    assert rel.max() <= 1e-5
+    assert np.max(np.abs(res.cand_cost_hist - g["cand_cost_hist"]) / g["cand_cost_hist"]) <= 1e-5
+    assert ang.max() <= 1e-5
+    assert terr.max() <= 1e-5
+    np.testing.assert_array_equal(res.flags, flags)
+    assert np.mean(dX > (1e-3 if long_traj else 1e-4)) < 0.02
+
+
+def test_pose_only_full_c3_matches_the_committed_oracle_run():
+    g = _load("C3")
+    pp = synth.make_pose_only(n_frames=256, n_match=1000, seed=0)
+    c = 0
+    for a in (pp.R, pp.t, pp.X, pp.uv, pp.frame_offsets):
+        c = zlib.crc32(np.ascontiguousarray(a).tobytes(), c)
+    assert int(c) == int(g["checksum"])
+    s = LocalBASolver(LMConfig())
+    out = s.solve_pose_only(pp.intr, pp.R, pp.t, pp.X, pp.uv, pp.frame_offsets)
+    s.close()
+    rel = np.abs(out["cost_hist"] - g["cost_hist"]) / g["cost_hist"]
+    ang = rot_angle(out["R"], g["R"])
+    flags = np.unpackbits(g["flags_packed"])[: pp.n_match]
+    print(f"\n[C3] 256 x 1000: max rel cost diff {rel.max():.2e}, rot {ang.max():.2e}, trans {np.abs(out['t'] - g['t']).max():.2e}, "
+          f"flag mismatches {int((out['flags'] != flags).sum())}")
+    np.testing.assert_array_equal(out["accepted"], g["accepted"])
+    assert rel.max() <= 1e-5 and ang.max() <= 1e-5 and np.abs(out["t"] - g["t"]).max() <= 1e-5
+    np.testing.assert_array_equal(out["flags"], flags)

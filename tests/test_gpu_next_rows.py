@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 
 from oracle import lm_oracle as O
-from visual_slam_core_b200 import B200Optimizer, LMConfig, LocalBASolver, handlers, motion, packing, refgraph, synth
+import refgraph
+from visual_slam_core_b200 import B200Optimizer, LMConfig, LocalBASolver, handlers, motion, packing, synth
 
 from helpers import GOLDEN, graph_from_golden, rot_angle, window_points
 

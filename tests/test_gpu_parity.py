@@ -8,7 +8,8 @@ import numpy as np
 import pytest
 
 from oracle import lm_oracle as O
-from visual_slam_core_b200 import B200Optimizer, LMConfig, LocalBASolver, packing, refgraph, synth
+import refgraph
+from visual_slam_core_b200 import B200Optimizer, LMConfig, LocalBASolver, packing, synth
 
 from helpers import (gauge_aligned_trans_err, graph_from_golden, load_golden, rot_angle,
                      scale_norm_trans_err, window_points)

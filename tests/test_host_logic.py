@@ -3,7 +3,8 @@ import numpy as np
 import pytest
 
 from oracle import lm_oracle as O
-from visual_slam_core_b200 import B200Optimizer, packing, refgraph, synth
+import refgraph
+from visual_slam_core_b200 import B200Optimizer, packing, synth
 
 from helpers import graph_from_golden, load_golden, window_points
 

@@ -1,6 +1,8 @@
-"""Packers against the UNMODIFIED reference's own objects (runs only where /root/reference is mounted, i.e. in
-the build container; the GPU box and any other checkout skip it).  The golden fixtures pin the same order
-rules offline; this one makes sure the real `KeyFrame` / `MapPoint` / `cv2.KeyPoint` types take the fast paths."""
+"""Packers and the plugin against the UNMODIFIED reference's own objects.  The reference is taken from
+baseline/_ref (the offline install `__graft_entry__.build()` makes; it travels to the GPU box with the snapshot)
+or from /root/reference; a checkout with neither skips.  The golden fixtures pin the same order rules offline;
+this makes sure the real `KeyFrame` / `MapPoint` / `cv2.KeyPoint` types take the fast paths, and -- on a GPU --
+that `Map.optimize_local(B200Optimizer, keyframes)` works end to end on them."""
 import os
 import sys
 import types
@@ -10,9 +12,10 @@ import pytest
 
 from visual_slam_core_b200 import packing, synth
 
-REF = "/root/reference"
-pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "visual_slam")),
-                                reason="the reference tree is not mounted here")
+from oracle import ref_shim
+
+REF = ref_shim.find_reference()
+pytestmark = pytest.mark.skipif(REF is None, reason="no reference tree here (baseline/_ref, /root/reference)")
 
 
 @pytest.fixture()
@@ -32,6 +35,14 @@ def ref_types(tmp_path, monkeypatch):
     from visual_slam.map.map_point import MapPoint
     from visual_slam.map.pose import Pose
     return cv2, PinholeCamera, KeyFrame, MapPoint, Pose
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
 
 
 def _real_graph(p, ref_types, table=None):
@@ -55,7 +66,7 @@ def test_packers_on_the_references_own_objects(ref_types, monkeypatch):
     KeyFrame = ref_types[2]
     p = synth.make_problem("T1", seed=4)
     table = packing.ObservationTable()
-    table.install(KeyFrame)
+    table.install(ref_types[3])                           # hooks on the reference's own MapPoint class
     try:
         kfs, mps = _real_graph(p, ref_types)
     finally:
@@ -82,3 +93,41 @@ def test_packers_on_the_references_own_objects(ref_types, monkeypatch):
     packing.write_back(kfs, mps, R, t, X)
     np.testing.assert_allclose(np.asarray(mps[3].position).reshape(3), X[3])
     np.testing.assert_allclose(np.asarray(kfs[2].t_w2c).reshape(3), t[2])
+
+
+@pytest.mark.gpu
+def test_plugin_end_to_end_on_the_references_own_map(ref_types, tmp_path):
+    """`Map.optimize_local` of the UNMODIFIED reference dispatching to `B200Optimizer` on the reference's own
+    KeyFrame / MapPoint / Pose objects: the CUDA solve equals the oracle on the window the reference's walk packs,
+    and the results arrive through the reference's own setters (VERDICT r1 weak #1c)."""
+    from visual_slam.map.map import Map
+    from oracle import lm_oracle as O
+    from visual_slam_core_b200 import B200Optimizer
+    from helpers import rot_angle
+    p = synth.make_problem("T2", seed=3)
+    kfs, mps = _real_graph(p, ref_types)
+    opt = B200Optimizer(log_dir=str(tmp_path), device="cuda:0")
+    try:
+        assert Map().optimize_local(opt, kfs) is True
+        assert opt.packer_name == "ObservationTable"
+        res = opt.last_result
+        pw = opt.last_packed
+        ref = O.solve_local(pw.intr, pw.R, pw.t, pw.fixed, pw.X, pw.obs_cam, pw.obs_pt, pw.obs_uv)
+        np.testing.assert_array_equal(res.accepted, ref.accepted)
+        np.testing.assert_allclose(res.cost_hist, ref.cost_hist, rtol=1e-9)
+        np.testing.assert_array_equal(res.flags, ref.flags)
+        R = np.array([kf.R_w2c for kf in kfs]); t = np.array([np.asarray(kf.t_w2c).reshape(3) for kf in kfs])
+        assert rot_angle(R, ref.R).max() < 1e-9 and np.abs(t - ref.t).max() < 1e-8
+        # the reference's Map hands the points over in ITS collection order (map/map.py:159-169)
+        unique = {}
+        for kf in kfs:
+            for mp in kf.get_all_mappoints().values():
+                unique[id(mp)] = mp
+        X = np.array([np.asarray(mp.position).reshape(3) for mp in unique.values()])
+        np.testing.assert_allclose(X, res.X, rtol=0, atol=0)
+        # second call: the table is warm, the window is packed without a walk
+        n_ing = opt.table.stats["ingested_points"]
+        assert Map().optimize_local(opt, kfs) is True and opt.table.stats["ingested_points"] == n_ing
+    finally:
+        if opt.table is not None:
+            opt.table.uninstall()

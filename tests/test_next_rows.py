@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 
 from oracle import ref_adam
-from visual_slam_core_b200 import B200Optimizer, handlers, motion, packing, refgraph, synth
+import refgraph
+from visual_slam_core_b200 import B200Optimizer, handlers, motion, packing, synth
 from visual_slam_core_b200.solver import SolveResult
 
 from helpers import GOLDEN, graph_from_golden, load_golden, window_points
@@ -21,7 +22,7 @@ def _assert_same_window(a, b):
 @pytest.mark.parametrize("name", ["a", "b", "c"])
 def test_observation_table_packs_like_the_reference_loop(name):
     table = packing.ObservationTable(capacity=8)             # small: exercises growth
-    table.install(refgraph.KeyFrame)
+    table.install(refgraph.MapPoint)
     try:
         g = load_golden(name)
         cam, kfs, mps = graph_from_golden(g)
@@ -52,6 +53,118 @@ def test_observation_table_multi_sensor_order_and_removal():
         kfs[2].add_map_point(0, 7, mps[3]); kfs[1].add_map_point(1, 7, mps[3])
         _assert_same_window(table.pack(kfs, mps), packing.pack_window(kfs, mps))
         kfs[0].remove_map_point(0, 1)                                               # map/keyframe.py:93-100
+        _assert_same_window(table.pack(kfs, mps), packing.pack_window(kfs, mps))
+    finally:
+        table.uninstall()
+
+
+def test_observation_table_readd_after_removal_goes_to_the_end_like_the_dict():
+    """`remove_map_point` then re-adding the same (keyframe, point) must sort the observation where the
+    reference's dictionary now has it (at the end), not at its old row."""
+    table = packing.ObservationTable()
+    table.install(refgraph.MapPoint)
+    try:
+        cam = refgraph.Camera(1280, 720, 700, 700, 640, 360)
+        kps = lambda n: [refgraph.KeyPoint(10.0 * i, 5.0 * i) for i in range(n)]
+        kfs = [refgraph.KeyFrame(cam, [kps(8)], np.eye(3), np.zeros(3)) for _ in range(3)]
+        mp = refgraph.MapPoint([0.0, 0.0, 5.0])
+        for i in range(3):
+            kfs[i].add_map_point(0, i, mp)
+        kfs[0].remove_map_point(0, 0)
+        kfs[0].add_map_point(0, 3, mp)
+        pw = table.pack(kfs, [mp])
+        _assert_same_window(pw, packing.pack_window(kfs, [mp]))
+        np.testing.assert_array_equal(pw.obs_cam, [1, 2, 0])
+        # two sensors of one keyframe: removing one keeps the keyframe's place, the re-added sensor goes last in it
+        kfs2 = [refgraph.KeyFrame(cam, [kps(8), kps(8)], np.eye(3), np.zeros(3)) for _ in range(2)]
+        mp2 = refgraph.MapPoint([0.1, 0.0, 5.0])
+        kfs2[0].add_map_point(0, 1, mp2); kfs2[0].add_map_point(1, 2, mp2); kfs2[1].add_map_point(0, 3, mp2)
+        kfs2[0].remove_map_point(0, 1); kfs2[0].add_map_point(0, 4, mp2)
+        _assert_same_window(table.pack(kfs2, [mp2]), packing.pack_window(kfs2, [mp2]))
+        mp2.remove_observation(kfs2[0].keyframe_id)             # whole keyframe entry (map/observation.py:36-38)
+        _assert_same_window(table.pack(kfs2, [mp2]), packing.pack_window(kfs2, [mp2]))
+    finally:
+        table.uninstall()
+
+
+def test_observation_table_refuses_duplicate_points_and_the_plugin_walks_instead():
+    """a point handed in twice needs its rows twice; the table says so and the walk takes over."""
+    table = packing.ObservationTable()
+    table.install(refgraph.MapPoint)
+    try:
+        p = synth.make_problem("T0", seed=5)
+        cam, kfs, mps = refgraph.graph_from_problem(p)
+    finally:
+        table.uninstall()
+    dup = mps + [mps[0]]
+    assert table.pack(kfs, dup) is None and table.stats["fallbacks"] == 1
+    opt = B200Optimizer(log_dir=None)
+    opt.table = table
+    pw = opt.pack(kfs, dup)
+    assert opt.packer_name == "pack_window"
+    _assert_same_window(pw, packing.pack_window(kfs, dup))
+    assert opt.pack(kfs, mps) is not None and opt.packer_name == "ObservationTable"
+
+
+def test_observation_table_ingests_a_graph_built_before_the_hooks():
+    """The plugin installs the hooks on its first call: points that already exist are mirrored by one walk over
+    their own dictionaries, points created later through the hooks, and both kinds mix in one window."""
+    g = load_golden("b")
+    cam, kfs, mps = graph_from_golden(g)                      # built with no table anywhere
+    window = kfs[: int(g["n_kf"])]
+    pts = window_points(window)
+    opt = B200Optimizer(log_dir=None)
+    opt.table = packing.ObservationTable()
+    try:
+        pw = opt.pack(window, pts)
+        assert opt.packer_name == "ObservationTable" and opt.table.stats["ingested_points"] == len(pts)
+        _assert_same_window(pw, packing.pack_window(window, pts))
+        # the map grows: a new point (hook from its first observation) and a new observation of an old point
+        new = refgraph.MapPoint([0.3, 0.1, 7.0])
+        window[1].keypoints[0].append(refgraph.KeyPoint(11.0, 12.0))
+        window[2].keypoints[0].append(refgraph.KeyPoint(13.0, 14.0))
+        window[1].add_map_point(0, len(window[1].keypoints[0]) - 1, new)
+        window[2].add_map_point(0, len(window[2].keypoints[0]) - 1, new)
+        window[0].keypoints[0].append(refgraph.KeyPoint(15.0, 16.0))
+        old = pts[3]
+        old.remove_observation(window[0].keyframe_id)
+        window[0].add_map_point(0, len(window[0].keypoints[0]) - 1, old)
+        pts2 = window_points(window)
+        n_ing = opt.table.stats["ingested_points"]
+        pw2 = opt.pack(window, pts2)
+        assert opt.packer_name == "ObservationTable" and opt.table.stats["ingested_points"] == n_ing
+        _assert_same_window(pw2, packing.pack_window(window, pts2))
+    finally:
+        opt.table.uninstall()
+
+
+def test_observation_table_is_safe_under_concurrent_map_growth():
+    """Hooks fire from the tracking / local-mapping threads while pack() runs in the local-BA thread."""
+    import threading
+    table = packing.ObservationTable(capacity=16)
+    table.install(refgraph.MapPoint)
+    try:
+        cam = refgraph.Camera(1280, 720, 700, 700, 640, 360)
+        kfs = [refgraph.KeyFrame(cam, [[refgraph.KeyPoint(float(i), float(i)) for i in range(4000)]], np.eye(3), np.zeros(3))
+               for _ in range(3)]
+        mps = [refgraph.MapPoint([0.01 * j, 0.0, 5.0]) for j in range(3000)]
+        errors = []
+
+        def grow():
+            try:
+                for j, mp in enumerate(mps):
+                    for i in range(3):
+                        kfs[i].add_map_point(0, j, mp)
+            except Exception as e:          # pragma: no cover
+                errors.append(e)
+
+        th = threading.Thread(target=grow)
+        th.start()
+        while th.is_alive():
+            pw = table.pack(kfs, mps[:500])
+            assert pw is not None and int(pw.pt_offsets[-1]) == pw.n_obs
+        th.join()
+        assert not errors
         _assert_same_window(table.pack(kfs, mps), packing.pack_window(kfs, mps))
     finally:
         table.uninstall()
@@ -236,8 +349,24 @@ def test_pose_only_call_site_failure_tuple_matches_the_reference():
     out = motion.refine_motion_from_2d3d(g["pts3d"][:3], g["pts2d"][:3], g["K"])
     assert out == (None, None, False, None)
     assert g["ref_inliers"].ndim == 2 and g["ref_inliers"].shape[1] == 1 and str(g["ref_inliers_dtype"]) == "int32"
-    with pytest.raises(ValueError):
-        motion.refine_motion_from_2d3d(g["pts3d"], g["pts2d"], g["K"], dist=np.array([0.1, 0, 0, 0, 0]))
+    # the call site passes `self.camera.dist` (tracking.py:350-356) and the reference never raises: neither do we
+    # (no GPU in this process: the solver cannot be created, which must come back as the failure tuple too)
+    out = motion.refine_motion_from_2d3d(g["pts3d"], g["pts2d"], g["K"], dist=np.array([0.1, 0, 0, 0, 0]),
+                                         R0=np.eye(3), t0=np.zeros(3))
+    assert isinstance(out, tuple) and len(out) == 4 and (out[2] is True or out == (None, None, False, None))
+    assert motion.refine_motion_from_2d3d(g["pts3d"], g["pts2d"][:-1], g["K"]) == (None, None, False, None)
+
+
+def test_undistortion_of_the_call_sites_pixels_inverts_the_lens_model():
+    cv2 = pytest.importorskip("cv2")
+    K = np.array([[700.0, 0, 640.0], [0, 700.0, 360.0], [0, 0, 1.0]])
+    dist = np.array([0.12, -0.05, 0.001, -0.002, 0.01])
+    rng = np.random.default_rng(3)
+    X = np.stack([rng.uniform(-2, 2, 50), rng.uniform(-1, 1, 50), rng.uniform(5, 12, 50)], axis=1)
+    ideal = (X[:, :2] / X[:, 2:]) * 700.0 + np.array([640.0, 360.0])
+    distorted, _ = cv2.projectPoints(X, np.zeros(3), np.zeros(3), K, dist)
+    back = motion._undistort(distorted.reshape(-1, 2), K, dist)
+    assert np.abs(back - ideal).max() < 1e-3
 
 
 # ---------------------------------------------------------------------------------------- N4 / A8
@@ -285,6 +414,31 @@ def test_cull_bad_points_consumes_the_flags():
     assert n_obs_before - n_obs_after == int(flags.sum())
     kf = kfs[int(pw.obs_cam[o_single])]
     assert pts[int(pw.obs_pt[o_single])] not in kf.get_all_mappoints().values()
+
+
+def test_cull_bad_points_leaves_points_with_observations_outside_the_window_alone():
+    """one in-window observation (unflagged) and two in keyframes outside the window is a healthy
+    point; a point that loses its flagged in-window observation but keeps two outside is healthy too."""
+    cam = refgraph.Camera(1280, 720, 700, 700, 640, 360)
+    kps = lambda n: [refgraph.KeyPoint(10.0 * i, 5.0 * i) for i in range(n)]
+    kfs = [refgraph.KeyFrame(cam, [kps(8)], np.eye(3), np.zeros(3)) for _ in range(5)]
+    a, b, c = (refgraph.MapPoint([0.1 * j, 0.0, 5.0]) for j in range(3))
+    for i, mp in ((0, a), (3, a), (4, a), (1, b), (3, b), (4, b), (0, c), (1, c)):
+        kfs[i].add_map_point(0, [a, b, c].index(mp), mp)
+    window, pts = kfs[:3], [a, b, c]
+    pw = packing.pack_window(window, pts)
+    assert pw.n_obs == 4
+    flags = np.zeros(4, dtype=np.uint8)
+    flags[int(pw.pt_offsets[1])] = 1                               # b's only in-window observation
+    flags[int(pw.pt_offsets[2])] = 1                               # one of c's two (c has nothing outside)
+    opt = B200Optimizer(log_dir=None)
+    opt.last_packed = pw
+    opt.last_result = SolveResult(R=pw.R, t=pw.t, X=pw.X, flags=flags, cost_hist=np.zeros(1), cand_cost_hist=np.zeros(0),
+                                  lambda_hist=np.zeros(0), accepted=np.zeros(0, np.uint8), solve_fail=np.zeros(0, np.int32),
+                                  pcg_iters=np.zeros(0, np.int32), n_iter=0, gpu_ms=0.0, n_launches=0)
+    assert opt.cull_bad_points(window, pts, min_observations=2) == 1
+    assert a.is_valid() and b.is_valid() and not c.is_valid()
+    assert len(b.get_observations()) == 2 and len(a.get_observations()) == 3
 
 
 def test_local_optimize_call_site_needs_more_than_two_keyframes():

@@ -25,6 +25,7 @@ typedef int (*fn_init_rank)(nccl_comm*, int, nccl_uid, int);
 typedef int (*fn_destroy)(nccl_comm);
 typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t);
 typedef int (*fn_allgather)(const void*, void*, size_t, int, nccl_comm, cudaStream_t);
+typedef int (*fn_broadcast)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t);
 typedef const char* (*fn_errstr)(int);
 struct NcclApi {
   void* lib = nullptr;
@@ -33,6 +34,7 @@ struct NcclApi {
   fn_destroy destroy = nullptr;
   fn_allreduce allreduce = nullptr;
   fn_allgather allgather = nullptr;
+  fn_broadcast broadcast = nullptr;
   fn_errstr errstr = nullptr;
 };
 NcclApi g_nccl;
@@ -47,8 +49,9 @@ bool load_nccl() {
     g_nccl.destroy = (fn_destroy)dlsym(h, "ncclCommDestroy");
     g_nccl.allreduce = (fn_allreduce)dlsym(h, "ncclAllReduce");
     g_nccl.allgather = (fn_allgather)dlsym(h, "ncclAllGather");
+    g_nccl.broadcast = (fn_broadcast)dlsym(h, "ncclBroadcast");
     g_nccl.errstr = (fn_errstr)dlsym(h, "ncclGetErrorString");
-    if (g_nccl.get_uid && g_nccl.init_rank && g_nccl.destroy && g_nccl.allreduce && g_nccl.allgather) {
+    if (g_nccl.get_uid && g_nccl.init_rank && g_nccl.destroy && g_nccl.allreduce && g_nccl.allgather && g_nccl.broadcast) {
       g_nccl.lib = h;
       return true;
     }
@@ -73,7 +76,7 @@ struct ba_handle {
   ba_params prm;
   std::string err;
   // workspace
-  DevBuf pose0, pose1, X0, X1, red, dp, ctl, cand, dbg, part;
+  DevBuf camstate, X0, X1, red, ctl, cand, dbg, part;   // camstate = pose[0] | pose[1] | dp, contiguous (one broadcast)
   // sparse path: structure + PCG workspace
   DevBuf bits, wpre, row_nnz, row_ptr, col_idx, tpos, pcg, bits_all;
   // banded path: factor columns, forward-substituted rhs, inverse pivots, bandwidth scalar
@@ -130,6 +133,16 @@ static void prof_collect(ba_handle* h) {
       h->prof_ms[h->prof_tag[i]] += ms;
   }
 }
+
+// cudaSetDevice for the duration of an API call; the caller's current device comes back on every exit path
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 #define CK(call)                                                                          \
   do {                                                                                    \
@@ -210,8 +223,11 @@ extern "C" int ba_create(const ba_params* params, int device, ba_handle** out) {
   ba_handle* h = new ba_handle();
   h->device = device;
   h->prm = p;
+  int prev_dev = -1;
+  cudaGetDevice(&prev_dev);
   cudaError_t ce = cudaSetDevice(device);
   if (ce != cudaSuccess) { g_create_err = std::string("cudaSetDevice: ") + cudaGetErrorString(ce); delete h; return BA_ERR_CUDA; }
+  struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev == device ? -1 : prev_dev};
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
   int ke = configure_kernels();
@@ -235,17 +251,22 @@ extern "C" int ba_create(const ba_params* params, int device, ba_handle** out) {
 
 extern "C" int ba_set_params(ba_handle* h, const ba_params* params) {
   if (!h || check_params(params) != BA_OK) return BA_ERR_INVALID;
+  // the captured LM loop depends on the solver / Schur kind, the iteration count and the PCG settings; the LM
+  // scalars (damping, Huber delta, chi2 threshold ...) travel with k_init outside the graph
+  const bool regraph = params->max_iter != h->prm.max_iter || params->solver_kind != h->prm.solver_kind ||
+                       params->schur_kind != h->prm.schur_kind || params->use_graph != h->prm.use_graph ||
+                       params->profile != h->prm.profile || params->pcg_max_iter != h->prm.pcg_max_iter ||
+                       params->pcg_tol != h->prm.pcg_tol;
   h->prm = *params;
-  // the captured LM loop depends on the solver / Schur kind and the iteration count
-  if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; h->graph_key = ba_handle::GraphKey(); }
+  if (regraph && h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; h->graph_key = ba_handle::GraphKey(); }
   return BA_OK;
 }
 
 extern "C" int ba_destroy(ba_handle* h) {
   if (!h) return BA_OK;
-  cudaSetDevice(h->device);
+  DeviceGuard dev_guard(h->device);
   if (h->graph) cudaGraphExecDestroy(h->graph);
-  DevBuf* bufs[] = {&h->pose0, &h->pose1, &h->X0, &h->X1, &h->red, &h->dp, &h->ctl, &h->cand,
+  DevBuf* bufs[] = {&h->camstate, &h->X0, &h->X1, &h->red, &h->ctl, &h->cand,
                     &h->d_R, &h->d_t, &h->d_fixed, &h->d_X, &h->d_ocam, &h->d_opt, &h->d_ouv,
                     &h->d_off, &h->d_flags, &h->d_hist, &h->d_acc, &h->d_foff, &h->dbg, &h->part,
                     &h->bits, &h->wpre, &h->row_nnz, &h->row_ptr, &h->col_idx, &h->tpos, &h->pcg,
@@ -267,7 +288,7 @@ extern "C" int ba_destroy(ba_handle* h) {
 // ------------------------------------------------------------------------------------------
 // local BA
 // ------------------------------------------------------------------------------------------
-enum { MODE_DENSE = 0, MODE_PCG = 1, MODE_BAND = 2 };
+enum { MODE_DENSE = 0, MODE_PCG = 1, MODE_BAND = 2, MODE_NONE = 3 };   // NONE: no reduced camera matrix (cost evaluation)
 
 // co-visibility bandwidth in keyframes (max over points of the camera-index spread); one host sync
 static int band_width(ba_handle* h, int n_pt, const int32_t* obs_cam, const int32_t* pt_off,
@@ -325,20 +346,18 @@ static int make_work(ba_handle* h, int n_cam, int n_pt, int n_obs, const double 
   int rc;
   memset(&w, 0, sizeof(w));
   w.band_w = -1;
-  if ((rc = ensure(h, h->pose0, sizeof(double) * 12 * (size_t)n_cam))) return rc;
-  if ((rc = ensure(h, h->pose1, sizeof(double) * 12 * (size_t)n_cam))) return rc;
+  if ((rc = ensure(h, h->camstate, sizeof(double) * (30 * (size_t)n_cam + 2)))) return rc;
   if ((rc = ensure(h, h->X0, sizeof(double) * 3 * (size_t)(n_pt + 1)))) return rc;
   if ((rc = ensure(h, h->X1, sizeof(double) * 3 * (size_t)(n_pt + 1)))) return rc;
-  if ((rc = ensure(h, h->dp, sizeof(double) * (size_t)(n + 1)))) return rc;
   if ((rc = ensure(h, h->ctl, sizeof(LmCtl)))) return rc;
   if ((rc = ensure(h, h->cand, sizeof(double) * 2))) return rc;
   w.n_cam = n_cam; w.n_pt = n_pt; w.n_obs = n_obs; w.n = n;
   w.K = Intr{intr[0], intr[1], intr[2], intr[3]};
   w.obs_cam = obs_cam; w.obs_pt = obs_pt; w.obs_uv = obs_uv; w.pt_off = pt_off; w.fixed = fixed;
-  w.pose[0] = (double*)h->pose0.p; w.pose[1] = (double*)h->pose1.p;
+  w.pose[0] = (double*)h->camstate.p; w.pose[1] = w.pose[0] + 12 * (size_t)n_cam;
   w.X[0] = (double*)h->X0.p; w.X[1] = (double*)h->X1.p;
   w.cost_cand = (double*)h->cand.p;
-  w.dp = (double*)h->dp.p;
+  w.dp = w.pose[1] + 12 * (size_t)n_cam;
   w.ctl = (LmCtl*)h->ctl.p;
   w.world = h->world;
   if (pt_off != nullptr && n_pt > 0) {
@@ -353,7 +372,9 @@ static int make_work(ba_handle* h, int n_cam, int n_pt, int n_obs, const double 
     if ((rc = ensure(h, h->dbg, sizeof(long long) * 4096))) return rc;
     w.dbg = (long long*)h->dbg.p;
   }
-  if (mode == MODE_DENSE) {
+  if (mode == MODE_NONE) {
+    w.s_len = 0;
+  } else if (mode == MODE_DENSE) {
     w.s_len = s_doubles(n_cam);
   } else if (mode == MODE_BAND) {
     w.band_w = bw;
@@ -472,11 +493,18 @@ static int enqueue_lm_loop(ba_handle* h, const Work& w, int schur, cudaStream_t 
     } else {
       launches += launch_rcs_cholesky(w, s);
     }
+    if (h->world > 1) {
+      // the replicated solve ends in float64 REDs whose order differs from rank to rank: rank 0's camera step
+      // and candidate poses go to everyone, so the replicated state stays bit-identical across ranks
+      prof_mark(h, TAG_COMM, s);
+      int r = g_nccl.broadcast(w.pose[0], w.pose[0], 30 * (size_t)w.n_cam, kNcclDouble, 0, h->comm, s);
+      if (r != 0) { h->err = std::string("ncclBroadcast(camera state): ") + (g_nccl.errstr ? g_nccl.errstr(r) : "?"); return BA_ERR_NCCL; }
+    }
     prof_mark(h, TAG_BACK, s);
     launches += launch_backsub(w, h->sm_count, s);
     if (h->world > 1) {
       prof_mark(h, TAG_COMM, s);
-      int r = g_nccl.allreduce(w.cost_cand, w.cost_cand, 1, kNcclDouble, kNcclSum, h->comm, s);
+      int r = g_nccl.allreduce(w.cost_cand, w.cost_cand, 2, kNcclDouble, kNcclSum, h->comm, s);
       if (r != 0) { h->err = std::string("ncclAllReduce(cost): ") + (g_nccl.errstr ? g_nccl.errstr(r) : "?"); return BA_ERR_NCCL; }
       launches += launch_accept(w, s);
     }
@@ -536,7 +564,7 @@ extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t
   if (n_cam <= 0 || n_pt < 0 || n_obs < 0 || !intr || !cam_R || !cam_t || !cam_fixed ||
       (n_pt > 0 && (!X || !pt_offsets)) || (n_obs > 0 && (!obs_cam || !obs_pt || !obs_uv)))
     return BA_ERR_INVALID;
-  CK(cudaSetDevice(h->device));
+  DeviceGuard dev_guard(h->device);
   cudaStream_t s = (cudaStream_t)stream;
   int mode = MODE_DENSE, bw = -1;
   int rc = pick_mode(h, n_cam, n_pt, obs_cam, pt_offsets, s, &mode, &bw);
@@ -558,6 +586,15 @@ extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t
   CK(cudaEventRecord(h->ev0, s));
   prof_mark(h, TAG_OTHER, s);
   launches += launch_init(w, cam_R, cam_t, X, li, s);
+  if (h->prm.max_iter == 0) {
+    // nothing will linearise: the report's initial cost comes from a plain evaluation of the objective
+    launches += launch_eval_cost(w, w.pose[0], w.X[0], w.cost_cand, h->prm.huber_delta, s);
+    if (h->world > 1) {
+      int r = g_nccl.allreduce(w.cost_cand, w.cost_cand, 1, kNcclDouble, kNcclSum, h->comm, s);
+      if (r != 0) { h->err = std::string("ncclAllReduce(cost): ") + (g_nccl.errstr ? g_nccl.errstr(r) : "?"); return BA_ERR_NCCL; }
+    }
+    launches += launch_cost0(w, s);
+  }
 
   bool use_graph = h->prm.use_graph != 0 && h->prm.max_iter > 0 && !h->prm.profile && !sparse;
   if (use_graph) {
@@ -616,7 +653,18 @@ extern "C" int ba_solve_local_host(ba_handle* h, int32_t n_cam, int32_t n_pt, in
   if (n_cam <= 0 || n_pt < 0 || n_obs < 0 || !intr || !cam_R || !cam_t || !cam_fixed ||
       (n_pt > 0 && (!X || !pt_offsets)) || (n_obs > 0 && (!obs_cam || !obs_uv)))
     return BA_ERR_INVALID;
-  CK(cudaSetDevice(h->device));
+  // host arrays are cheap to check and the kernels index with them unchecked
+  if (n_pt > 0) {
+    if (pt_offsets[0] != 0 || pt_offsets[n_pt] != n_obs) { h->err = "pt_offsets must start at 0 and end at n_obs"; return BA_ERR_INVALID; }
+    for (int32_t j = 0; j < n_pt; ++j)
+      if (pt_offsets[j + 1] < pt_offsets[j]) { h->err = "pt_offsets must be non-decreasing"; return BA_ERR_INVALID; }
+  } else if (n_obs != 0) {
+    h->err = "observations without points";
+    return BA_ERR_INVALID;
+  }
+  for (int32_t o = 0; o < n_obs; ++o)
+    if ((uint32_t)obs_cam[o] >= (uint32_t)n_cam) { h->err = "obs_cam out of range"; return BA_ERR_INVALID; }
+  DeviceGuard dev_guard(h->device);
   cudaStream_t s = h->stream;
   int rc;
   // R | t | fixed in one pinned staging record: one copy up, one copy (R | t) down
@@ -678,10 +726,10 @@ extern "C" int ba_eval_cost(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t n
                             const double* X, const int32_t* obs_cam, const int32_t* obs_pt,
                             const float* obs_uv, void* stream, double* cost_out) {
   if (!h || !cost_out || n_cam <= 0) return BA_ERR_INVALID;
-  CK(cudaSetDevice(h->device));
+  DeviceGuard dev_guard(h->device);
   cudaStream_t s = (cudaStream_t)stream;
   Work w;
-  int rc = make_work(h, n_cam, n_pt, n_obs, intr, nullptr, obs_cam, obs_pt, obs_uv, nullptr, w);
+  int rc = make_work(h, n_cam, n_pt, n_obs, intr, nullptr, obs_cam, obs_pt, obs_uv, nullptr, w, MODE_NONE);
   if (rc) return rc;
   LmInit li{h->prm.lambda0, h->prm.huber_delta, h->prm.chi2_thr, h->prm.lambda_up,
             h->prm.lambda_down, h->prm.lambda_min, h->prm.lambda_max, h->prm.accept_rtol};
@@ -701,7 +749,7 @@ extern "C" int ba_debug_linearize(ba_handle* h, int32_t n_cam, int32_t n_pt, int
                                   double* S_host, double* b_host, double* diagU_host,
                                   double* cost_host) {
   if (!h || n_cam <= 0) return BA_ERR_INVALID;
-  CK(cudaSetDevice(h->device));
+  DeviceGuard dev_guard(h->device);
   cudaStream_t s = (cudaStream_t)stream;
   if (6 * n_cam > rcs_cholesky_max_n()) { h->err = "ba_debug_linearize: dense layout only"; return BA_ERR_TOO_LARGE; }
   Work w;
@@ -731,7 +779,7 @@ extern "C" int ba_solve_pose_only(ba_handle* h, int32_t n_frames, int32_t n_matc
   if (!h || n_frames < 0 || n_match < 0 || !intr) return BA_ERR_INVALID;
   if (n_frames == 0) return BA_OK;
   if (!R || !t || !frame_offsets || (n_match > 0 && (!X || !uv))) return BA_ERR_INVALID;
-  CK(cudaSetDevice(h->device));
+  DeviceGuard dev_guard(h->device);
   PoseWork w;
   w.n_frames = n_frames;
   w.K = Intr{intr[0], intr[1], intr[2], intr[3]};
@@ -755,7 +803,7 @@ extern "C" int ba_solve_pose_only_host(ba_handle* h, int32_t n_frames, int32_t n
   if (!h || n_frames < 0 || n_match < 0 || !intr) return BA_ERR_INVALID;
   if (n_frames == 0) return BA_OK;
   if (!R || !t || !frame_offsets || (n_match > 0 && (!X || !uv))) return BA_ERR_INVALID;
-  CK(cudaSetDevice(h->device));
+  DeviceGuard dev_guard(h->device);
   cudaStream_t s = h->stream;
   const int mi = h->prm.max_iter;
   int rc;
@@ -808,7 +856,7 @@ extern "C" int ba_dist_init(ba_handle* h, const void* id, int32_t rank, int32_t 
   if (!h || !id || world < 1 || rank < 0 || rank >= world) return BA_ERR_INVALID;
   if (world == 1) { h->rank = 0; h->world = 1; return BA_OK; }
   if (!load_nccl()) { h->err = "libnccl.so.2 not found"; return BA_ERR_NCCL; }
-  CK(cudaSetDevice(h->device));
+  DeviceGuard dev_guard(h->device);
   nccl_uid uid;
   memcpy(&uid, id, sizeof(uid));
   int r = g_nccl.init_rank(&h->comm, world, uid, rank);

@@ -21,7 +21,7 @@ struct Work {
   double* b;                          // [n]
   double* diagU;                      // [n]   diag of the un-damped pose blocks
   double* cost_lin;                   // [1]   cost at the linearisation point (same buffer as S)
-  double* cost_cand;                  // [1]
+  double* cost_cand;                  // [2]   candidate cost; [1] = solve-failed flag of this rank (sharded runs)
   double* dp;                         // [n]   camera step
   LmCtl* ctl;
   int world;                          // > 1: accept/reject runs as its own kernel after the all-reduce
@@ -110,6 +110,7 @@ int configure_band();
 int band_max_w();
 int launch_backsub(const Work& w, int sm_count, cudaStream_t s);
 int launch_accept(const Work& w, cudaStream_t s);
+int launch_cost0(const Work& w, cudaStream_t s);   // max_iter == 0: cost_cand -> cost_hist[0]
 int launch_finalize(const Work& w, double* R_out, double* t_out, double* X_out,
                     unsigned char* flags, cudaStream_t s);
 int launch_expand_obs_pt(const int* pt_off, int n_pt, int* obs_pt, cudaStream_t s);   // CSR offsets -> point of every observation

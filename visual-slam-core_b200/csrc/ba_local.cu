@@ -73,8 +73,31 @@ __global__ void k_init(Work w, const double* __restrict__ R_in, const double* __
     c->n_accepted = 0;
     c->ticket = 0u;
     c->pcg_iters_last = 0;
-    *w.cost_cand = 0.0;
+    w.cost_cand[0] = 0.0;
+    w.cost_cand[1] = 0.0;
   }
+  // histories start clean: a report of a solve with fewer iterations than the last one must not show stale entries
+  if (blockIdx.x == 0) {
+    LmCtl* c = w.ctl;
+    for (int i = threadIdx.x; i < 65; i += blockDim.x) c->cost_hist[i] = 0.0;
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+      c->cand_hist[i] = 0.0; c->lambda_hist[i] = 0.0; c->solve_fail_hist[i] = 0; c->pcg_iters_hist[i] = 0; c->accepted[i] = 0;
+    }
+  }
+}
+
+// max_iter == 0: nothing linearises, so the initial cost of the report comes from a plain evaluation
+__global__ void k_cost0(Work w) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const double c = w.cost_cand[0];
+    w.ctl->cost_hist[0] = c;
+    w.ctl->cost_cur = c;
+    w.cost_cand[0] = 0.0;
+  }
+}
+int launch_cost0(const Work& w, cudaStream_t s) {
+  k_cost0<<<1, 32, 0, s>>>(w);
+  return 1;
 }
 
 int launch_init(const Work& w, const double* R_in, const double* t_in, const double* X_in,
@@ -715,6 +738,9 @@ k_backsub(Work w) {
 #pragma unroll
     for (int i = 0; i < kWarps; ++i) c += s_cost[i];
     atomicAdd(w.cost_cand, c);
+    // sharded: a failed solve on ANY rank must reject the step on every rank, so the flag travels with the
+    // candidate cost through the all-reduce (sum > 0 = failed somewhere)
+    if (w.world > 1 && blockIdx.x == 0) w.cost_cand[1] = (ctl->solve_fail != 0) ? 1.0 : 0.0;
     // the LM state the decision needs does not change during this kernel: requested now, so that the last CTA
     // has it by the time its ticket comes back
     const LmIn in = lm_load(ctl);
@@ -787,9 +813,11 @@ int launch_expand_obs_pt(const int* pt_off, int n_pt, int* obs_pt, cudaStream_t 
 // accept / reject as its own kernel (multi-GPU: runs after the candidate-cost all-reduce)
 __global__ void k_accept(Work w) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    const LmIn in = lm_load(w.ctl);
-    const double cand = *w.cost_cand;
-    *w.cost_cand = 0.0;
+    LmIn in = lm_load(w.ctl);
+    const double cand = w.cost_cand[0];
+    if (w.cost_cand[1] != 0.0) in.solve_fail = 1;          // some rank's solve failed: every rank rejects
+    w.cost_cand[0] = 0.0;
+    w.cost_cand[1] = 0.0;
     lm_accept(w.ctl, in, cand);
   }
 }

@@ -174,10 +174,114 @@ fail:
   return NULL;
 }
 
+
+/* gather_points(map_points) -> (positions f64[n*3], keys i64[n]) as bytes, or None when a position is not three numbers.
+ * key = mp.id when the point has one (the reference's global counter, map/map_point.py:22-24), else the object identity. */
+static PyObject* gather_points(PyObject* self, PyObject* args) {
+  PyObject* map_points;
+  if (!PyArg_ParseTuple(args, "O", &map_points)) return NULL;
+  if (!PyList_CheckExact(map_points)) Py_RETURN_NONE;
+  static PyObject *s_pos = NULL, *s_id = NULL;
+  if (!s_pos) s_pos = PyUnicode_InternFromString("position");
+  if (!s_id) s_id = PyUnicode_InternFromString("id");
+  if (!s_pos || !s_id) return NULL;
+  const Py_ssize_t n = PyList_GET_SIZE(map_points);
+  PyObject* pos_b = PyBytes_FromStringAndSize(NULL, (Py_ssize_t)(n * 3 * sizeof(double)));
+  PyObject* key_b = PyBytes_FromStringAndSize(NULL, (Py_ssize_t)(n * sizeof(int64_t)));
+  if (!pos_b || !key_b) { Py_XDECREF(pos_b); Py_XDECREF(key_b); return NULL; }
+  double* X = (double*)PyBytes_AS_STRING(pos_b);
+  int64_t* keys = (int64_t*)PyBytes_AS_STRING(key_b);
+  int unsupported = 0;
+  for (Py_ssize_t j = 0; j < n; ++j) {
+    PyObject* mp = PyList_GET_ITEM(map_points, j);
+    PyObject* pos = PyObject_GetAttr(mp, s_pos);
+    if (!pos) goto fail;
+    int done = 0;
+    Py_buffer view;
+    if (PyObject_CheckBuffer(pos) && PyObject_GetBuffer(pos, &view, PyBUF_FORMAT | PyBUF_C_CONTIGUOUS) == 0) {
+      if (view.format && view.format[0] == 'd' && view.format[1] == 0 && view.len == 3 * (Py_ssize_t)sizeof(double)) {
+        memcpy(X + 3 * j, view.buf, 3 * sizeof(double));
+        done = 1;
+      } else if (view.format && view.format[0] == 'f' && view.format[1] == 0 && view.len == 3 * (Py_ssize_t)sizeof(float)) {
+        const float* f = (const float*)view.buf;
+        X[3 * j] = f[0]; X[3 * j + 1] = f[1]; X[3 * j + 2] = f[2];
+        done = 1;
+      }
+      PyBuffer_Release(&view);
+    } else {
+      PyErr_Clear();
+    }
+    if (!done) {
+      /* any flat sequence of three numbers */
+      if (PySequence_Check(pos) && PySequence_Size(pos) == 3) {
+        done = 1;
+        for (int c = 0; c < 3; ++c) {
+          PyObject* it = PySequence_GetItem(pos, c);
+          if (!it) { Py_DECREF(pos); goto fail; }
+          const double v = PyFloat_AsDouble(it);
+          Py_DECREF(it);
+          if (v == -1.0 && PyErr_Occurred()) { PyErr_Clear(); done = 0; break; }
+          X[3 * j + c] = v;
+        }
+      } else {
+        PyErr_Clear();
+      }
+    }
+    Py_DECREF(pos);
+    if (!done) { unsupported = 1; break; }
+    PyObject* ido = PyObject_GetAttr(mp, s_id);
+    if (ido) {
+      const long long k = PyLong_AsLongLong(ido);
+      Py_DECREF(ido);
+      if (k == -1 && PyErr_Occurred()) { PyErr_Clear(); keys[j] = (int64_t)(intptr_t)mp; }
+      else keys[j] = (int64_t)k;
+    } else {
+      PyErr_Clear();
+      keys[j] = (int64_t)(intptr_t)mp;                 /* id(mp) */
+    }
+  }
+  if (unsupported) { Py_DECREF(pos_b); Py_DECREF(key_b); Py_RETURN_NONE; }
+  {
+    PyObject* out = PyTuple_Pack(2, pos_b, key_b);
+    Py_DECREF(pos_b);
+    Py_DECREF(key_b);
+    return out;
+  }
+fail:
+  Py_DECREF(pos_b);
+  Py_DECREF(key_b);
+  return NULL;
+}
+
+/* scatter_points(map_points, X) -> True: mp.update_position(X[j]) for every point, X any sequence of rows
+ * (a C-contiguous (n,3) float64 numpy array hands out row views).  The write-back of torch_optimizer.py:201-203. */
+static PyObject* scatter_points(PyObject* self, PyObject* args) {
+  PyObject *map_points, *X;
+  if (!PyArg_ParseTuple(args, "OO", &map_points, &X)) return NULL;
+  if (!PyList_CheckExact(map_points) || !PySequence_Check(X)) Py_RETURN_FALSE;
+  static PyObject* s_upd = NULL;
+  if (!s_upd) s_upd = PyUnicode_InternFromString("update_position");
+  if (!s_upd) return NULL;
+  const Py_ssize_t n = PyList_GET_SIZE(map_points);
+  if (PySequence_Size(X) < n) { PyErr_SetString(PyExc_ValueError, "fewer rows than points"); return NULL; }
+  for (Py_ssize_t j = 0; j < n; ++j) {
+    PyObject* row = PySequence_GetItem(X, j);
+    if (!row) return NULL;
+    PyObject* r = PyObject_CallMethodOneArg(PyList_GET_ITEM(map_points, j), s_upd, row);
+    Py_DECREF(row);
+    if (!r) return NULL;
+    Py_DECREF(r);
+  }
+  Py_RETURN_TRUE;
+}
+
 static PyMethodDef methods[] = {
     {"pack_observations", pack_observations, METH_VARARGS,
      "pack_observations(map_points, pose_index, keypoints_of) -> (cam i32, cam_id i32, uv f32, counts i64) bytes, "
      "or None when a container is not an exact dict / list"},
+    {"gather_points", gather_points, METH_VARARGS,
+     "gather_points(map_points) -> (positions f64 bytes, keys i64 bytes), or None when a position is not three numbers"},
+    {"scatter_points", scatter_points, METH_VARARGS, "scatter_points(map_points, X) -> True after mp.update_position(X[j]) for all j"},
     {NULL, NULL, 0, NULL}};
 
 static struct PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_fastpack", "window packer inner loop", -1, methods};

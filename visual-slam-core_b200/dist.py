@@ -44,6 +44,31 @@ def init_solver(solver, rank: int, world: int, group=None, device=None) -> None:
     solver.dist_init(uid, rank, world)
 
 
+def shard_point_range(pt_offsets: np.ndarray, rank: int, world: int):
+    """Point range [lo, hi) of `rank`: the CSR over observations cut at equal observation counts, so every
+    shard carries the same linearisation work."""
+    n_pt = len(pt_offsets) - 1
+    n_obs = int(pt_offsets[-1])
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(pt_offsets, (n_obs * r) // world, side="left")))
+    cuts.append(n_pt)
+    cuts = np.maximum.accumulate(np.clip(cuts, 0, n_pt))
+    return int(cuts[rank]), int(cuts[rank + 1])
+
+
+def gather_flags(flags_local: np.ndarray, obs_range, n_obs: int, group=None) -> np.ndarray:
+    """All-gather the per-rank outlier flags into the full (n_obs,) array (host side, any backend)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    objs = [None] * world
+    dist.all_gather_object(objs, (int(obs_range[0]), int(obs_range[1]), np.asarray(flags_local)), group=group)
+    out = np.zeros(n_obs, dtype=np.uint8)
+    for lo, hi, f in objs:
+        out[lo:hi] = f
+    return out
+
+
 def gather_points(X_local: np.ndarray, pt_range, n_pt: int, group=None) -> Optional[np.ndarray]:
     """All-gather the per-rank point blocks into the full (n_pt, 3) array (host side, any backend)."""
     import torch

@@ -93,14 +93,39 @@ class B200Optimizer(BaseOptimizer):
         self.last_result: Optional[SolveResult] = None
         self.last_packed: Optional[packing.PackedWindow] = None
         self.mark_bad_points = bool(getattr(getattr(config, "optimization", None), "mark_bad_points", False))
-        # optional incremental SoA mirror of the observation graph (packing.ObservationTable):
-        # when set, windows are packed from it instead of walking the object graph
+        # incremental SoA mirror of the observation graph (packing.ObservationTable): windows are
+        # packed from it instead of walking the object graph.  On by default (`config.optimization.observation_table
+        # = False` turns it off); the hooks go onto the map-point class on the first call; whatever the table cannot
+        # represent falls back to the reference's walk (`packing.pack_window`).
+        self.use_table = bool(getattr(getattr(config, "optimization", None), "observation_table", True))
         self.table: Optional[packing.ObservationTable] = None
+        self.packer_name = "pack_window"
+        # sharded global BA: set by `enable_sharding` or picked up from torch.distributed
+        self._dist = None                      # (rank, world, group)
 
     def _get_solver(self) -> LocalBASolver:
         if self._solver is None:
             self._solver = LocalBASolver(self._lm, device=self._dev_index)   # raises without a GPU
         return self._solver
+
+    def pack(self, keyframes: List[Any], map_points: List[Any]) -> packing.PackedWindow:
+        """Snapshot of the window as structure-of-arrays (`torch_optimizer.py:43-95`): from the observation table
+        when it can represent the window, by the reference's walk otherwise.  Same arrays either way."""
+        if self.use_table and map_points:
+            try:
+                if self.table is None:
+                    self.table = packing.shared_table()
+                cls = type(map_points[0])
+                if hasattr(cls, "add_observation") and not self.table.installed_on(cls):
+                    self.table.install(cls)
+                pw = self.table.pack(keyframes, map_points)
+                if pw is not None:
+                    self.packer_name = "ObservationTable"
+                    return pw
+            except Exception as e:             # never costs the solve: the walk is always there
+                self.logger.warning(f"[B200Optimizer] observation table unavailable ({e!r}); walking the graph.")
+        self.packer_name = "pack_window"
+        return packing.pack_window(keyframes, map_points)
 
     # ------------------------------------------------------------------------------ local BA
     def optimize_local(self, keyframes: List[Any], map_points: List[Any]) -> bool:
@@ -108,10 +133,7 @@ class B200Optimizer(BaseOptimizer):
             self.logger.info(f"[B200Optimizer] keyframes - {len(keyframes)}, points - {len(map_points)}.")
             if not keyframes:
                 return False
-            if self.table is not None:
-                pw = self.table.pack(keyframes, map_points)
-            else:
-                pw = packing.pack_window(keyframes, map_points)  # snapshot up front, as :46-95
+            pw = self.pack(keyframes, map_points)               # snapshot up front, as :46-95
             self.logger.info(f"[B200Optimizer] observations - {pw.n_obs}.")
             if pw.n_obs < packing.MIN_OBSERVATIONS:              # :99-101: False, nothing mutated
                 self.logger.warning("[B200Optimizer] too few observations for local optimisation.")
@@ -151,9 +173,66 @@ class B200Optimizer(BaseOptimizer):
         return None if self.last_result is None else self.last_result.flags
 
     # ------------------------------------------------------------------------------ global / initial
+    def enable_sharding(self, rank: int, world: int, group=None) -> None:
+        """Global BA sharded by map point over `world` processes, one GPU each.  Every
+        process calls `optimize_global` with the same keyframes and map points; `torch.distributed` only carries
+        the NCCL id and the refined points of the other shards."""
+        self._dist = (int(rank), int(world), group)
+
+    def _dist_state(self):
+        if self._dist is not None:
+            return self._dist
+        try:
+            import torch.distributed as td
+            if td.is_available() and td.is_initialized() and td.get_world_size() > 1:
+                return (td.get_rank(), td.get_world_size(), None)
+        except Exception:
+            pass
+        return None
+
     def optimize_global(self, keyframes: List[Any], map_points: List[Any]) -> bool:
-        """Same solver over every keyframe (the reference's is an empty stub, torch_optimizer.py:319-320)."""
-        return self.optimize_local(keyframes, map_points)
+        """Global BA: the same LM solver over every keyframe (the reference's is an empty stub,
+        `torch_optimizer.py:319-320`, reached from `Map.optimize_global`, `map/map.py:173-178`).  In a
+        `torch.distributed` job of more than one process the window is sharded by map point: every rank solves
+        its contiguous point range (balanced by observation count) with the cameras replicated, the reduced
+        camera system and the costs are NCCL all-reduced inside the CUDA library, and the refined points of all
+        shards are gathered before the write-back, so every process ends with the same map."""
+        st = self._dist_state()
+        if st is None or st[1] <= 1:
+            return self.optimize_local(keyframes, map_points)
+        rank, world, group = st
+        try:
+            from . import dist as badist
+            if not keyframes:
+                return False
+            pw = self.pack(keyframes, map_points)
+            if pw.n_obs < packing.MIN_OBSERVATIONS:
+                self.logger.warning("[B200Optimizer] too few observations for global optimisation.")
+                return False
+            lo, hi = badist.shard_point_range(pw.pt_offsets, rank, world)
+            o0, o1 = int(pw.pt_offsets[lo]), int(pw.pt_offsets[hi])
+            with self._lock:
+                solver = self._get_solver()
+                if getattr(solver, "_world", 1) != world:
+                    badist.init_solver(solver, rank, world, group=group, device=f"cuda:{self._dev_index}")
+                    solver._world = world
+                res = solver.solve_local(pw.intr, pw.R, pw.t, pw.fixed, pw.X[lo:hi], pw.obs_cam[o0:o1],
+                                         pw.obs_pt[o0:o1] - lo, pw.obs_uv[o0:o1], pw.pt_offsets[lo:hi + 1] - o0)
+            X = badist.gather_points(res.X, (lo, hi), pw.X.shape[0], group=group)
+            flags = badist.gather_flags(res.flags, (o0, o1), pw.n_obs, group=group)
+            if not (np.isfinite(res.R).all() and np.isfinite(res.t).all() and np.isfinite(X).all()):
+                self.logger.error("[B200Optimizer] non-finite result; nothing written back.")
+                return False
+            for i in range(res.n_iter):
+                self.logger.info(f"[Global BA] iter={i}, loss={res.cost_hist[i + 1]:.3f}, lambda={res.lambda_hist[i]:.1e}, "
+                                 f"accepted={int(res.accepted[i])}, shard={rank}/{world}")
+            packing.write_back(keyframes, map_points, res.R, res.t, X)
+            self.last_result = dataclasses.replace(res, X=X, flags=flags)
+            self.last_packed = pw
+            return True
+        except Exception as e:
+            self.logger.error(f"[B200Optimizer] optimize_global (sharded) failed: {e!r}")
+            return False
 
     def optimize_initial(self, keyframes: List[Any], map_points: List[Any]) -> bool:
         """Two-view refinement (reference: torch_optimizer.py:209-317) on the LM solver.
@@ -207,23 +286,30 @@ class B200Optimizer(BaseOptimizer):
         """What the stub `LocalHandler.cull_bad_points` (`handlers/local_handler.py:79-80`) was waiting
         for: drop the observations flagged by the last `optimize_local` over the same window
         (`KeyFrame.remove_map_point`, `map/keyframe.py:93-100`, which also removes the point's
-        observation) and `mark_as_bad()` (`map/map_point.py:75-78`) the points left with fewer than
-        `min_observations` in-window observations.  Returns the number of points marked bad."""
+        observation) and `mark_as_bad()` (`map/map_point.py:75-78`) the points that lost an observation here
+        and are left with fewer than `min_observations` observations in the whole map.  Returns the number of
+        points marked bad."""
         res, pw = self.last_result, self.last_packed
         if res is None or pw is None or res.flags is None or len(map_points) != pw.X.shape[0] \
                 or len(keyframes) != pw.R.shape[0] or pw.obs_cam_id.shape[0] != res.flags.shape[0]:
             return 0
         flagged = np.flatnonzero(res.flags)
+        touched = set()
         for o in flagged:
-            kf, mp, cam_id = keyframes[int(pw.obs_cam[o])], map_points[int(pw.obs_pt[o])], int(pw.obs_cam_id[o])
+            j = int(pw.obs_pt[o])
+            kf, mp, cam_id = keyframes[int(pw.obs_cam[o])], map_points[j], int(pw.obs_cam_id[o])
             ob = mp.get_observations().get(kf.keyframe_id, {})
             if cam_id in ob and hasattr(kf, "remove_map_point"):
                 kf.remove_map_point(cam_id, ob[cam_id])
-        left = np.bincount(pw.obs_pt, weights=(res.flags == 0).astype(np.float64), minlength=len(map_points))
-        had = np.diff(pw.pt_offsets)
+                touched.add(j)
+        # only points that LOST an observation in this call can starve, and what counts is everything the point
+        # still has in the map (keyframes outside the window included), not its in-window share
         n_bad = 0
-        for j in np.flatnonzero((had > 0) & (left < min_observations)):
-            map_points[int(j)].mark_as_bad()
-            n_bad += 1
+        for j in sorted(touched):
+            mp = map_points[j]
+            left = sum(len(cams) for cams in mp.get_observations().values())
+            if left < min_observations:
+                mp.mark_as_bad()
+                n_bad += 1
         self.logger.info(f"[B200Optimizer] culled {len(flagged)} observations, marked {n_bad} points bad.")
         return n_bad

@@ -16,8 +16,9 @@ The outer loop is over points, so the list is already sorted by point: `pt_offse
 from __future__ import annotations
 
 import operator
+import threading
 from dataclasses import dataclass
-from typing import Any, List
+from typing import Any, List, Optional
 
 import numpy as np
 
@@ -148,8 +149,7 @@ def write_back(keyframes: List[Any], map_points: List[Any], R: np.ndarray, t: np
     (the fixed one included) gets `set_pose_Rt(R 3x3, t 3x1)`, every point `update_position`."""
     for i, kf in enumerate(keyframes):
         kf.set_pose_Rt(np.array(R[i], dtype=np.float64), np.array(t[i], dtype=np.float64).reshape(3, 1))
-    for mp, pos in zip(map_points, X):
-        mp.update_position(np.asarray(pos))
+    write_back_points(map_points, X)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -225,30 +225,71 @@ def _stable_order_by(keys: np.ndarray, n_keys: int) -> np.ndarray:
     return np.argsort(keys, kind="stable")
 
 
-class ObservationTable:
-    """Append-only SoA mirror of `KeyFrame.add_map_point` / `MapPoint.add_observation`
-    (`map/keyframe.py:82-86`, `map/map_point.py:37-39`): one row (keyframe_id, point id, cam_id,
-    kp_idx, u, v) per recorded observation, in insertion order.
+def gather_points(map_points: List[Any]):
+    """Positions (n,3) float64 and integer keys (`mp.id`, else the object identity) of a list of map points:
+    one C loop when the extension is built, a comprehension otherwise."""
+    n_pt = len(map_points)
+    if n_pt == 0:
+        return np.zeros((0, 3), dtype=np.float64), np.zeros(0, dtype=np.int64)
+    if _fastpack is not None and hasattr(_fastpack, "gather_points") and isinstance(map_points, list):
+        out = _fastpack.gather_points(map_points)
+        if out is not None:
+            return (np.frombuffer(out[0], dtype=np.float64).reshape(n_pt, 3),
+                    np.frombuffer(out[1], dtype=np.int64))
+    try:
+        X = np.concatenate([mp.position for mp in map_points]).astype(np.float64).reshape(n_pt, 3)
+    except ValueError:                                  # a position that is not a flat array of three
+        X = np.array([mp.position for mp in map_points], dtype=np.float64).reshape(n_pt, 3)
+    try:
+        keys = np.fromiter(map(_ID_OF, map_points), dtype=np.int64, count=n_pt)
+    except AttributeError:                              # points without an `id`: the object identity is the key
+        keys = np.fromiter((ObservationTable.point_key(mp) for mp in map_points), dtype=np.int64, count=n_pt)
+    return X, keys
 
-    With it `pack()` builds the same `PackedWindow` as `pack_window` with numpy selections and one
-    stable sort instead of a Python loop over every observation (~1-2 us each, which is > 99 % of
-    `optimize_local`'s wall time once the solve takes a millisecond).  The table follows the
-    reference's first-write-wins rule (`map/observation.py:10-22`): a second (keyframe, cam_id)
-    observation of the same point is ignored.  Removals (`KeyFrame.remove_map_point`,
-    `map/keyframe.py:93-100`) tombstone the row.
+
+def write_back_points(map_points: List[Any], X: np.ndarray) -> None:
+    """`mp.update_position(X[j])` for every point (`torch_optimizer.py:201-203`), the loop in C when it can be."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    if _fastpack is not None and hasattr(_fastpack, "scatter_points") and isinstance(map_points, list):
+        if _fastpack.scatter_points(map_points, X):
+            return
+    for mp, pos in zip(map_points, X):
+        mp.update_position(pos)
+
+
+class ObservationTable:
+    """Append-only SoA mirror of the map's observation dictionaries: one row (point key, keyframe_id, cam_id,
+    kp_idx) per `MapPoint.add_observation` (`map/map_point.py:37-39`, reached from `KeyFrame.add_map_point`,
+    `map/keyframe.py:82-86`), in insertion order; `remove_observation` / `clear_observations` tombstone rows.
+    Pixels are not stored per row: each keyframe's keypoints are mirrored ONCE as a float32 (N_kp, 2) array per
+    sensor (they do not change after the keyframe is created) and gathered at pack time.
+
+    `pack()` then builds the same `PackedWindow` as `pack_window` -- array for array, order and skip rules of
+    `torch_optimizer.py:74-95` included -- with numpy selections and one stable counting sort instead of a Python
+    loop over every observation (~1-2 us each, > 90 % of `optimize_local`'s wall time once the solve takes a
+    millisecond).
+
+    A point is mirrored either from its first observation on (hook) or, if it existed before the hooks were
+    installed, by one walk over its own dictionary the first time a window contains it (`ingest`).  Anything
+    the table cannot represent (a point handed in twice, a container it does not know) makes `pack()` return
+    None and the caller falls back to `pack_window`.  All entry points take the table's lock: the map is mutated
+    from the tracking / local-mapping threads while `pack()` runs in the local-BA thread.
     """
 
     def __init__(self, capacity: int = 1 << 16):
+        self._lock = threading.RLock()
         self._n = 0
         self._kf = np.empty(capacity, dtype=np.int64)
         self._mp = np.empty(capacity, dtype=np.int64)
         self._cam = np.empty(capacity, dtype=np.int32)
-        self._kp = np.empty(capacity, dtype=np.int32)
-        self._uv = np.empty((capacity, 2), dtype=np.float32)
+        self._kp = np.empty(capacity, dtype=np.int64)
         self._alive = np.empty(capacity, dtype=bool)
-        self._grp = np.empty(capacity, dtype=np.int64)   # row of the first observation of the same (keyframe, point)
-        self._seen = {}          # (kf_id, point key, cam_id) -> row
-        self._first = {}         # (kf_id, point key) -> first row (the reference groups a point's observations by keyframe)
+        self._grp = np.empty(capacity, dtype=np.int64)   # row of the first live observation of the same (point, keyframe)
+        self._pairs = {}         # (point key, kf_id) -> [first row, {cam_id: row}]   live observations only
+        self._known = set()      # point keys whose dictionaries are mirrored in full
+        self._kp_cache = {}      # kf_id -> (tuple of sensor lengths, [float32 (N,2) per sensor])
+        self._hooks = []
+        self.stats = {"ingested_points": 0, "packs": 0, "fallbacks": 0}
 
     def __len__(self) -> int:
         return self._n
@@ -258,45 +299,134 @@ class ObservationTable:
         return int(getattr(mp, "id", id(mp)))
 
     def _grow(self):
-        for name in ("_kf", "_mp", "_cam", "_kp", "_uv", "_alive", "_grp"):
+        for name in ("_kf", "_mp", "_cam", "_kp", "_alive", "_grp"):
             a = getattr(self, name)
             b = np.empty((2 * a.shape[0],) + a.shape[1:], dtype=a.dtype)
             b[: self._n] = a[: self._n]
             setattr(self, name, b)
 
-    def add(self, kf, cam_id: int, kp_idx: int, mp) -> bool:
-        key = (int(kf.keyframe_id), self.point_key(mp), int(cam_id))
-        if key in self._seen:
-            return False
+    # ----------------------------------------------------------------------------- rows
+    def _add_row(self, pt: int, kf_id: int, cam_id: int, kp_idx: int) -> bool:
+        pair = self._pairs.get((pt, kf_id))
+        if pair is not None and cam_id in pair[1]:
+            return False                                  # first write wins (map/observation.py:10-22)
         if self._n == self._kf.shape[0]:
             self._grow()
         i = self._n
-        kps = kf.keypoints
-        in_range = cam_id < len(kps) and kp_idx < len(kps[cam_id])
-        self._kf[i], self._mp[i], self._cam[i], self._kp[i] = key[0], key[1], cam_id, kp_idx
-        self._uv[i] = kps[cam_id][kp_idx].pt if in_range else (np.nan, np.nan)
-        self._alive[i] = in_range        # out-of-range entries are skipped by the reference's packer (:90-93)
-        self._grp[i] = self._first.setdefault(key[:2], i)
-        self._seen[key] = i
+        self._kf[i], self._mp[i], self._cam[i], self._kp[i] = kf_id, pt, cam_id, kp_idx
+        self._alive[i] = True
+        if pair is None:
+            self._pairs[(pt, kf_id)] = [i, {cam_id: i}]
+            self._grp[i] = i
+        else:
+            pair[1][cam_id] = i
+            self._grp[i] = pair[0]
         self._n += 1
         return True
 
-    def remove(self, kf, cam_id: int, mp) -> None:
-        row = self._seen.pop((int(kf.keyframe_id), self.point_key(mp), int(cam_id)), None)
+    def _remove_rows(self, pt: int, kf_id: int, cam_id) -> None:
+        pair = self._pairs.get((pt, kf_id))
+        if pair is None:
+            return
+        if cam_id is None:                                # the whole keyframe entry goes (map/observation.py:36-38)
+            for row in pair[1].values():
+                self._alive[row] = False
+            del self._pairs[(pt, kf_id)]
+            return
+        row = pair[1].pop(cam_id, None)
         if row is not None:
             self._alive[row] = False
+            if not pair[1]:                               # a later re-add starts a new dictionary entry, at the end
+                del self._pairs[(pt, kf_id)]
 
-    def install(self, keyframe_cls) -> None:
-        """Hook `keyframe_cls.add_map_point` / `remove_map_point` so the table follows the map."""
+    def add(self, kf, cam_id: int, kp_idx: int, mp) -> bool:
+        """Record one observation by hand (what the hooks do); marks the point as mirrored."""
+        with self._lock:
+            pt = self.point_key(mp)
+            self._known.add(pt)
+            return self._add_row(pt, int(kf.keyframe_id), int(cam_id), int(kp_idx))
+
+    def remove(self, kf, cam_id, mp) -> None:
+        with self._lock:
+            self._remove_rows(self.point_key(mp), int(kf.keyframe_id), None if cam_id is None else int(cam_id))
+
+    def ingest(self, mp) -> None:
+        """Mirror a point that existed before the hooks: one walk over its own dictionary, in its order."""
+        with self._lock:
+            pt = self.point_key(mp)
+            if pt in self._known:
+                return
+            for kf_id, cams in mp.get_observations().items():
+                for cam_id, kp_idx in cams.items():
+                    self._add_row(pt, int(kf_id), int(cam_id), int(kp_idx))
+            self._known.add(pt)
+            self.stats["ingested_points"] += 1
+
+    def _forget(self, pt: int) -> None:
+        n = self._n
+        self._alive[:n][self._mp[:n] == pt] = False
+        for key in [k for k in self._pairs if k[0] == pt]:
+            del self._pairs[key]
+
+    # ----------------------------------------------------------------------------- hooks
+    def _on_add(self, mp, kf_id, cam_id, kp_idx, n_before: int) -> None:
+        with self._lock:
+            pt = self.point_key(mp)
+            if pt not in self._known:
+                if n_before != 0:
+                    return                                # older point, not mirrored yet: `ingest` will take all of it
+                self._known.add(pt)
+            self._add_row(pt, int(kf_id), int(cam_id), int(kp_idx))
+
+    def install(self, cls) -> None:
+        """Hook a MapPoint class (`add_observation` / `remove_observation` / `clear_observations`) so the table
+        follows the map.  A KeyFrame class may be given instead (older call sites): its `add_map_point` /
+        `remove_map_point` are hooked, which covers a map that is only ever changed through them."""
         table = self
-        orig_add = keyframe_cls.add_map_point
-        orig_remove = getattr(keyframe_cls, "remove_map_point", None)
+        if hasattr(cls, "add_observation"):
+            orig_add = cls.add_observation
+            orig_remove = getattr(cls, "remove_observation", None)
+            orig_clear = getattr(cls, "clear_observations", None)
+
+            def add_observation(mp, kf_idx, cam_id, kp_idx):
+                n_before = table._n_observations(mp)
+                ok = orig_add(mp, kf_idx, cam_id, kp_idx)
+                if ok or ok is None:
+                    table._on_add(mp, kf_idx, cam_id, kp_idx, n_before)
+                return ok
+
+            cls.add_observation = add_observation
+            restore = [("add_observation", orig_add)]
+            if orig_remove is not None:
+                def remove_observation(mp, kf_id, cam_id=None):
+                    out = orig_remove(mp, kf_id, cam_id)
+                    with table._lock:
+                        table._remove_rows(table.point_key(mp), int(kf_id), None if cam_id is None else int(cam_id))
+                    return out
+
+                cls.remove_observation = remove_observation
+                restore.append(("remove_observation", orig_remove))
+            if orig_clear is not None:
+                def clear_observations(mp):
+                    out = orig_clear(mp)
+                    with table._lock:
+                        table._forget(table.point_key(mp))
+                    return out
+
+                cls.clear_observations = clear_observations
+                restore.append(("clear_observations", orig_clear))
+            self._hooks.append((cls, restore))
+            return
+        orig_add = cls.add_map_point
+        orig_remove = getattr(cls, "remove_map_point", None)
 
         def add_map_point(kf, cam_id, kp_idx, map_point):
+            n_before = table._n_observations(map_point)
             orig_add(kf, cam_id, kp_idx, map_point)
-            table.add(kf, cam_id, kp_idx, map_point)
+            table._on_add(map_point, kf.keyframe_id, cam_id, kp_idx, n_before)
 
-        keyframe_cls.add_map_point = add_map_point
+        cls.add_map_point = add_map_point
+        restore = [("add_map_point", orig_add)]
         if orig_remove is not None:
             def remove_map_point(kf, cam_id, kp_idx):
                 mp = kf.map_points.get((cam_id, kp_idx)) if hasattr(kf, "map_points") else None
@@ -304,15 +434,30 @@ class ObservationTable:
                 if mp is not None:
                     table.remove(kf, cam_id, mp)
 
-            keyframe_cls.remove_map_point = remove_map_point
-        self._uninstall = (keyframe_cls, orig_add, orig_remove)
+            cls.remove_map_point = remove_map_point
+            restore.append(("remove_map_point", orig_remove))
+        self._hooks.append((cls, restore))
+
+    @staticmethod
+    def _n_observations(mp) -> int:
+        try:
+            f = getattr(mp, "num_observations", None)
+            if f is not None:
+                return int(f())
+            return len(mp.get_observations())
+        except Exception:
+            return 1                                      # unknown: treat as an older point, `ingest` decides
+
+    def installed_on(self, cls) -> bool:
+        return any(c is cls for c, _ in self._hooks)
 
     def uninstall(self) -> None:
-        cls, orig_add, orig_remove = self._uninstall
-        cls.add_map_point = orig_add
-        if orig_remove is not None:
-            cls.remove_map_point = orig_remove
+        for cls, restore in reversed(self._hooks):
+            for name, orig in restore:
+                setattr(cls, name, orig)
+        self._hooks = []
 
+    # ----------------------------------------------------------------------------- pack
     @staticmethod
     def _lookup(window_keys: np.ndarray, row_keys: np.ndarray, last_wins: bool) -> np.ndarray:
         """Window position of every table row's key (int32, -1: not in the window)."""
@@ -340,54 +485,119 @@ class ObservationTable:
         out[ok] = order[pos[ok]]
         return out
 
-    def pack(self, keyframes: List[Any], map_points: List[Any]) -> PackedWindow:
-        """Same result as `pack_window(keyframes, map_points)` for a graph that was built through the
-        hooked `add_map_point` (observation order inside a point = insertion order, as
-        `mp.get_observations()` yields it)."""
-        kf_fixed = keyframes[0]
-        K = np.asarray(kf_fixed._camera.K, dtype=np.float32)
-        intr = np.array([K[0, 0], K[1, 1], K[0, 2], K[1, 2]], dtype=np.float64)
-        n_cam, n_pt = len(keyframes), len(map_points)
-        R = np.empty((n_cam, 3, 3), dtype=np.float64)
-        t = np.empty((n_cam, 3), dtype=np.float64)
-        fixed = np.zeros(n_cam, dtype=np.uint8)
-        kf_ids = np.empty(n_cam, dtype=np.int64)
-        for i, kf in enumerate(keyframes):
-            R[i] = np.asarray(kf.R_w2c, dtype=np.float32)
-            t[i] = np.asarray(kf.t_w2c, dtype=np.float32).reshape(3)
-            fixed[i] = 1 if kf is kf_fixed else 0
-            kf_ids[i] = kf.keyframe_id
-        if n_pt:
-            try:                                        # positions are (3,) arrays: one concatenation, one rounding
-                X = np.concatenate([mp.position for mp in map_points]).astype(np.float32).astype(np.float64).reshape(n_pt, 3)
-            except ValueError:                          # a position that is not a flat array of three
-                X = np.array([mp.position for mp in map_points], dtype=np.float32).reshape(n_pt, 3).astype(np.float64)
-        else:
-            X = np.zeros((0, 3), dtype=np.float64)
-        try:
-            mp_keys = np.fromiter(map(_ID_OF, map_points), dtype=np.int64, count=n_pt)
-        except AttributeError:                          # points without an `id`: the object identity is the key
-            mp_keys = np.fromiter((self.point_key(mp) for mp in map_points), dtype=np.int64, count=n_pt)
+    def _keypoint_arrays(self, kf):
+        """float32 (N,2) pixel array per sensor of a keyframe, built once (keypoints do not change after the
+        keyframe is created; the cache is keyed by id and checked against the sensor lengths)."""
+        kps = kf.keypoints
+        lens = tuple(len(s) for s in kps)
+        hit = self._kp_cache.get(kf.keyframe_id)
+        if hit is not None and hit[0] == lens:
+            return hit[1]
+        arrs = []
+        for s in kps:
+            if len(s) == 0:
+                arrs.append(np.zeros((0, 2), dtype=np.float32))
+                continue
+            a = None
+            try:
+                import cv2
+                if isinstance(s[0], cv2.KeyPoint):
+                    a = cv2.KeyPoint_convert(list(s)).astype(np.float32).reshape(-1, 2)
+            except Exception:
+                a = None
+            if a is None:
+                a = np.array([kp.pt for kp in s], dtype=np.float32).reshape(-1, 2)
+            arrs.append(a)
+        self._kp_cache[kf.keyframe_id] = (lens, arrs)
+        if len(self._kp_cache) > 4096:                   # bounded: drop the oldest entries
+            for k in list(self._kp_cache)[:1024]:
+                del self._kp_cache[k]
+        return arrs
 
-        n = self._n
-        alive = self._alive[:n]
-        # key -> window row through a lookup table when the ids are small integers (the reference's global
-        # counters), through a sorted search otherwise (object identities)
-        cam_of = self._lookup(kf_ids, self._kf[:n], last_wins=True)      # a later duplicate id wins, as the dict at :61 does
-        pt_of = self._lookup(mp_keys, self._mp[:n], last_wins=False)
-        rows = np.flatnonzero(alive & (cam_of >= 0) & (pt_of >= 0))
-        cam_row, pt_row = cam_of[rows], pt_of[rows]
-        # group by point; inside a point by keyframe in first-insertion order, then by insertion (= the nested
-        # dict iteration of the reference's packing loop, :80-95).  Rows are in insertion order already, so
-        # when no (keyframe, point) pair was observed twice a stable counting sort by point is all it takes.
-        if np.array_equal(self._grp[rows], rows):
-            o = _stable_order_by(pt_row, n_pt)
-        else:
-            o = np.lexsort((rows, self._grp[rows], pt_row))
-        rows, cam_row, pt_row = rows[o], cam_row[o], pt_row[o]
-        pt_offsets = np.zeros(n_pt + 1, dtype=np.int32)
-        np.cumsum(np.bincount(pt_row, minlength=n_pt), out=pt_offsets[1:])
-        return PackedWindow(intr=intr, R=R, t=t, fixed=fixed, X=X,
-                            obs_cam=cam_row.astype(np.int32), obs_pt=pt_row.astype(np.int32),
-                            obs_uv=np.ascontiguousarray(self._uv[rows]),
-                            obs_cam_id=np.ascontiguousarray(self._cam[rows]), pt_offsets=pt_offsets)
+    def pack(self, keyframes: List[Any], map_points: List[Any]) -> Optional[PackedWindow]:
+        """Same result as `pack_window(keyframes, map_points)`, or None when the window has something the table
+        does not represent (a point listed twice) -- the caller then walks the graph."""
+        with self._lock:
+            self.stats["packs"] += 1
+            kf_fixed = keyframes[0]
+            K = np.asarray(kf_fixed._camera.K, dtype=np.float32)
+            intr = np.array([K[0, 0], K[1, 1], K[0, 2], K[1, 2]], dtype=np.float64)
+            n_cam, n_pt = len(keyframes), len(map_points)
+            R = np.empty((n_cam, 3, 3), dtype=np.float64)
+            t = np.empty((n_cam, 3), dtype=np.float64)
+            fixed = np.zeros(n_cam, dtype=np.uint8)
+            kf_ids = np.empty(n_cam, dtype=np.int64)
+            uv_parts, n_sens = [], np.zeros(n_cam, dtype=np.int64)
+            max_sens = max((len(kf.keypoints) for kf in keyframes), default=0)
+            base = np.zeros((n_cam, max(max_sens, 1)), dtype=np.int64)
+            count = np.zeros((n_cam, max(max_sens, 1)), dtype=np.int64)
+            at = 0
+            for i, kf in enumerate(keyframes):
+                R[i] = np.asarray(kf.R_w2c, dtype=np.float32)
+                t[i] = np.asarray(kf.t_w2c, dtype=np.float32).reshape(3)
+                fixed[i] = 1 if kf is kf_fixed else 0
+                kf_ids[i] = kf.keyframe_id
+                arrs = self._keypoint_arrays(kf)
+                n_sens[i] = len(arrs)
+                for c, a in enumerate(arrs):
+                    base[i, c], count[i, c] = at, a.shape[0]
+                    uv_parts.append(a)
+                    at += a.shape[0]
+            Xd, mp_keys = gather_points(map_points)
+            X = Xd.astype(np.float32).astype(np.float64)
+            if n_pt and np.unique(mp_keys).shape[0] != n_pt:        # a point handed in twice: its rows would be needed twice
+                self.stats["fallbacks"] += 1
+                return None
+            if n_pt:
+                known = self._known
+                for j, k in enumerate(mp_keys.tolist()):
+                    if k not in known:
+                        self.ingest(map_points[j])
+
+            n = self._n
+            # key -> window row through a lookup table when the ids are small integers (the reference's global
+            # counters), through a sorted search otherwise (object identities)
+            cam_of = self._lookup(kf_ids, self._kf[:n], last_wins=True)      # a later duplicate id wins, as the dict at :61 does
+            pt_of = self._lookup(mp_keys, self._mp[:n], last_wins=False)
+            rows = np.flatnonzero(self._alive[:n] & (cam_of >= 0) & (pt_of >= 0))
+            cam_row, pt_row = cam_of[rows], pt_of[rows]
+            cid, kpi = self._cam[rows], self._kp[rows]
+            # the packer's skip rules (:90-93): sensor index and keypoint index must be in range
+            ns = n_sens[cam_row]
+            ok = (cid < ns) & (cid >= -ns)
+            cc = np.where(ok, np.where(cid < 0, cid + ns, cid), 0)     # Python's negative indexing, as kps[cam_id] would
+            ok &= (kpi < count[cam_row, cc]) & (kpi >= -count[cam_row, cc])
+            if not ok.all():
+                rows, cam_row, pt_row, cid, kpi, cc = rows[ok], cam_row[ok], pt_row[ok], cid[ok], kpi[ok], cc[ok]
+            kpi = np.where(kpi < 0, kpi + count[cam_row, cc], kpi)           # Python's negative indexing, as kps[idx] would
+            # group by point; inside a point by keyframe in first-insertion order, then by insertion (= the nested
+            # dict iteration of the reference's packing loop, :80-95).  Rows are in insertion order already, so
+            # when no (keyframe, point) pair was observed twice a stable counting sort by point is all it takes.
+            if np.array_equal(self._grp[rows], rows):
+                o = _stable_order_by(pt_row, n_pt)
+            else:
+                o = np.lexsort((rows, self._grp[rows], pt_row))
+            cam_row, pt_row, cid = cam_row[o], pt_row[o], cid[o]
+            src = (base[cam_row, cc[o]] + kpi[o])
+            uv_all = np.concatenate(uv_parts) if uv_parts else np.zeros((0, 2), dtype=np.float32)
+            pt_offsets = np.zeros(n_pt + 1, dtype=np.int32)
+            if n_pt:
+                np.cumsum(np.bincount(pt_row, minlength=n_pt), out=pt_offsets[1:])
+            return PackedWindow(intr=intr, R=R, t=t, fixed=fixed, X=X,
+                                obs_cam=cam_row.astype(np.int32), obs_pt=pt_row.astype(np.int32),
+                                obs_uv=np.ascontiguousarray(uv_all[src]) if src.size else np.zeros((0, 2), dtype=np.float32),
+                                obs_cam_id=np.ascontiguousarray(cid.astype(np.int32)), pt_offsets=pt_offsets)
+
+
+_SHARED_TABLE: Optional[ObservationTable] = None
+_SHARED_LOCK = threading.Lock()
+
+
+def shared_table() -> ObservationTable:
+    """The process-wide table the plugin uses by default: one set of hooks per map-point class, however many
+    optimizer instances there are."""
+    global _SHARED_TABLE
+    with _SHARED_LOCK:
+        if _SHARED_TABLE is None:
+            _SHARED_TABLE = ObservationTable()
+        return _SHARED_TABLE

@@ -108,9 +108,10 @@ class LocalBASolver:
         _lib.check(self.lib, self._h, rc, "ba_dist_init")
 
     def set_config(self, cfg: LMConfig):
-        self.cfg = cfg
-        prm = cfg.to_c()
-        _lib.check(self.lib, self._h, self.lib.ba_set_params(self._h, C.byref(prm)), "ba_set_params")
+        with self._lock:
+            self.cfg = cfg
+            prm = cfg.to_c()
+            _lib.check(self.lib, self._h, self.lib.ba_set_params(self._h, C.byref(prm)), "ba_set_params")
 
     # ------------------------------------------------------------------ local BA, host buffers
     def solve_local(self, intr, R, t, fixed, X, obs_cam, obs_pt, obs_uv, pt_offsets,
@@ -204,13 +205,14 @@ class LocalBASolver:
 
     # ------------------------------------------------------------------ pose-only
     def solve_pose_only(self, intr, R, t, X, uv, frame_offsets, want_hist: bool = True, inplace: bool = False,
-                        flags=None, cost_hist=None, accepted=None):
+                        flags=None, cost_hist=None, accepted=None, chi2_thr: Optional[float] = None):
         """Batched motion-only LM (one free pose per frame, points fixed).
 
         `inplace=True` refines the caller's float64 C-contiguous `R` (n,3,3) / `t` (n,3) where they are;
         `flags` (uint8 [n_match]), `cost_hist` (float64 [n, max_iter+1]) and `accepted` (uint8 [n, max_iter])
         may be passed in to be filled.  With all of them (and X, uv, frame_offsets) in pinned host memory the
-        host<->device copies inside the call are plain DMA transfers."""
+        host<->device copies inside the call are plain DMA transfers.  `chi2_thr` overrides the flag threshold
+        for this call only (applied and restored under the solver's lock)."""
         intr = np.ascontiguousarray(intr, dtype=np.float64)
         if inplace:
             for name, a in (("R", R), ("t", t)):
@@ -242,9 +244,19 @@ class LocalBASolver:
         acc = _out(accepted, (nF, max(mi, 1)), "accepted") if (want_hist or accepted is not None) else None
         ms = C.c_float(0.0)
         with self._lock:
-            rc = self.lib.ba_solve_pose_only_host(
-                self._h, nF, nM, _dptr(intr), _ptr(R), _ptr(t), _ptr(X), _ptr(uv), _ptr(fo),
-                _ptr(flags), _ptr(hist), _ptr(acc), C.byref(ms))
+            swapped = chi2_thr is not None and float(chi2_thr) != self.cfg.chi2_thr
+            if swapped:
+                import dataclasses
+                tmp = dataclasses.replace(self.cfg, chi2_thr=float(chi2_thr)).to_c()
+                _lib.check(self.lib, self._h, self.lib.ba_set_params(self._h, C.byref(tmp)), "ba_set_params")
+            try:
+                rc = self.lib.ba_solve_pose_only_host(
+                    self._h, nF, nM, _dptr(intr), _ptr(R), _ptr(t), _ptr(X), _ptr(uv), _ptr(fo),
+                    _ptr(flags), _ptr(hist), _ptr(acc), C.byref(ms))
+            finally:
+                if swapped:
+                    old = self.cfg.to_c()
+                    self.lib.ba_set_params(self._h, C.byref(old))
             _lib.check(self.lib, self._h, rc, "ba_solve_pose_only_host")
         return dict(R=R, t=t, flags=flags, cost_hist=None if hist is None else hist.reshape(nF, mi + 1),
                     accepted=None if acc is None else acc.reshape(nF, max(mi, 1))[:, :mi], gpu_ms=float(ms.value))
