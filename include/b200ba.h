@@ -61,11 +61,13 @@ enum {
 };
 /* schur_kind */
 enum {
-  BA_SCHUR_AUTO = 0,     /* BA_SCHUR_MMA for windows of <= 20 keyframes and for banded (sequential) windows, else BA_SCHUR_STREAM */
+  BA_SCHUR_AUTO = 0,     /* BA_SCHUR_PANEL for windows of <= 20 keyframes and for banded (sequential) windows, else BA_SCHUR_STREAM */
   BA_SCHUR_SCATTER = 1,  /* warp per point, one float64 RED per entry (no ordering requirement) */
   BA_SCHUR_TILED = 2,    /* round-1 v2 kernel: thread-owned blocks over a slot table */
   BA_SCHUR_STREAM = 3,   /* compact block lists, Q lanes per block, rows sorted by camera */
-  BA_SCHUR_MMA = 4       /* lane-per-keyframe staging + FP64 tensor-core (mma m8n8k4) panel products, warp specialised */
+  BA_SCHUR_MMA = 4,      /* round-1 kernel: lane-per-keyframe staging + FP64 tensor-core (mma m8n8k4) panel products */
+  BA_SCHUR_PANEL = 5     /* round-2 default: point-block pass + camera-major pass + lane-per-observation staging fed by
+                            bulk copies, FP64 tensor-core products restricted to each point's camera interval */
 };
 
 typedef struct ba_params {

@@ -12,7 +12,7 @@ BA_NCCL_ID_BYTES = 128
 BA_OK = 0
 BA_ERR_INVALID, BA_ERR_CUDA, BA_ERR_TOO_LARGE, BA_ERR_NCCL, BA_ERR_NO_DEVICE = -1, -2, -3, -4, -5
 BA_SOLVER_AUTO, BA_SOLVER_CHOLESKY, BA_SOLVER_PCG, BA_SOLVER_BAND, BA_SOLVER_BAND_SEQ = 0, 1, 2, 3, 4
-BA_SCHUR_AUTO, BA_SCHUR_SCATTER, BA_SCHUR_TILED, BA_SCHUR_STREAM, BA_SCHUR_MMA = 0, 1, 2, 3, 4
+BA_SCHUR_AUTO, BA_SCHUR_SCATTER, BA_SCHUR_TILED, BA_SCHUR_STREAM, BA_SCHUR_MMA, BA_SCHUR_PANEL = 0, 1, 2, 3, 4, 5
 
 
 class BAParams(C.Structure):

@@ -76,7 +76,8 @@ struct ba_handle {
   ba_params prm;
   std::string err;
   // workspace
-  DevBuf camstate, X0, X1, red, ctl, cand, dbg, part;   // camstate = pose[0] | pose[1] | dp, contiguous (one broadcast)
+  DevBuf camstate, X0, X1, red, ctl, cand, dbg, part;
+  DevBuf rec, cs_cnt, cs_blk_off, cs_blk_cam, cs_pt, cs_uv, cs_nblk;   // panel linearise path   // camstate = pose[0] | pose[1] | dp, contiguous (one broadcast)
   // sparse path: structure + PCG workspace
   DevBuf bits, wpre, row_nnz, row_ptr, col_idx, tpos, pcg, bits_all;
   // banded path: factor columns, forward-substituted rhs, inverse pivots, bandwidth scalar
@@ -266,7 +267,7 @@ extern "C" int ba_destroy(ba_handle* h) {
   if (!h) return BA_OK;
   DeviceGuard dev_guard(h->device);
   if (h->graph) cudaGraphExecDestroy(h->graph);
-  DevBuf* bufs[] = {&h->camstate, &h->X0, &h->X1, &h->red, &h->ctl, &h->cand,
+  DevBuf* bufs[] = {&h->camstate, &h->X0, &h->X1, &h->red, &h->ctl, &h->cand, &h->rec, &h->cs_cnt, &h->cs_blk_off, &h->cs_blk_cam, &h->cs_pt, &h->cs_uv, &h->cs_nblk,
                     &h->d_R, &h->d_t, &h->d_fixed, &h->d_X, &h->d_ocam, &h->d_opt, &h->d_ouv,
                     &h->d_off, &h->d_flags, &h->d_hist, &h->d_acc, &h->d_foff, &h->dbg, &h->part,
                     &h->bits, &h->wpre, &h->row_nnz, &h->row_ptr, &h->col_idx, &h->tpos, &h->pcg,
@@ -364,6 +365,20 @@ static int make_work(ba_handle* h, int n_cam, int n_pt, int n_obs, const double 
     w.part_n = mma_grid(n_cam, n_pt, h->sm_count);
     if ((rc = ensure(h, h->part, sizeof(int) * (size_t)(w.part_n + 1)))) return rc;
     w.part = (int*)h->part.p;
+    if (n_obs > 0 && (h->prm.schur_kind == BA_SCHUR_AUTO || h->prm.schur_kind == BA_SCHUR_PANEL)) {
+      // panel path: one record per point, camera-sorted copy of the observations (cameras padded to 32 entries)
+      w.cs_nblk_max = panel_cs_blocks_max(n_cam, n_obs);
+      if ((rc = ensure(h, h->rec, sizeof(double) * panel_rec_doubles(n_pt)))) return rc;
+      if ((rc = ensure(h, h->cs_cnt, sizeof(int) * (size_t)(n_cam + 1)))) return rc;
+      if ((rc = ensure(h, h->cs_blk_off, sizeof(int) * (size_t)(n_cam + 2)))) return rc;
+      if ((rc = ensure(h, h->cs_blk_cam, sizeof(int) * (size_t)(w.cs_nblk_max + 1)))) return rc;
+      if ((rc = ensure(h, h->cs_pt, sizeof(int) * 32 * (size_t)(w.cs_nblk_max + 1)))) return rc;
+      if ((rc = ensure(h, h->cs_uv, sizeof(float) * 64 * (size_t)(w.cs_nblk_max + 1)))) return rc;
+      if ((rc = ensure(h, h->cs_nblk, sizeof(int) * 4))) return rc;
+      w.rec = (double*)h->rec.p;
+      w.cs_cnt = (int*)h->cs_cnt.p; w.cs_blk_off = (int*)h->cs_blk_off.p; w.cs_blk_cam = (int*)h->cs_blk_cam.p;
+      w.cs_pt = (int*)h->cs_pt.p; w.cs_uv = (float2*)h->cs_uv.p; w.cs_nblk = (int*)h->cs_nblk.p;
+    }
   }
   w.dbg = nullptr;
   static int want_dbg = -1;
@@ -454,12 +469,15 @@ static int pick_schur(const ba_handle* h, const Work& w) {
     // lane-per-keyframe staging needs the cameras of consecutive points inside a 20-keyframe window:
     // whole local windows, or sequential (banded) co-visibility
     const bool seq = w.band_w >= 0 && w.band_w < mma_window();
-    kind = (w.n_cam <= mma_window() || seq) ? BA_SCHUR_MMA : BA_SCHUR_STREAM;
+    kind = (w.n_cam <= mma_window() || seq) ? BA_SCHUR_PANEL : BA_SCHUR_STREAM;
   }
+  // the panel path needs its workspace and 16-byte aligned observation arrays (bulk copies); the round-1 kernel takes anything
+  if (kind == BA_SCHUR_PANEL && !panel_supported(w)) kind = BA_SCHUR_MMA;
   return kind;
 }
 
 static int launch_linearize(const Work& w, int schur, int sm_count, cudaStream_t s) {
+  if (schur == BA_SCHUR_PANEL) return launch_linearize_panel(w, sm_count, s);
   if (schur == BA_SCHUR_MMA) return launch_linearize_mma(w, sm_count, s);
   if (schur == BA_SCHUR_STREAM) return launch_linearize_stream(w, sm_count, s);
   if (schur == BA_SCHUR_TILED) return launch_linearize_tiled(w, sm_count, s);
@@ -586,6 +604,7 @@ extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t
   CK(cudaEventRecord(h->ev0, s));
   prof_mark(h, TAG_OTHER, s);
   launches += launch_init(w, cam_R, cam_t, X, li, s);
+  if (schur == BA_SCHUR_PANEL && h->prm.max_iter > 0) launches += launch_panel_setup(w, h->sm_count, s);
   if (h->prm.max_iter == 0) {
     // nothing will linearise: the report's initial cost comes from a plain evaluation of the objective
     launches += launch_eval_cost(w, w.pose[0], w.X[0], w.cost_cand, h->prm.huber_delta, s);
@@ -758,7 +777,9 @@ extern "C" int ba_debug_linearize(ba_handle* h, int32_t n_cam, int32_t n_pt, int
   LmInit li{lambda, h->prm.huber_delta, h->prm.chi2_thr, h->prm.lambda_up,
             h->prm.lambda_down, h->prm.lambda_min, h->prm.lambda_max, h->prm.accept_rtol};
   launch_init(w, cam_R, cam_t, X, li, s);
-  launch_linearize(w, pick_schur(h, w), h->sm_count, s);
+  const int dbg_schur = pick_schur(h, w);
+  if (dbg_schur == BA_SCHUR_PANEL) launch_panel_setup(w, h->sm_count, s);
+  launch_linearize(w, dbg_schur, h->sm_count, s);
   const size_t n = (size_t)w.n;
   if (S_host) CK(cudaMemcpyAsync(S_host, w.S, sizeof(double) * s_doubles(w.n_cam), cudaMemcpyDeviceToHost, s));
   if (b_host) CK(cudaMemcpyAsync(b_host, w.b, sizeof(double) * n, cudaMemcpyDeviceToHost, s));

@@ -28,6 +28,15 @@ struct Work {
   long long* dbg;                     // optional clock64() trace (BA_DBG_TIMES=1), null otherwise
   int* part;                          // [part_n + 1] first point of every CTA of the mma linearise kernel (equal
   int part_n;                         // observation shares), written once per solve by k_init; null / 0: none
+  // panel linearise path (ba_panel.cu): per-point records and the camera-sorted copy of the observations
+  double* rec;                        // [10 (n_pt + 1)] C (6) | q (3) | cmin, cmax | flags
+  int* cs_cnt;                        // [n_cam] observation counts, then fill cursors
+  int* cs_blk_off;                    // [n_cam + 1] first 32-entry block of every camera
+  int* cs_blk_cam;                    // [cs_nblk_max] camera of every block
+  int* cs_pt;                         // [32 cs_nblk_max] point of every entry (-1: pad)
+  float2* cs_uv;                      // [32 cs_nblk_max]
+  int* cs_nblk;                       // [1] blocks in use
+  int cs_nblk_max;
   // block-sparse reduced camera matrix (large windows); all null / 0 for the dense packed layout
   const unsigned* bsr_bits;           // [n_cam * bsr_W] structure bitmap (symmetric, diagonal set)
   const int* bsr_wpre;                // [n_cam * bsr_W] set bits before each word of its row
@@ -89,6 +98,13 @@ int launch_linearize_tiled(const Work& w, int sm_count, cudaStream_t s);
 int launch_linearize_stream(const Work& w, int sm_count, cudaStream_t s);
 int configure_stream();
 int launch_linearize_mma(const Work& w, int sm_count, cudaStream_t s);
+int launch_linearize_panel(const Work& w, int sm_count, cudaStream_t s);   // point blocks + camera blocks + Schur panels
+int launch_panel_setup(const Work& w, int sm_count, cudaStream_t s);       // once per solve: camera-sorted observations
+int configure_panel();
+int panel_window();
+size_t panel_rec_doubles(int n_pt);
+int panel_cs_blocks_max(int n_cam, int n_obs);
+bool panel_supported(const Work& w);
 int configure_mma();
 int mma_grid(int n_cam, int n_pt, int sm_count);   // CTAs launch_linearize_mma will use
 int mma_window();

@@ -50,6 +50,7 @@ __global__ void k_init(Work w, const double* __restrict__ R_in, const double* __
           const int mid = (lo + hi) >> 1;
           if (w.pt_off[mid] < target) lo = mid + 1; else hi = mid;
         }
+        lo &= ~3;          // ranges start at multiples of 4 points: the panel kernel's bulk copies need 16-byte aligned sources
       }
       w.part[i] = lo;
     }
@@ -573,6 +574,8 @@ int configure_kernels() {
   r = configure_stream();
   if (r != 0) return r;
   r = configure_mma();
+  if (r != 0) return r;
+  r = configure_panel();
   if (r != 0) return r;
   r = configure_bcr();
   if (r != 0) return r;

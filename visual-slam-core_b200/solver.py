@@ -30,7 +30,7 @@ class LMConfig:
     accept_rtol: float = 1e-8
     max_iter: int = 10
     solver: str = "auto"        # auto | cholesky | pcg | band | band_seq
-    schur: str = "auto"         # auto | scatter | tiled | stream | mma
+    schur: str = "auto"         # auto | scatter | tiled | stream | mma | panel
     pcg_max_iter: int = 500
     pcg_tol: float = 1e-10
     use_graph: bool = True
@@ -44,7 +44,7 @@ class LMConfig:
         p.accept_rtol = self.accept_rtol
         p.max_iter = int(self.max_iter)
         p.solver_kind = {"auto": 0, "cholesky": 1, "pcg": 2, "band": 3, "band_seq": 4}[self.solver]
-        p.schur_kind = {"auto": 0, "scatter": 1, "tiled": 2, "stream": 3, "mma": 4}[self.schur]
+        p.schur_kind = {"auto": 0, "scatter": 1, "tiled": 2, "stream": 3, "mma": 4, "panel": 5}[self.schur]
         p.pcg_max_iter, p.pcg_tol = int(self.pcg_max_iter), float(self.pcg_tol)
         p.use_graph = 1 if self.use_graph else 0
         p.profile = 1 if self.profile else 0

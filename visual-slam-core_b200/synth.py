@@ -193,12 +193,14 @@ def make_problem(
     noise_px: float = 1.0,
     chunk: int = 250_000,
     sort_points: Optional[bool] = None,
+    init_scale: float = 1.0,
 ) -> BAProblem:
     """Generate one of the named configs (or a custom size).
 
     `sort_points` (default: on when n_cam > 40) orders the points by their anchor camera, the
     order a SLAM map has naturally: `Map.optimize_local` collects points keyframe by keyframe
     (map/map.py:159-169), so consecutive points are seen by neighbouring keyframes.
+    `init_scale` scales the perturbation of the initial estimate (1.0 = SURVEY 8d-D2: 0.05 m / 0.01 rad).
     """
     if name is not None:
         cfg = dict(CONFIGS[name])
@@ -299,9 +301,9 @@ def make_problem(
         outlier[o0:o1] = out
 
     # initial estimate
-    X0 = X_true + rng.normal(0.0, 0.05, (n_pt, 3))
-    t0 = t_true + rng.normal(0.0, 0.05, (n_cam, 3))
-    dR = so3_exp(rng.normal(0.0, 0.01, (n_cam, 3)))
+    X0 = X_true + rng.normal(0.0, 0.05 * init_scale, (n_pt, 3))
+    t0 = t_true + rng.normal(0.0, 0.05 * init_scale, (n_cam, 3))
+    dR = so3_exp(rng.normal(0.0, 0.01 * init_scale, (n_cam, 3)))
     R0 = dR @ R_true
     R0[0], t0[0] = R_true[0], t_true[0]
     fixed = np.zeros(n_cam, dtype=np.uint8)
