@@ -469,7 +469,9 @@ static int pick_schur(const ba_handle* h, const Work& w) {
     // lane-per-keyframe staging needs the cameras of consecutive points inside a 20-keyframe window:
     // whole local windows, or sequential (banded) co-visibility
     const bool seq = w.band_w >= 0 && w.band_w < mma_window();
-    kind = (w.n_cam <= mma_window() || seq) ? BA_SCHUR_PANEL : BA_SCHUR_STREAM;
+    // whole windows (<= 20 keyframes): the round-1 kernel (its lane-per-keyframe staging has no set-up passes; measured
+    // C1 25 vs 39 us, C2 55 vs 75 us per linearisation); longer banded windows: the panel path (C4 3.7 -> 2.1 ms)
+    kind = (w.n_cam <= mma_window()) ? BA_SCHUR_MMA : (seq ? BA_SCHUR_PANEL : BA_SCHUR_STREAM);
   }
   // the panel path needs its workspace and 16-byte aligned observation arrays (bulk copies); the round-1 kernel takes anything
   if (kind == BA_SCHUR_PANEL && !panel_supported(w)) kind = BA_SCHUR_MMA;

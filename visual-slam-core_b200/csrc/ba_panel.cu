@@ -396,11 +396,15 @@ struct YObs { double y[6][3]; };
 
 __device__ __forceinline__ void obs_Y(const Intr& K, const double* __restrict__ P, double X0, double X1, double X2,
                                       float2 uv, double delta, const double* __restrict__ c, YObs& out) {
-  const double R0 = P[0], R1 = P[1], R2 = P[2], R3 = P[3], R4 = P[4], R5 = P[5], R6 = P[6], R7 = P[7], R8 = P[8];
+  // the 96-byte pose record in six 16-byte loads
+  const double2* P2 = reinterpret_cast<const double2*>(P);
+  const double2 q0 = __ldg(P2), q1 = __ldg(P2 + 1), q2 = __ldg(P2 + 2), q3 = __ldg(P2 + 3), q4 = __ldg(P2 + 4), q5 = __ldg(P2 + 5);
+  const double R0 = q0.x, R1 = q0.y, R2 = q1.x, R3 = q1.y, R4 = q2.x, R5 = q2.y, R6 = q3.x, R7 = q3.y, R8 = q4.x;
+  const double T0 = q4.y, T1 = q5.x, T2 = q5.y;
   const double Y0 = R0 * X0 + R1 * X1 + R2 * X2;
   const double Y1 = R3 * X0 + R4 * X1 + R5 * X2;
   const double Y2 = R6 * X0 + R7 * X1 + R8 * X2;
-  const double xc = Y0 + P[9], yc = Y1 + P[10], zc = Y2 + P[11];
+  const double xc = Y0 + T0, yc = Y1 + T1, zc = Y2 + T2;
   const double iz = 1.0 / (zc + kDepthEps);
   const double xz = xc * iz, yz = yc * iz;
   const double ru = K.fx * xz + K.cx - (double)uv.x;
@@ -638,7 +642,10 @@ k_schur_panel(const __grid_constant__ Work w) {
   // =========================================== staging warps ================================================
   const int g = wid / kGW;                       // staging group = panel buffer
   const int gt = tid - g * kGL;                  // thread index inside the group
-  const bool producer = gt == 0;
+  // service warp of the group = its LAST warp (lanes 96..127 carry an observation least often): it issues the bulk
+  // copies of the next panel (five lanes, one copy each) and keeps the panel's books, off the other warps' critical path
+  const int sl = gt - (kGL - 32);                // lane inside the service warp (negative: not in it)
+  const bool producer = sl == 0;
   double* __restrict__ Yb = sm.Yt[g];
 
   for (int sc0 = 0; sc0 < n_panels; sc0 += kBoundsCap) {
@@ -669,7 +676,7 @@ k_schur_panel(const __grid_constant__ Work w) {
       unsigned bytes = 0;
       if (a1 > lim) {
         a1 = max(lim, a0);
-        for (int o = max(a1, o0); o < o0 + nob; ++o) {
+        for (int o = max(a1, o0); sl == 0 && o < o0 + nob; ++o) {
           si.cam[o - a0] = __ldg(w.obs_cam + o); si.pt[o - a0] = __ldg(w.obs_pt + o);
           si.uv[o - a0] = __ldg(reinterpret_cast<const float2*>(w.obs_uv) + o);
         }
@@ -678,25 +685,25 @@ k_schur_panel(const __grid_constant__ Work w) {
       // points and records: CTA ranges start at multiples of 4 points, so the sources are 16-byte aligned;
       // an odd point count leaves 8 bytes for plain loads
       const unsigned xb = (24u * npts) & ~15u, rb = 80u * npts;
-      if ((24u * npts) & 15u) {
+      if (sl == 0 && ((24u * npts) & 15u)) {
         si.X[3 * npts - 1] = X[3 * (size_t)(j0 + npts) - 1];
       }
       if (a_hi > a_lo) bytes += 16u * (unsigned)(a_hi - a_lo);
       bytes += xb + rb;
-      mbar_expect_tx(&sm.bar[g][st], bytes);
-      if (a_hi > a_lo) {
-        const unsigned nb4 = 4u * (unsigned)(a_hi - a_lo);
-        bulk_g2s(&si.cam[a_lo - a0], w.obs_cam + a_lo, nb4, &sm.bar[g][st]);
-        bulk_g2s(&si.pt[a_lo - a0], w.obs_pt + a_lo, nb4, &sm.bar[g][st]);
-        bulk_g2s(&si.uv[a_lo - a0], reinterpret_cast<const float2*>(w.obs_uv) + a_lo, 2 * nb4, &sm.bar[g][st]);
-      }
-      if (xb) bulk_g2s(si.X, X + 3 * (size_t)j0, xb, &sm.bar[g][st]);
-      bulk_g2s(si.rec, rec + kRecD * (size_t)j0, rb, &sm.bar[g][st]);
+      // one arrival (lane 0, with the byte count) + five copies, one per lane; a copy that completes before the count is
+      // posted only drives the transaction count negative for a moment, the phase still needs the arrival
+      const unsigned nb4 = (a_hi > a_lo) ? 4u * (unsigned)(a_hi - a_lo) : 0u;
+      if (sl == 0) mbar_expect_tx(&sm.bar[g][st], bytes);
+      if (sl == 0 && nb4) bulk_g2s(&si.cam[a_lo - a0], w.obs_cam + a_lo, nb4, &sm.bar[g][st]);
+      if (sl == 1 && nb4) bulk_g2s(&si.pt[a_lo - a0], w.obs_pt + a_lo, nb4, &sm.bar[g][st]);
+      if (sl == 2 && nb4) bulk_g2s(&si.uv[a_lo - a0], reinterpret_cast<const float2*>(w.obs_uv) + a_lo, 2 * nb4, &sm.bar[g][st]);
+      if (sl == 3 && xb) bulk_g2s(si.X, X + 3 * (size_t)j0, xb, &sm.bar[g][st]);
+      if (sl == 4) bulk_g2s(si.rec, rec + kRecD * (size_t)j0, rb, &sm.bar[g][st]);
     };
 
     const int n_first = sc0 + g;                          // this group's panels: sc0 + g, + kNG, ...
     const int sc_end = sc0 + sc_n;
-    if (producer && n_first < sc_end) issue(n_first, (n_first / kNG) & 1);
+    if (sl >= 0 && sl < 5 && n_first < sc_end) issue(n_first, (n_first / kNG) & 1);
 
     for (int n = n_first; n < sc_end; n += kNG) {
       const int it = n / kNG;                             // this group's it-th panel overall
@@ -705,9 +712,9 @@ k_schur_panel(const __grid_constant__ Work w) {
       if (producer) sm.gbase[g] = sm.cur_base;
       // everyone is done with the other stage (panel n - kNG): its buffers may be refilled
       bar_sync<kGL>(kBarGroup + g);
-      const bool tr = gt == 0 && n >= 8 && n < 16;
+      const bool tr = sl == 0 && n >= 8 && n < 16;
       pmark(w, tr, 8 * (n - 8), 10 * n + 1);
-      if (producer && n + kNG < sc_end) issue(n + kNG, st ^ 1);
+      if (sl >= 0 && sl < 5 && n + kNG < sc_end) issue(n + kNG, st ^ 1);
       pmark(w, tr, 8 * (n - 8) + 1, 10 * n + 2);
       mbar_wait(&sm.bar[g][st], (it >> 1) & 1);
       pmark(w, tr, 8 * (n - 8) + 2, 10 * n + 3);
@@ -724,12 +731,12 @@ k_schur_panel(const __grid_constant__ Work w) {
       if (it >= 1) bar_sync<kGL + 32 * kXW>(kBarEmpty + g);
       pmark(w, tr, 8 * (n - 8) + 3, 10 * n + 4);
 
-      // slot intervals + window bookkeeping by the group's first warp
-      if (gt < 32) {
+      // slot intervals + window bookkeeping by the group's service warp
+      if (sl >= 0) {
         int my_cmin = 0x7fffffff;
         bool ahead = false, fits_any = false;
-        if (gt < npts) {
-          const Rec& r = reinterpret_cast<const Rec*>(si.rec)[gt];
+        if (sl < npts) {
+          const Rec& r = reinterpret_cast<const Rec*>(si.rec)[sl];
           const int flags = ((unsigned)r.cmaxf) >> 28, cmax = r.cmaxf & 0x0fffffff;
           int iv = 0xff;                                  // no interval: skipped by the mma warps
           if (!(flags & kFlagSkip)) {
@@ -742,7 +749,7 @@ k_schur_panel(const __grid_constant__ Work w) {
             ahead = cmax >= base + kWin;                  // the window is exhausted in the direction the points move
             my_cmin = r.cmin;
           }
-          sm.piv[g][gt] = (unsigned char)iv;
+          sm.piv[g][sl] = (unsigned char)iv;
         }
         if (sliding) {
           // The window only moves when a point lies beyond its end, or when nothing of the panel fits; a point
@@ -750,11 +757,13 @@ k_schur_panel(const __grid_constant__ Work w) {
           // New base: three cameras before the panel's first camera, so that wider points of the same
           // neighbourhood still fit.
           const bool any_ahead = __any_sync(kFull, ahead), any_fit = __any_sync(kFull, fits_any);
+          if (any_ahead || !any_fit) {                    // rare: only then is the panel's first camera needed
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) my_cmin = min(my_cmin, __shfl_xor_sync(kFull, my_cmin, o));
-          if ((any_ahead || !any_fit) && gt == 0 && my_cmin != 0x7fffffff) sm.cur_base = max(0, my_cmin - 3);
+            for (int o = 16; o > 0; o >>= 1) my_cmin = min(my_cmin, __shfl_xor_sync(kFull, my_cmin, o));
+            if (sl == 0 && my_cmin != 0x7fffffff) sm.cur_base = max(0, my_cmin - 3);
+          }
         }
-        if (gt == 0) { sm.pbase[g] = base; sm.pnpts[g] = npts; }
+        if (sl == 0) { sm.pbase[g] = base; sm.pnpts[g] = npts; }
       }
 
       pmark(w, tr, 8 * (n - 8) + 4, 10 * n + 5);
