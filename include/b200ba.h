@@ -12,6 +12,7 @@
  *   ba_solve_pose_only[_host]  <- estimate_motion_from_2d3d (cv2.solvePnPRansac refinement)
  *                                 visual_slam/utils/motion_estimation.py:57-132,
  *                                 called from visual_slam/tracking.py:350-356
+ *   ba_pose_ransac_host        <- the RANSAC consensus inside cv2.solvePnPRansac at the same call site (no prior passed)
  *   ba_dist_*                  <- (no reference counterpart; shard-by-point multi-GPU, 8e-E1)
  *
  * Conventions
@@ -157,6 +158,14 @@ int ba_solve_pose_only_host(ba_handle* h, int32_t n_frames, int32_t n_match,
                             double* R, double* t,
                             const float* X, const float* uv, const int32_t* frame_offsets,
                             uint8_t* flags, double* cost_hist, uint8_t* accepted, float* gpu_ms);
+
+/* Pose of ONE frame without a prior, HOST pointers: RANSAC over `n_hyp` minimal three-point (P3P) samples on the device,
+ * every admissible root scored by the number of the frame's matches that reproject within `thr_px`; the best pose comes
+ * back in R_out (9, row-major, world->camera) / t_out (3) with its inlier count (0: no admissible hypothesis).  This is the
+ * bootstrap cv2.solvePnPRansac provides at the reference's call site, which passes no initial guess
+ * (visual_slam/utils/motion_estimation.py:107-116, visual_slam/tracking.py:350-356); ba_solve_pose_only refines it. */
+int ba_pose_ransac_host(ba_handle* h, int32_t n_match, const double intr[4], const float* X, const float* uv,
+                        int32_t n_hyp, double thr_px, uint32_t seed, double* R_out, double* t_out, int32_t* n_inliers);
 
 /* Objective only (reference cost, torch_optimizer.py:152-177) at the given state; device pointers. */
 int ba_eval_cost(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t n_obs, const double intr[4],

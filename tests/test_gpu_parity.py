@@ -63,7 +63,7 @@ def _check(p, res, ref, gauge_free=False):
                 x_max=float(np.abs(res.X - ref.X).max()))
 
 
-@pytest.mark.parametrize("schur", ["scatter", "tiled", "stream", "mma"])
+@pytest.mark.parametrize("schur", ["scatter", "tiled", "stream", "mma", "panel"])
 @pytest.mark.parametrize("name,seed", [("T0", 1), ("T1", 2), ("T2", 3), ("T2", 4), ("C1", 0)])
 def test_lm_trajectory_matches_oracle(name, seed, schur):
     p = synth.make_problem(name, seed=seed)
@@ -77,7 +77,7 @@ def test_lm_trajectory_matches_oracle(name, seed, schur):
     assert info["cost_rel"] < 1e-9
 
 
-@pytest.mark.parametrize("schur", ["scatter", "tiled", "stream", "mma"])
+@pytest.mark.parametrize("schur", ["scatter", "tiled", "stream", "mma", "panel"])
 @pytest.mark.parametrize("name,seed,lam", [("T0", 1, 1e-4), ("T1", 2, 1e-2), ("T2", 3, 1e-6)])
 def test_reduced_camera_system_matches_oracle(name, seed, lam, schur):
     """S (before damping of the pose blocks), b and diag(U) of one linearisation."""

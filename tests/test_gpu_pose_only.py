@@ -61,3 +61,60 @@ def test_pose_only_inplace_with_caller_buffers_equals_the_copying_call():
     with pytest.raises(ValueError):
         s.solve_pose_only(pp.intr, R, t, pp.X, pp.uv, pp.frame_offsets, flags=np.zeros(3, np.uint8))
     s.close()
+
+
+# ---------------------------------------------------------------------------------------- no prior
+def _frame(seed, n=400, outliers=0.15):
+    rng = np.random.default_rng(seed)
+    fx = fy = 700.0
+    K = np.array([[fx, 0, 640.0], [0, fy, 360.0], [0, 0, 1.0]])
+    w = rng.normal(0, 0.4, 3)
+    th = np.linalg.norm(w)
+    Kx = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    R = np.eye(3) + np.sin(th) / th * Kx + (1 - np.cos(th)) / th ** 2 * Kx @ Kx
+    Xc = np.stack([rng.uniform(-4, 4, n), rng.uniform(-2, 2, n), rng.uniform(5, 25, n)], axis=1)
+    t = rng.normal(0, 1.0, 3)
+    Xw = (Xc - t) @ R                                  # Xc = R Xw + t
+    uv = Xc[:, :2] / Xc[:, 2:] * fx + np.array([640.0, 360.0]) + rng.normal(0, 0.5, (n, 2))
+    out = rng.random(n) < outliers
+    uv[out] += rng.normal(0, 40.0, (int(out.sum()), 2))
+    return K, R, t, Xw.astype(np.float32), uv.astype(np.float32), out
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_p3p_ransac_bootstrap_finds_the_pose_without_a_prior(seed):
+    K, R, t, Xw, uv, out = _frame(seed)
+    s = LocalBASolver(LMConfig())
+    got = s.pose_ransac([700.0, 700.0, 640.0, 360.0], Xw, uv, n_hypotheses=100, threshold_px=3.0, seed=42)
+    s.close()
+    assert got is not None
+    ang = rot_angle(got["R"][None], R[None])[0]
+    print(f"\n[p3p seed {seed}] inliers {got['n_inliers']} of {int((~out).sum())} clean, rot err {ang:.2e}, |dt| {np.abs(got['t'] - t).max():.2e}")
+    assert got["n_inliers"] >= 0.8 * int((~out).sum())
+    assert ang < 2e-2 and np.abs(got["t"] - t).max() < 0.2
+    assert abs(np.linalg.det(got["R"]) - 1.0) < 1e-9
+
+
+def test_call_site_without_prior_matches_the_references_opencv_result():
+    """`refine_motion_from_2d3d(pts3d, pts2d, K, dist)` exactly as `Tracking._optimize_pose_mono` calls the function it
+    replaces (tracking.py:350-356: no initial guess), on the frame the reference's own `estimate_motion_from_2d3d` was
+    run on (fixture ref_pose_only.npz): same pose within the noise of the two estimators, same inliers but for
+    threshold stragglers, same return types."""
+    import os
+    from helpers import GOLDEN
+    from visual_slam_core_b200 import motion
+    g = np.load(os.path.join(GOLDEN, "ref_pose_only.npz"))
+    R, t, ok, inl = motion.refine_motion_from_2d3d(g["pts3d"], g["pts2d"], g["K"], np.zeros(5), True)
+    assert ok is True and R.shape == (3, 3) and t.shape == (3, 1) and inl.dtype == np.int32 and inl.shape[1] == 1
+    ang = rot_angle(R[None], g["ref_R"][None])[0]
+    both = np.intersect1d(inl.ravel(), g["ref_inliers"].ravel()).size
+    print(f"\n[call site] rot diff to cv2 {ang:.2e}, |dt| {np.abs(t - g['ref_t']).max():.2e}, inliers {inl.shape[0]} vs {g['ref_inliers'].shape[0]} (common {both})")
+    assert ang < 3e-3 and np.abs(t - g["ref_t"]).max() < 3e-2
+    assert both >= 0.95 * g["ref_inliers"].shape[0]
+    # lens distortion at the call site: undistorted first, never an exception
+    import cv2
+    dist = np.array([0.1, -0.05, 0.001, 0.001, 0.0])
+    Xc = g["pts3d"].astype(np.float64) @ g["R_true"].T + g["t_true"]
+    uvd, _ = cv2.projectPoints(Xc, np.zeros(3), np.zeros(3), g["K"], dist)
+    R2, t2, ok2, _ = motion.refine_motion_from_2d3d(g["pts3d"], uvd.reshape(-1, 2).astype(np.float32), g["K"], dist, True)
+    assert ok2 is True and rot_angle(R2[None], g["R_true"][None])[0] < 2e-3 and np.abs(t2.ravel() - g["t_true"]).max() < 2e-2

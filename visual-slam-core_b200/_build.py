@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_NAME = "libb200ba.so"
 LIB_PATH = os.path.join(HERE, LIB_NAME)
-SOURCES = ["ba_local.cu", "ba_tiled.cu", "ba_stream.cu", "ba_mma.cu", "ba_panel.cu", "ba_sparse.cu", "ba_band.cu", "ba_bcr.cu", "ba_pose.cu", "ba_api.cu"]
+SOURCES = ["ba_local.cu", "ba_tiled.cu", "ba_stream.cu", "ba_mma.cu", "ba_panel.cu", "ba_sparse.cu", "ba_band.cu", "ba_bcr.cu", "ba_pose.cu", "ba_ransac.cu", "ba_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

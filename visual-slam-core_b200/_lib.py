@@ -46,7 +46,7 @@ EXPORTS = [
     "ba_version", "ba_error_string", "ba_last_error", "ba_default_params", "ba_create",
     "ba_destroy", "ba_set_params", "ba_solve_local", "ba_solve_local_host",
     "ba_solve_pose_only", "ba_solve_pose_only_host", "ba_eval_cost", "ba_nccl_unique_id",
-    "ba_dist_init", "ba_dist_shutdown", "ba_debug_linearize",
+    "ba_dist_init", "ba_dist_shutdown", "ba_debug_linearize", "ba_pose_ransac_host",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -90,6 +90,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.ba_solve_pose_only_host.argtypes = [vp, i32, i32, dp, vp, vp, vp, vp, vp, vp, vp, vp,
                                             C.POINTER(C.c_float)]
     lib.ba_eval_cost.argtypes = [vp, i32, i32, i32, dp, vp, vp, vp, vp, vp, vp, vp, dp]
+    lib.ba_pose_ransac_host.argtypes = [vp, i32, dp, vp, vp, i32, C.c_double, C.c_uint32, dp, dp, C.POINTER(i32)]
     lib.ba_nccl_unique_id.argtypes = [vp]
     lib.ba_dist_init.argtypes = [vp, vp, i32, i32]
     lib.ba_dist_shutdown.argtypes = [vp]

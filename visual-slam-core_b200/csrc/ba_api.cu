@@ -863,6 +863,42 @@ extern "C" int ba_solve_pose_only_host(ba_handle* h, int32_t n_frames, int32_t n
   return BA_OK;
 }
 
+extern "C" int ba_pose_ransac_host(ba_handle* h, int32_t n_match, const double intr[4], const float* X, const float* uv,
+                                   int32_t n_hyp, double thr_px, uint32_t seed, double* R_out, double* t_out,
+                                   int32_t* n_inliers) {
+  if (!h || !intr || !R_out || !t_out || !n_inliers || n_hyp <= 0 || n_hyp > 65535 || !(thr_px > 0)) return BA_ERR_INVALID;
+  *n_inliers = 0;
+  if (n_match < 4 || !X || !uv) return BA_ERR_INVALID;
+  DeviceGuard dev_guard(h->device);
+  cudaStream_t s = h->stream;
+  int rc;
+  const int od = ransac_out_doubles();
+  if ((rc = ensure(h, h->d_X, sizeof(float) * 3 * (size_t)(n_match + 1)))) return rc;
+  if ((rc = ensure(h, h->d_ouv, sizeof(float) * 2 * (size_t)(n_match + 1)))) return rc;
+  if ((rc = ensure(h, h->d_hist, sizeof(double) * (size_t)n_hyp * od))) return rc;
+  CK(cudaMemcpyAsync(h->d_X.p, X, sizeof(float) * 3 * (size_t)n_match, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->d_ouv.p, uv, sizeof(float) * 2 * (size_t)n_match, cudaMemcpyHostToDevice, s));
+  RansacWork w;
+  w.n_match = n_match; w.n_hyp = n_hyp;
+  w.K = Intr{intr[0], intr[1], intr[2], intr[3]};
+  w.X = (const float*)h->d_X.p; w.uv = (const float*)h->d_ouv.p;
+  w.thr2 = thr_px * thr_px; w.seed = seed; w.out = (double*)h->d_hist.p;
+  launch_pose_ransac(w, s);
+  CK(cudaGetLastError());
+  std::vector<double> out((size_t)n_hyp * od);
+  CK(cudaMemcpyAsync(out.data(), h->d_hist.p, sizeof(double) * out.size(), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  int best = -1;
+  double best_cnt = 0.0;
+  for (int i = 0; i < n_hyp; ++i)
+    if (out[(size_t)i * od] > best_cnt) { best_cnt = out[(size_t)i * od]; best = i; }
+  if (best < 0) return BA_OK;                       // no admissible hypothesis: n_inliers stays 0
+  for (int q = 0; q < 9; ++q) R_out[q] = out[(size_t)best * od + 1 + q];
+  for (int q = 0; q < 3; ++q) t_out[q] = out[(size_t)best * od + 10 + q];
+  *n_inliers = (int32_t)best_cnt;
+  return BA_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // multi-GPU plumbing
 // ------------------------------------------------------------------------------------------

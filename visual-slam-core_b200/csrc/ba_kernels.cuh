@@ -154,4 +154,17 @@ struct PoseWork {
 };
 int launch_pose_only(const PoseWork& w, cudaStream_t s);
 
+// pose without a prior: RANSAC over minimal P3P samples (ba_ransac.cu)
+struct RansacWork {
+  int n_match, n_hyp;
+  Intr K;
+  const float* X;            // [3 n_match] world points
+  const float* uv;           // [2 n_match] pixels
+  double thr2;               // squared reprojection threshold (px^2)
+  unsigned seed;
+  double* out;               // [n_hyp][16]: inliers | R (9) | t (3)
+};
+int ransac_out_doubles();
+int launch_pose_ransac(const RansacWork& w, cudaStream_t s);
+
 }  // namespace ba

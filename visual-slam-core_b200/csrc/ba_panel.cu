@@ -112,7 +112,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 // k_point_blocks
 // ------------------------------------------------------------------------------------------------------------
 template <int kG>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_point_blocks(const __grid_constant__ Work w) {
   __shared__ double s_cost[8];
   constexpr int kPer = 32 / kG;

@@ -261,6 +261,25 @@ class LocalBASolver:
         return dict(R=R, t=t, flags=flags, cost_hist=None if hist is None else hist.reshape(nF, mi + 1),
                     accepted=None if acc is None else acc.reshape(nF, max(mi, 1))[:, :mi], gpu_ms=float(ms.value))
 
+    def pose_ransac(self, intr, X, uv, n_hypotheses: int = 100, threshold_px: float = 3.0, seed: int = 42):
+        """Pose of one frame without a prior: RANSAC over minimal P3P samples on the device (`ba_pose_ransac_host`).
+        Returns dict(R (3,3), t (3,), n_inliers) or None when no hypothesis is admissible."""
+        intr = np.ascontiguousarray(intr, dtype=np.float64)
+        X = np.ascontiguousarray(X, dtype=np.float32).reshape(-1, 3)
+        uv = np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 2)
+        if X.shape[0] != uv.shape[0] or X.shape[0] < 4:
+            return None
+        R = np.zeros(9, dtype=np.float64)
+        t = np.zeros(3, dtype=np.float64)
+        n_in = C.c_int32(0)
+        with self._lock:
+            rc = self.lib.ba_pose_ransac_host(self._h, X.shape[0], _dptr(intr), _ptr(X), _ptr(uv), int(n_hypotheses),
+                                              float(threshold_px), int(seed) & 0xffffffff, _dptr(R), _dptr(t), C.byref(n_in))
+            _lib.check(self.lib, self._h, rc, "ba_pose_ransac_host")
+        if n_in.value <= 0:
+            return None
+        return dict(R=R.reshape(3, 3), t=t, n_inliers=int(n_in.value))
+
     # ------------------------------------------------------------------ inspection (tests)
     def debug_linearize(self, intr, R, t, fixed, X, obs_cam, obs_pt, obs_uv, pt_offsets, lam):
         """Run init + one linearise/Schur on device and return (S lower-valid, b, diagU, cost)."""
