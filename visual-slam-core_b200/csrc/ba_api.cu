@@ -513,7 +513,9 @@ static int enqueue_lm_loop(ba_handle* h, const Work& w, int schur, cudaStream_t 
     } else {
       launches += launch_rcs_cholesky(w, s);
     }
-    if (h->world > 1) {
+    static int no_bcast = -1;       // diagnostics only (BA_NO_BCAST=1): how much of the iteration is the broadcast
+    if (no_bcast < 0) { const char* e = getenv("BA_NO_BCAST"); no_bcast = (e && atoi(e)) ? 1 : 0; }
+    if (h->world > 1 && !no_bcast) {
       // the replicated solve ends in float64 REDs whose order differs from rank to rank: rank 0's camera step
       // and candidate poses go to everyone, so the replicated state stays bit-identical across ranks
       prof_mark(h, TAG_COMM, s);

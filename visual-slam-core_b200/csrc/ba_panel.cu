@@ -24,6 +24,7 @@
 //   fallback (every observation pair of the point -> float64 REDs); the window then moves to the panel's first
 //   camera (accumulators flushed by REDs, entries that are exactly zero skipped).
 #include <stdint.h>
+#include <stdio.h>
 
 #include "ba_kernels.cuh"
 #include "ba_scatter.cuh"
@@ -389,6 +390,7 @@ struct __align__(16) PanelSmem {
   int pnpts[kNG];
   int gbase[kNG];                       // the group's snapshot of cur_base for the panel it is staging
   int cur_base;                         // window base for the panels that start from now on
+  int n_rebase, n_fallback;             // diagnostics (-DBA_PANEL_TRACE)
 };
 
 // Y = W C of one observation: rows d = 0..2 of y[r][d], r = 0..5
@@ -629,6 +631,7 @@ k_schur_panel(const __grid_constant__ Work w) {
   if (tid == 0) {
     for (int g = 0; g < kNG; ++g) { mbar_init(&sm.bar[g][0], 1); mbar_init(&sm.bar[g][1], 1); sm.pbase[g] = 0; sm.pnpts[g] = 0; }
     sm.cur_base = 0;
+    sm.n_rebase = 0; sm.n_fallback = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -760,7 +763,7 @@ k_schur_panel(const __grid_constant__ Work w) {
           if (any_ahead || !any_fit) {                    // rare: only then is the panel's first camera needed
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) my_cmin = min(my_cmin, __shfl_xor_sync(kFull, my_cmin, o));
-            if (sl == 0 && my_cmin != 0x7fffffff) sm.cur_base = max(0, my_cmin - 3);
+            if (sl == 0 && my_cmin != 0x7fffffff) { sm.cur_base = max(0, my_cmin - 3); sm.n_rebase++; }
           }
         }
         if (sl == 0) { sm.pbase[g] = base; sm.pnpts[g] = npts; }
@@ -783,6 +786,9 @@ k_schur_panel(const __grid_constant__ Work w) {
             int i0 = e, i1 = e + 1;
             while (i0 > (o0 - a0) && si.pt[i0 - 1] - j0 == slot) --i0;
             while (i1 < (o0 - a0) + nob && si.pt[i1] - j0 == slot) ++i1;
+#ifdef BA_PANEL_TRACE
+            atomicAdd(&sm.n_fallback, 1);
+#endif
             pair_fallback(w, pose, si, e, i0, i1, X0, X1, X2, r.c, delta);
             continue;
           }
@@ -860,6 +866,10 @@ k_schur_panel(const __grid_constant__ Work w) {
       bar_arrive<kGL + 32 * kXW>(kBarFull + g);
     }
   }
+#ifdef BA_PANEL_TRACE
+  bar_sync<kNG * kGL>(kBarStageAll);
+  if (tid == 0 && w.dbg && (blockIdx.x % 16 == 0)) printf("cta %d: points %d panels %d rebases %d fallback observations %d\n", (int)blockIdx.x, p_hi - p_lo, n_panels, sm.n_rebase, sm.n_fallback);
+#endif
 }
 
 template <int kG>
