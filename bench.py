@@ -357,13 +357,22 @@ def time_resident(ctx, win, solver, steps, warmup):
 def time_e2e_abi(ctx, p, solver, steps, warmup):
     """The host-buffer C ABI with pinned host memory: H2D, solve, D2H inside the timed wall-clock region."""
     pin = ctx.pin
+    n_calls = max(warmup, 3) + steps
+    # the API refines R, t, X in place: every call gets its own pinned copy of the initial state, filled BEFORE the
+    # timed region, so that the region holds the call itself (H2D, solve, D2H) and no host-side reset copies
+    states = [(pin(p.R), pin(p.t), pin(p.X)) for _ in range(n_calls)] if p.X.nbytes * n_calls < 2e9 else None
     hR, ht, hX = pin(p.R), pin(p.t), pin(p.X)
     hfixed, hoc, hop, huv, hoff = pin(p.fixed), pin(p.obs_cam), pin(p.obs_pt), pin(p.obs_uv), pin(p.pt_offsets)
     hflags = pin(np.zeros(p.n_obs, dtype=np.uint8))
+    it = iter(states) if states is not None else None
 
     def e2e_step():
-        np.copyto(hR, p.R); np.copyto(ht, p.t); np.copyto(hX, p.X)
-        return solver.solve_local_inplace(p.intr, hR, ht, hfixed, hX, hoc, hop, huv, hoff, hflags)
+        if it is not None:
+            r_, t_, x_ = next(it)
+        else:
+            np.copyto(hR, p.R); np.copyto(ht, p.t); np.copyto(hX, p.X)
+            r_, t_, x_ = hR, ht, hX
+        return solver.solve_local_inplace(p.intr, r_, t_, hfixed, x_, hoc, hop, huv, hoff, hflags)
 
     res = None
     for _ in range(max(warmup, 3)):
@@ -383,16 +392,19 @@ def profile_kernels(ctx, win, solver_factory, lmcfg, max_iter, reps):
     """CUDA events around every kernel (no graph), same workload: ms per LM iteration per kernel class."""
     from visual_slam_core_b200 import LMConfig
     prof = solver_factory(LMConfig(profile=True, **lmcfg))
-    acc = np.zeros(5)
+    acc = np.zeros(7)
     r = None
     for i in range(reps + 2):
         r = win.solve(prof, ctx.stream, sync=True)
         if i >= 2:
-            acc += np.array([r.ms_linearize, r.ms_solve, r.ms_backsub, r.ms_other, r.ms_comm])
+            acc += np.array([r.ms_linearize, r.ms_solve, r.ms_backsub, r.ms_other, r.ms_comm, r.ms_point_blocks, r.ms_cam_blocks])
     acc /= reps
     k_ms = {"linearize_schur": acc[0] / max_iter, "rcs_solve": acc[1] / max_iter,
             "backsub_cost": acc[2] / max_iter, "init_finalize_per_step": acc[3],
             "nccl_allreduce": acc[4] / max_iter}
+    if acc[5] > 0:          # panel path: the three kernels of a linearisation, timed separately
+        k_ms["linearize_parts"] = {"point_blocks": acc[5] / max_iter, "cam_blocks": acc[6] / max_iter,
+                                   "schur_panel": (acc[0] - acc[5] - acc[6]) / max_iter}
     return k_ms, r
 
 
@@ -408,9 +420,20 @@ def roofline_block(cfg_name, p, k_ms, ms_per_iter, band_blocks=None):
     fp64_tf = flops / (lin_ms * 1e-3) / 1e12
     dom = max(("linearize_schur", "rcs_solve", "backsub_cost"), key=lambda k: k_ms[k])
     resident = b_iter < 100e6
+    parts = None
+    if "linearize_parts" in k_ms:
+        # what each of the three kernels of the panel path has to move (its own inputs once, its outputs once)
+        lp = k_ms["linearize_parts"]
+        own = {"point_blocks": 16 * p.n_obs + 24 * p.n_pt + 80 * p.n_pt + 96 * p.n_cam,
+               "cam_blocks": 12 * p.n_obs + 48 * p.n_obs + 96 * p.n_cam + 216 * p.n_cam,
+               "schur_panel": 16 * p.n_obs + 104 * p.n_pt + 96 * p.n_cam + (b_rjs - 17 * p.n_obs - 48 * p.n_pt - 72 * p.n_cam)}
+        parts = {k: {"launch_ms": lp[k], "bytes": own[k], "achieved": own[k] / (lp[k] * 1e-3) / 1e9,
+                     "frac": own[k] / (lp[k] * 1e-3) / 1e9 / peak} for k in lp if lp[k] > 0}
+        parts["dominant"] = max(lp, key=lambda k: lp[k])
     return {"bound": "hbm", "kernel": "linearise (residual + Jacobian + Schur)", "achieved": lin_gbs, "peak": peak,
             "unit": "GB/s", "frac": lin_gbs / peak, "traffic": ncu_traffic(cfg_name), "peak_source": peak_src,
             "algorithmic_bytes_per_launch": b_rjs, "launch_ms": lin_ms, "dominant_kernel_by_time": dom,
+            "kernels_of_the_linearisation": parts,
             "whole_iteration": {"algorithmic_bytes": b_iter, "achieved": b_iter / (ms_per_iter * 1e-3) / 1e9,
                                 "frac": b_iter / (ms_per_iter * 1e-3) / 1e9 / peak},
             "fp64": {"algorithmic_flop_per_launch": flops, "achieved_tflops": fp64_tf, "peak_tflops": FP64_PEAK_TFLOPS,
@@ -779,7 +802,8 @@ def run_b200(args, rank, local_rank, world):
     else:
         factory = lambda cfg: LocalBASolver(cfg, device=local_rank)   # noqa: E731
     k_ms, r_prof = profile_kernels(ctx, win, factory, lmcfg, max_iter, 3)
-    k_ms = {k: ctx.max_over_ranks(v) for k, v in k_ms.items()}
+    k_ms = {k: ({kk: ctx.max_over_ranks(vv) for kk, vv in v.items()} if isinstance(v, dict) else ctx.max_over_ranks(v))
+            for k, v in k_ms.items()}
     if world > 1:
         solver.set_config(LMConfig(**lmcfg))
     band_blocks = int(r_prof.s_blocks) if int(r_prof.band_width) >= 0 else None

@@ -109,6 +109,8 @@ typedef struct ba_report {
   int32_t band_width;                   /* BA_SOLVER_BAND: co-visibility bandwidth in keyframes, else -1 */
   int32_t s_blocks;                     /* 6x6 blocks of the reduced camera matrix that are stored / all-reduced */
   float ms_comm;                        /* profile=1, sharded: NCCL all-reduces (reduced camera system, candidate cost + accept) */
+  float ms_point_blocks;                /* profile=1, panel path: the point-block pass inside ms_linearize */
+  float ms_cam_blocks;                  /* profile=1, panel path: the camera-major pass inside ms_linearize */
 } ba_report;
 
 typedef struct ba_handle ba_handle;

@@ -108,10 +108,10 @@ struct ba_handle {
   std::vector<cudaEvent_t> prof_ev;
   std::vector<int> prof_tag;
   int prof_n = 0;
-  float prof_ms[5] = {0, 0, 0, 0, 0};
+  float prof_ms[7] = {0, 0, 0, 0, 0, 0, 0};
 };
 
-enum { TAG_LIN = 0, TAG_SOLVE = 1, TAG_BACK = 2, TAG_OTHER = 3, TAG_COMM = 4 };
+enum { TAG_LIN = 0, TAG_SOLVE = 1, TAG_BACK = 2, TAG_OTHER = 3, TAG_COMM = 4, TAG_LIN_PB = 5, TAG_LIN_CAM = 6 };
 
 static void prof_mark(ba_handle* h, int tag, cudaStream_t s) {
   if (!h->prm.profile) return;
@@ -126,8 +126,20 @@ static void prof_mark(ba_handle* h, int tag, cudaStream_t s) {
   h->prof_n++;
 }
 
+// reserve an event slot (recorded by the callee) that closes the interval of `tag_before` and opens one of `tag`
+static cudaEvent_t prof_slot(ba_handle* h, int tag) {
+  if (h->prof_n >= (int)h->prof_ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->prof_ev.push_back(e);
+    h->prof_tag.push_back(0);
+  }
+  h->prof_tag[h->prof_n] = tag;
+  return h->prof_ev[h->prof_n++];
+}
+
 static void prof_collect(ba_handle* h) {
-  for (int i = 0; i < 5; ++i) h->prof_ms[i] = 0.f;
+  for (int i = 0; i < 7; ++i) h->prof_ms[i] = 0.f;
   for (int i = 0; i + 1 < h->prof_n; ++i) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]) == cudaSuccess)
@@ -478,8 +490,8 @@ static int pick_schur(const ba_handle* h, const Work& w) {
   return kind;
 }
 
-static int launch_linearize(const Work& w, int schur, int sm_count, cudaStream_t s) {
-  if (schur == BA_SCHUR_PANEL) return launch_linearize_panel(w, sm_count, s);
+static int launch_linearize(const Work& w, int schur, int sm_count, cudaStream_t s, cudaEvent_t* marks = nullptr) {
+  if (schur == BA_SCHUR_PANEL) return launch_linearize_panel(w, sm_count, s, marks);
   if (schur == BA_SCHUR_MMA) return launch_linearize_mma(w, sm_count, s);
   if (schur == BA_SCHUR_STREAM) return launch_linearize_stream(w, sm_count, s);
   if (schur == BA_SCHUR_TILED) return launch_linearize_tiled(w, sm_count, s);
@@ -493,9 +505,13 @@ static int enqueue_lm_loop(ba_handle* h, const Work& w, int schur, cudaStream_t 
   const bool sparse = w.bsr_bits != nullptr;
   const int pcg_grid = sparse ? pcg_grid_size(w.n_cam, h->sm_count) : 0;
   for (int it = 0; it < h->prm.max_iter; ++it) {
-    prof_mark(h, TAG_LIN, s);
     {
-      const int nl = launch_linearize(w, schur, h->sm_count, s);
+      // profile mode, panel path: the three kernels of a linearisation are timed separately
+      cudaEvent_t marks[2];
+      const bool split = h->prm.profile && schur == BA_SCHUR_PANEL;
+      prof_mark(h, split ? TAG_LIN_PB : TAG_LIN, s);
+      if (split) { marks[0] = prof_slot(h, TAG_LIN_CAM); marks[1] = prof_slot(h, TAG_LIN); }
+      const int nl = launch_linearize(w, schur, h->sm_count, s, split ? marks : nullptr);
       if (nl < 0) { h->err = std::string("linearise launch: ") + cudaGetErrorString(cudaGetLastError()); return BA_ERR_CUDA; }
       launches += nl;
     }
@@ -570,7 +586,9 @@ static void fill_report(const ba_handle* h, const LmCtl* c, ba_report* rep, int 
   }
   rep->gpu_ms = ms;
   rep->n_launches = launches;
-  rep->ms_linearize = h->prof_ms[TAG_LIN];
+  rep->ms_linearize = h->prof_ms[TAG_LIN] + h->prof_ms[TAG_LIN_PB] + h->prof_ms[TAG_LIN_CAM];
+  rep->ms_point_blocks = h->prof_ms[TAG_LIN_PB];
+  rep->ms_cam_blocks = h->prof_ms[TAG_LIN_CAM];
   rep->ms_solve = h->prof_ms[TAG_SOLVE];
   rep->ms_backsub = h->prof_ms[TAG_BACK];
   rep->ms_other = h->prof_ms[TAG_OTHER];

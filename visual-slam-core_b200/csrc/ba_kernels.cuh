@@ -98,7 +98,7 @@ int launch_linearize_tiled(const Work& w, int sm_count, cudaStream_t s);
 int launch_linearize_stream(const Work& w, int sm_count, cudaStream_t s);
 int configure_stream();
 int launch_linearize_mma(const Work& w, int sm_count, cudaStream_t s);
-int launch_linearize_panel(const Work& w, int sm_count, cudaStream_t s);   // point blocks + camera blocks + Schur panels
+int launch_linearize_panel(const Work& w, int sm_count, cudaStream_t s, cudaEvent_t* marks = nullptr);   // point blocks + camera blocks + Schur panels
 int launch_panel_setup(const Work& w, int sm_count, cudaStream_t s);       // once per solve: camera-sorted observations
 int configure_panel();
 int panel_window();

@@ -913,18 +913,21 @@ int launch_panel_setup(const Work& w, int sm_count, cudaStream_t s) {
   return 3;
 }
 
-int launch_linearize_panel(const Work& w, int sm_count, cudaStream_t s) {
+int launch_linearize_panel(const Work& w, int sm_count, cudaStream_t s, cudaEvent_t* marks) {
+  // marks (profile mode, else null): events after the point-block pass and after the camera pass
   // lanes per point of the point-block pass: the mean observation count picks it
   const double mean_k = w.n_pt > 0 ? (double)w.n_obs / (double)w.n_pt : 0.0;
   if (mean_k <= 6.0) launch_pb<4>(w, sm_count, s);
   else if (mean_k <= 12.0) launch_pb<8>(w, sm_count, s);
   else if (mean_k <= 24.0) launch_pb<16>(w, sm_count, s);
   else launch_pb<32>(w, sm_count, s);
+  if (marks) cudaEventRecord(marks[0], s);
   {
     const int warps = (w.cs_nblk_max + kCamBlocksPerWarp - 1) / kCamBlocksPerWarp;
     const int blocks = (warps + 7) / 8;
     k_cam_blocks<<<blocks < 1 ? 1 : blocks, 256, 0, s>>>(w);
   }
+  if (marks) cudaEventRecord(marks[1], s);
   k_schur_panel<<<w.part_n, kThreadsP, sizeof(PanelSmem), s>>>(w);
   return 3;
 }

@@ -174,6 +174,7 @@ class LocalBASolver:
             n_iter=k, gpu_ms=float(rep.gpu_ms), n_launches=int(rep.n_launches),
             extra=dict(ms_linearize=float(rep.ms_linearize), ms_solve=float(rep.ms_solve),
                        ms_backsub=float(rep.ms_backsub), ms_other=float(rep.ms_other), ms_comm=float(rep.ms_comm),
+                       ms_point_blocks=float(rep.ms_point_blocks), ms_cam_blocks=float(rep.ms_cam_blocks),
                        solver_used={1: "cholesky", 2: "pcg", 3: "band"}.get(int(rep.solver_used), "?"),
                        band_width=int(rep.band_width), s_blocks=int(rep.s_blocks)))
 
