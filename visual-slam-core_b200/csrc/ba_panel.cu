@@ -393,6 +393,14 @@ struct __align__(16) PanelSmem {
   int n_rebase, n_fallback;             // diagnostics (-DBA_PANEL_TRACE)
 };
 
+// Where a window should start so that it holds a point AND the widest point the co-visibility band allows around the same
+// place: the centre of the point's cameras minus half the band, minus one.  (Starting at the panel's first camera minus a
+// margin left the rare 16-keyframe point behind the window for a whole run of panels: ten such points made one CTA three
+// times slower than the rest, and the kernel with it.)
+__device__ __forceinline__ int window_start(int cmin, int cmax, int half_band) {
+  return ((cmin + cmax) >> 1) - half_band - 1;
+}
+
 // Y = W C of one observation: rows d = 0..2 of y[r][d], r = 0..5
 struct YObs { double y[6][3]; };
 
@@ -624,15 +632,33 @@ k_schur_panel(const __grid_constant__ Work w) {
   const double* __restrict__ X = w.X[cur];
   const double* __restrict__ rec = w.rec;
   const bool sliding = w.n_cam > kWin;
+  const int half_band = (min(w.band_w >= 0 ? w.band_w : kWin - 1, kWin - 3) + 1) >> 1;   // half the widest camera span a point can have
 
   const int p_lo = __ldg(w.part + blockIdx.x), p_hi = __ldg(w.part + blockIdx.x + 1);
   const int n_panels = (p_hi - p_lo + kPP - 1) / kPP;
+#ifdef BA_PANEL_TRACE
+  const long long t_start = clock64();
+#endif
 
   if (tid == 0) {
     for (int g = 0; g < kNG; ++g) { mbar_init(&sm.bar[g][0], 1); mbar_init(&sm.bar[g][1], 1); sm.pbase[g] = 0; sm.pnpts[g] = 0; }
     sm.cur_base = 0;
     sm.n_rebase = 0; sm.n_fallback = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (sliding && tid < 32) {
+    // the window starts where this CTA's points start (three cameras before the first camera of its first 32 points);
+    // starting every CTA at camera 0 sent the first two panels of each through the pair fallback: a fixed ~0.15-0.7 ms
+    // per launch, the whole kernel time of a small shard
+    int c = 0x7fffffff;
+    if (p_lo + tid < p_hi) {
+      const Rec& r = reinterpret_cast<const Rec*>(rec)[p_lo + tid];
+      if (!((((unsigned)r.cmaxf) >> 28) & kFlagSkip)) c = window_start(r.cmin, r.cmaxf & 0x0fffffff, half_band);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c = min(c, __shfl_xor_sync(kFull, c, o));
+    __syncwarp();
+    if (tid == 0 && c != 0x7fffffff) sm.cur_base = max(0, c);
   }
   __syncthreads();
 
@@ -727,46 +753,53 @@ k_schur_panel(const __grid_constant__ Work w) {
       const int o0 = sm.bounds[n - sc0], o1 = sm.bounds[n - sc0 + 1];
       const int a0 = o0 & ~3;
       const int nob = o1 - o0;
-      const int base = sliding ? sm.gbase[g] : 0;
       const bool overflow = nob > kOB;                    // more observations than the stage holds: fallback, from global memory
+      // Window base of THIS panel, decided by every warp on its own from the same records (no barrier): the group's
+      // snapshot, unless a point of the panel lies beyond the window's end or nothing of the panel fits -- then the window
+      // moves now, to window_start() of the panel's points, and the mma warps flush their accumulators when they see the
+      // new base.  (Moving it only for LATER panels sent the points that triggered the move through the pair fallback,
+      // ~50-100 k clk per point: one such point made a CTA of a small shard a third slower than the others.)  A point
+      // that starts before the window never moves it back: it takes the fallback.
+      int base = 0;
+      bool moved = false;
+      Rec myrec;
+      myrec.cmin = 0x7fffffff; myrec.cmaxf = kFlagSkip << 28;
+      if (lane < npts) myrec = reinterpret_cast<const Rec*>(si.rec)[lane];
+      const int my_flags = ((unsigned)myrec.cmaxf) >> 28, my_cmax = myrec.cmaxf & 0x0fffffff;
+      if (sliding) {
+        base = sm.gbase[g];
+        const bool live = !(my_flags & kFlagSkip);
+        const bool ahead = live && my_cmax >= base + kWin;
+        const bool fits = live && myrec.cmin >= base && my_cmax < base + kWin;
+        if (__any_sync(kFull, ahead) || !__any_sync(kFull, fits)) {
+          int ws = live ? window_start(myrec.cmin, my_cmax, half_band) : 0x7fffffff;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) ws = min(ws, __shfl_xor_sync(kFull, ws, o));
+          if (ws != 0x7fffffff && max(0, ws) != base) { base = max(0, ws); moved = true; }
+        }
+      }
 
       // the panel buffer is free again once the mma warps have consumed this group's previous panel
       if (it >= 1) bar_sync<kGL + 32 * kXW>(kBarEmpty + g);
       pmark(w, tr, 8 * (n - 8) + 3, 10 * n + 4);
 
-      // slot intervals + window bookkeeping by the group's service warp
+      // slot intervals + the books, by the group's service warp
       if (sl >= 0) {
-        int my_cmin = 0x7fffffff;
-        bool ahead = false, fits_any = false;
         if (sl < npts) {
-          const Rec& r = reinterpret_cast<const Rec*>(si.rec)[sl];
-          const int flags = ((unsigned)r.cmaxf) >> 28, cmax = r.cmaxf & 0x0fffffff;
           int iv = 0xff;                                  // no interval: skipped by the mma warps
-          if (!(flags & kFlagSkip)) {
-            const bool fits = r.cmin >= base && cmax < base + kWin;
-            if (fits && !(flags & kFlagFallback) && !overflow) {
-              const int lo = (6 * (r.cmin - base)) >> 4, hi = (6 * (cmax - base) + 5) >> 4;   // super-tiles of 16 columns
+          if (!(my_flags & kFlagSkip)) {
+            const bool fits = myrec.cmin >= base && my_cmax < base + kWin;
+            if (fits && !(my_flags & kFlagFallback) && !overflow) {
+              const int lo = (6 * (myrec.cmin - base)) >> 4, hi = (6 * (my_cmax - base) + 5) >> 4;   // super-tiles of 16 columns
               iv = lo | (hi << 4);
             }
-            fits_any = fits;
-            ahead = cmax >= base + kWin;                  // the window is exhausted in the direction the points move
-            my_cmin = r.cmin;
           }
           sm.piv[g][sl] = (unsigned char)iv;
         }
-        if (sliding) {
-          // The window only moves when a point lies beyond its end, or when nothing of the panel fits; a point
-          // that starts before the window (a wide point among narrow ones) takes the fallback without moving it.
-          // New base: three cameras before the panel's first camera, so that wider points of the same
-          // neighbourhood still fit.
-          const bool any_ahead = __any_sync(kFull, ahead), any_fit = __any_sync(kFull, fits_any);
-          if (any_ahead || !any_fit) {                    // rare: only then is the panel's first camera needed
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) my_cmin = min(my_cmin, __shfl_xor_sync(kFull, my_cmin, o));
-            if (sl == 0 && my_cmin != 0x7fffffff) { sm.cur_base = max(0, my_cmin - 3); sm.n_rebase++; }
-          }
+        if (sl == 0) {
+          sm.pbase[g] = base; sm.pnpts[g] = npts;
+          if (moved) { sm.cur_base = base; sm.n_rebase++; }
         }
-        if (sl == 0) { sm.pbase[g] = base; sm.pnpts[g] = npts; }
       }
 
       pmark(w, tr, 8 * (n - 8) + 4, 10 * n + 5);
@@ -868,7 +901,7 @@ k_schur_panel(const __grid_constant__ Work w) {
   }
 #ifdef BA_PANEL_TRACE
   bar_sync<kNG * kGL>(kBarStageAll);
-  if (tid == 0 && w.dbg && (blockIdx.x % 16 == 0)) printf("cta %d: points %d panels %d rebases %d fallback observations %d\n", (int)blockIdx.x, p_hi - p_lo, n_panels, sm.n_rebase, sm.n_fallback);
+  if (tid == 0 && w.dbg) printf("cta %d: points %d panels %d rebases %d fallback observations %d clocks %lld\n", (int)blockIdx.x, p_hi - p_lo, n_panels, sm.n_rebase, sm.n_fallback, clock64() - t_start);
 #endif
 }
 
