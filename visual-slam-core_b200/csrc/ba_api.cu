@@ -522,7 +522,7 @@ static int enqueue_lm_loop(ba_handle* h, const Work& w, int schur, cudaStream_t 
     }
     prof_mark(h, TAG_SOLVE, s);
     if (w.band_w >= 0) {
-      launches += w.bcr_ws ? launch_rcs_bcr(w, w.bcr_ws, s) : launch_rcs_band(w, s);
+      launches += w.bcr_ws ? launch_rcs_bcr(w, w.bcr_ws, s, h->sm_count) : launch_rcs_band(w, s);
     } else if (sparse) {
       if (launch_rcs_pcg(w, pcg_grid, s) < 0) { h->err = std::string("cooperative PCG launch: ") + cudaGetErrorString(cudaGetLastError()); return BA_ERR_CUDA; }
       launches += 1;

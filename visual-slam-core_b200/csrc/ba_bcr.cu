@@ -145,44 +145,74 @@ k_bcr_assemble(Work w, double* __restrict__ D, double* __restrict__ L, double* _
   if (i == 0 && tid == 0) *w.cost_lin = 0.0;
 }
 
-// next level = the even super-blocks; their couplings start from zero
-__global__ void __launch_bounds__(256)
-k_bcr_next(const double* __restrict__ D, const double* __restrict__ b, double* __restrict__ D2,
-           double* __restrict__ L2, double* __restrict__ b2) {
-  const int j = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-  for (int e = tid; e < kD; e += nt) D2[(size_t)j * kD + e] = D[(size_t)(2 * j) * kD + e];
-  for (int e = tid; e < kL; e += nt) L2[(size_t)j * kL + e] = 0.0;
-  for (int e = tid; e < kV; e += nt) b2[(size_t)j * kV + e] = b[(size_t)(2 * j) * kV + e];
+// block index of the lower triangle -> (row, column)
+__device__ __forceinline__ void tri_decode(int blk, int& p, int& q) {
+  p = (int)((sqrtf(8.0f * (float)blk + 1.0f) - 1.0f) * 0.5f);
+  while (p * (p + 1) / 2 > blk) --p;
+  while ((p + 1) * (p + 2) / 2 <= blk) ++p;
+  q = blk - p * (p + 1) / 2;
+}
+
+// acc[2][6] += Pa[2 rows][6] * Pb[6][6]^T   (two rows of one 6x6 block product)
+__device__ __forceinline__ void mac2(const double* __restrict__ Pa, const double* __restrict__ Pb, double* acc) {
+  double a0[6], a1[6];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) { a0[q] = Pa[q]; a1[q] = Pa[6 + q]; }
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      const double bq = Pb[6 * c + q];
+      acc[c] = fma(a0[q], bq, acc[c]);
+      acc[6 + c] = fma(a1[q], bq, acc[6 + c]);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
-// elimination of the odd super-blocks of one level (or of the last remaining super-block)
+// elimination of the odd super-blocks of one level (or of the last remaining super-block), phase 1.
+// R CTAs per super-block: the partial Cholesky of the tall panel needs no exchange between block ROWS of the
+// two neighbour panels (row I of E only ever reads the D part of the same column), so every CTA factors the 15 x 15
+// diagonal part redundantly and carries its own slice of the 30 neighbour rows -- the depth of a level is the
+// 15 column steps of ONE small panel, not of 45 rows.  Tasks are two rows of a 6x6 block (72 FMAs), so that a column
+// step is one or two rounds over the 512 threads.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kET, 1)
-k_bcr_elim(int N, const double* __restrict__ D, const double* __restrict__ L, const double* __restrict__ b,
-           double* __restrict__ F, double* __restrict__ D2, double* __restrict__ L2, double* __restrict__ b2,
-           int* fail) {
+k_bcr_elim(int N, int R, const double* __restrict__ D, const double* __restrict__ L, const double* __restrict__ b,
+           double* __restrict__ F, int* fail) {
   extern __shared__ double sm[];
   double* __restrict__ A = sm;                      // kCells cells
   double* __restrict__ y = A + kCells * kCS;        // rhs row
   double* __restrict__ Dinv = y + kV;
   __shared__ int s_fail;
+  if (*(volatile int*)fail) return;                 // an earlier level failed: the finish kernel zeroes the step
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int e_idx = blockIdx.x;
+  const int e_idx = blockIdx.x / R, rk = blockIdx.x - e_idx * R;
   const int i = (N == 1) ? 0 : 2 * e_idx + 1;
   const bool has1 = (N > 1);                        // left neighbour i-1 (always there for an odd block)
   const bool has2 = (N > 1) && (i + 1 < N);
+  if (!has1 && rk != 0) return;
+  // my slice [s0, s1) of the stacked neighbour rows: 0..14 = E1 (keyframes of i-1), 15..29 = E2 (keyframes of i+1)
+  const int rp = (2 * kSB + R - 1) / R;
+  const int slim = has2 ? 2 * kSB : (has1 ? kSB : 0);
+  const int s0 = min(rk * rp, slim), s1 = min(s0 + rp, slim);
+  const int nEr = s1 - s0;
 
   if (tid == 0) s_fail = 0;
-  // ---- load: D_i, E1 = L_i^T (rows = keyframes of i-1), E2 = L_(i+1) (rows = keyframes of i+1) ---------
+  // ---- load: D_i, my rows of E1 = L_i^T and E2 = L_(i+1), the rhs --------------------------------------
   for (int e = tid; e < kD; e += nt) A[(e / 36) * kCS + (e % 36)] = D[(size_t)i * kD + e];
-  for (int e = tid; e < kL; e += nt) {
-    const int blk = e / 36, q = e - 36 * blk;
-    const int a = blk / kSB, c = blk - kSB * a;     // E1 block (a, c), element q = (r, cc)
-    const int r = q / 6, cc = q - 6 * r;
-    // (L_i[c][a])^T : element (r, cc) = L_i block (c, a) element (cc, r)
-    A[(kDB + blk) * kCS + q] = has1 ? L[(size_t)i * kL + (c * kSB + a) * 36 + cc * 6 + r] : 0.0;
-    A[(kDB + kLB + blk) * kCS + q] = has2 ? L[(size_t)(i + 1) * kL + e] : 0.0;
+  for (int e = tid; e < nEr * kSB * 36; e += nt) {
+    const int bl = e / 36, q = e - 36 * bl;
+    const int s = s0 + bl / kSB, c = bl % kSB;
+    double v;
+    if (s < kSB) {
+      // (L_i[c][s])^T : element (r, cc) = L_i block (c, s) element (cc, r)
+      const int r = q / 6, cc = q - 6 * r;
+      v = L[(size_t)i * kL + (c * kSB + s) * 36 + cc * 6 + r];
+    } else {
+      v = L[(size_t)(i + 1) * kL + ((s - kSB) * kSB + c) * 36 + q];
+    }
+    A[(kDB + s * kSB + c) * kCS + q] = v;
   }
   for (int e = tid; e < kV; e += nt) y[e] = b[(size_t)i * kV + e];
   __syncthreads();
@@ -218,20 +248,21 @@ k_bcr_elim(int N, const double* __restrict__ D, const double* __restrict__ L, co
   if (tid == 0) factor_diag(0);
   __syncthreads();
 
-  // ---- phase 1: right-looking partial Cholesky over the 15 block columns ---------------------------
+  // ---- right-looking partial Cholesky over the 15 block columns ------------------------------------
   for (int K = 0; K < kSB; ++K) {
     if (s_fail) break;                             // uniform: written before the last barrier
     const int mD = kSB - 1 - K;                    // rows of D below the diagonal block
     {
-      // panel: rows below in D, every row of E1 / E2, the rhs row:  v <- v * L_KK^-T
+      // panel: rows below in D, my rows of E1 / E2, the rhs row:  v <- v * L_KK^-T
       const double* __restrict__ Lk = A + cell(K, K);
       const double* __restrict__ di = Dinv + 6 * K;
-      const int nrow = 6 * (mD + 2 * kSB) + 1;
+      const int nrow = 6 * (mD + nEr) + 1;
       for (int row = tid; row < nrow; row += nt) {
         double* v;
         if (row < nrow - 1) {
-          const int I = K + 1 + row / 6;
-          v = A + cell(I, K) + 6 * (row % 6);
+          const int br = row / 6;
+          const int I = br < mD ? K + 1 + br : kSB + s0 + (br - mD);
+          v = A + cell(I, K) + 6 * (row - 6 * br);
         } else {
           v = y + 6 * K;
         }
@@ -249,55 +280,38 @@ k_bcr_elim(int N, const double* __restrict__ D, const double* __restrict__ L, co
       }
     }
     __syncthreads();
-    // trailing: blocks (I, J), K < J <= 14, J <= I <= 44; then the rhs rows
-    const int nD = mD * (mD + 1) / 2, nE = 2 * kSB * mD;
-    for (int t = tid; t < nD + nE + mD; t += nt) {
-      if (t < nD + nE) {
+    // trailing: blocks (I, J), K < J <= 14, I >= J in D or one of my neighbour rows, two rows per task; the rhs rows
+    const int nD = mD * (mD + 1) / 2, nE = nEr * mD;
+    const int nfine = 3 * (nD + nE);
+    for (int t = tid; t < nfine + mD; t += nt) {
+      if (t < nfine) {
+        const int blk = t / 3, part = t - 3 * blk;
         int I, J;
-        if (t < nD) {
-          int a = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-          while (a * (a + 1) / 2 > t) --a;
-          while ((a + 1) * (a + 2) / 2 <= t) ++a;
+        if (blk < nD) {
+          int a, c;
+          tri_decode(blk, a, c);
           I = K + 1 + a;
-          J = K + 1 + (t - a * (a + 1) / 2);
+          J = K + 1 + c;
         } else {
-          const int u = t - nD;
-          I = kSB + u / mD;
+          const int u = blk - nD;
+          I = kSB + s0 + u / mD;
           J = K + 1 + u % mD;
         }
-        const double* __restrict__ Aik = A + cell(I, K);
+        const double* __restrict__ Aik = A + cell(I, K) + 12 * part;
         const double* __restrict__ Ajk = A + cell(J, K);
-        double* __restrict__ Aij = A + cell(I, J);
-        double bj[36];
+        double* __restrict__ Aij = A + cell(I, J) + 12 * part;
+        double acc[12];
 #pragma unroll
-        for (int q = 0; q < 36; ++q) bj[q] = Ajk[q];
+        for (int q = 0; q < 12; ++q) acc[q] = 0.0;
+        mac2(Aik, Ajk, acc);
 #pragma unroll
-        for (int r = 0; r < 6; r += 2) {
-          double a0[6], a1[6], c0[6], c1[6];
-#pragma unroll
-          for (int q = 0; q < 6; ++q) {
-            a0[q] = Aik[6 * r + q];
-            a1[q] = Aik[6 * r + 6 + q];
-            c0[q] = Aij[6 * r + q];
-            c1[q] = Aij[6 * r + 6 + q];
-          }
-#pragma unroll
-          for (int q = 0; q < 6; ++q) {
-#pragma unroll
-            for (int c = 0; c < 6; ++c) {
-              c0[c] = fma(-a0[q], bj[6 * c + q], c0[c]);
-              c1[c] = fma(-a1[q], bj[6 * c + q], c1[c]);
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 6; ++q) {
-            Aij[6 * r + q] = c0[q];
-            Aij[6 * r + 6 + q] = c1[q];
-          }
+        for (int q = 0; q < 12; ++q) Aij[q] -= acc[q];
+        if (t < 3) {                               // look-ahead: block (K+1,K+1) is final once its three parts are
+          __syncwarp(0x7u);
+          if (t == 0) factor_diag(K + 1);
         }
-        if (t == 0) factor_diag(K + 1);            // look-ahead: block (K+1,K+1) is final now
       } else {
-        const int J = K + 1 + (t - nD - nE);
+        const int J = K + 1 + (t - nfine);
         const double* __restrict__ Ajk = A + cell(J, K);
         const double* yk = y + 6 * K;
         double* yj = y + 6 * J;
@@ -315,79 +329,122 @@ k_bcr_elim(int N, const double* __restrict__ D, const double* __restrict__ L, co
   __syncthreads();
   if (s_fail) {
     if (tid == 0) atomicOr(fail, 1);
-    return;                                        // the finish kernel zeroes the step
+    return;
   }
 
-  // ---- factors to global memory for the back substitution -------------------------------------------
+  // ---- factors to global memory: my neighbour rows; the first CTA also C, 1/diag and y ------------------
   double* __restrict__ Fe = F + (size_t)e_idx * kFac;
-  for (int e = tid; e < kD; e += nt) Fe[e] = A[(e / 36) * kCS + (e % 36)];
-  for (int e = tid; e < kV; e += nt) { Fe[kD + e] = Dinv[e]; Fe[kD + kV + 2 * kL + e] = y[e]; }
-  for (int e = tid; e < 2 * kL; e += nt) Fe[kD + kV + e] = A[(kDB + e / 36) * kCS + (e % 36)];
-  if (!has1) return;
+  if (rk == 0) {
+    for (int e = tid; e < kD; e += nt) Fe[e] = A[(e / 36) * kCS + (e % 36)];
+    for (int e = tid; e < kV; e += nt) { Fe[kD + e] = Dinv[e]; Fe[kD + kV + 2 * kL + e] = y[e]; }
+  }
+  for (int e = tid; e < nEr * kSB * 36; e += nt) {
+    const int bl = s0 * kSB + e / 36;
+    Fe[kD + kV + (size_t)bl * 36 + (e % 36)] = A[(kDB + bl) * kCS + (e % 36)];
+  }
+}
 
-  // ---- phase 2: Schur complement onto the even neighbours (next-level indices (i-1)/2, (i+1)/2) ------
-  const int jl = (i - 1) / 2, jr = (i + 1) / 2;
-  const int n_out = kDB + (has2 ? kDB + kLB : 0);
-  for (int t = tid; t < n_out + (has2 ? 2 : 1) * kSB; t += nt) {
-    if (t < n_out) {
-      int rowbase, colbase, p, q2;
-      double* dst;
-      if (t < kDB || (has2 && t < 2 * kDB)) {
-        const bool right = t >= kDB;
-        const int blk = right ? t - kDB : t;
-        p = (int)((sqrtf(8.0f * (float)blk + 1.0f) - 1.0f) * 0.5f);
-        while (p * (p + 1) / 2 > blk) --p;
-        while ((p + 1) * (p + 2) / 2 <= blk) ++p;
-        q2 = blk - p * (p + 1) / 2;
-        rowbase = colbase = right ? 2 * kSB : kSB;
-        dst = D2 + (size_t)(right ? jr : jl) * kD + (size_t)blk * 36;
+// ------------------------------------------------------------------------------------------
+// phase 2 of a level, gathered per super-block of the NEXT level (no REDs, no pre-copy, deterministic):
+//   D'_j = D_2j - E2(2j-1) E2(2j-1)^T - E1(2j+1) E1(2j+1)^T        ("D" CTAs)
+//   b'_j = b_2j - E2(2j-1) y(2j-1)    - E1(2j+1) y(2j+1)
+//   L'_j =      - E2(2j-1) E1(2j-1)^T                              ("L" CTAs; coupling of j to j-1)
+// P CTAs of each kind per super-block; a task is two rows of one output block, KS lanes share its 15 (30) block
+// products and add up with shuffles.
+// ------------------------------------------------------------------------------------------
+constexpr int kUT = 512;
+
+__global__ void __launch_bounds__(kUT, 1)
+k_bcr_update(int N, int P, int ksD, int ksL, const double* __restrict__ D, const double* __restrict__ b,
+             const double* __restrict__ F, double* __restrict__ D2, double* __restrict__ L2, double* __restrict__ b2,
+             const int* fail) {
+  extern __shared__ double sm[];
+  double* __restrict__ Ea = sm;                     // kLB cells
+  double* __restrict__ Eb = Ea + kLB * kCS;
+  double* __restrict__ ya = Eb + kLB * kCS;
+  double* __restrict__ yb = ya + kV;
+  if (*fail) return;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int j = blockIdx.x / (2 * P), rem = blockIdx.x - j * 2 * P;
+  const bool kindL = rem >= P;
+  const int part = kindL ? rem - P : rem;
+  const bool hasL = j >= 1, hasR = 2 * j + 1 < N;   // eliminated neighbours 2j-1 (index j-1) and 2j+1 (index j)
+  if (kindL && !hasL) return;                       // L'_0 is never read
+  const double* __restrict__ FL = F + (size_t)(hasL ? j - 1 : 0) * kFac;
+  const double* __restrict__ FR = F + (size_t)j * kFac;
+  // operands: Ea = E2 of the left elimination; Eb = E1 of the right one (D) / E1 of the left one (L)
+  const double* __restrict__ srcA = FL + kD + kV + kL;
+  const double* __restrict__ srcB = kindL ? FL + kD + kV : FR + kD + kV;
+  const bool useA = hasL, useB = kindL ? true : hasR;
+  for (int e = tid; e < kL; e += nt) {
+    const int at = (e / 36) * kCS + (e % 36);
+    if (useA) Ea[at] = srcA[e];
+    if (useB) Eb[at] = srcB[e];
+  }
+  if (!kindL) {
+    for (int e = tid; e < kV; e += nt) {
+      ya[e] = hasL ? FL[kD + kV + 2 * kL + e] : 0.0;
+      yb[e] = hasR ? FR[kD + kV + 2 * kL + e] : 0.0;
+    }
+  }
+  __syncthreads();
+  const int KS = kindL ? ksL : ksD;
+  const int n_fine = 3 * (kindL ? kLB : kDB);
+  const int per = (n_fine + P - 1) / P;
+  const int t0 = part * per, t1 = min(n_fine, t0 + per);
+  const int ks = tid % KS, slot = tid / KS, stride = nt / KS;
+  for (int base = t0; base < t1; base += stride) {  // uniform trip count: the shuffles below need whole warps
+    const int task = base + slot;
+    const bool active = task < t1;
+    const int blk = active ? task / 3 : 0, pr = active ? task - 3 * blk : 0;
+    int p, q;
+    if (kindL) { p = blk / kSB; q = blk - kSB * p; } else { tri_decode(blk, p, q); }
+    double acc[12];
+#pragma unroll
+    for (int x = 0; x < 12; ++x) acc[x] = 0.0;
+    if (active) {
+      if (kindL) {
+        for (int k = ks; k < kSB; k += KS) mac2(Ea + (p * kSB + k) * kCS + 12 * pr, Eb + (q * kSB + k) * kCS, acc);
       } else {
-        const int blk = t - 2 * kDB;
-        p = blk / kSB;
-        q2 = blk - kSB * p;
-        rowbase = 2 * kSB;                          // rows: keyframes of i+1 (E2)
-        colbase = kSB;                              // columns: keyframes of i-1 (E1)
-        dst = L2 + (size_t)jr * kL + (size_t)blk * 36;
+        if (hasL)
+          for (int k = ks; k < kSB; k += KS) mac2(Ea + (p * kSB + k) * kCS + 12 * pr, Ea + (q * kSB + k) * kCS, acc);
+        if (hasR)
+          for (int k = ks; k < kSB; k += KS) mac2(Eb + (p * kSB + k) * kCS + 12 * pr, Eb + (q * kSB + k) * kCS, acc);
       }
-      double acc[36];
+    }
+    for (int o = 1; o < KS; o <<= 1) {
 #pragma unroll
-      for (int q = 0; q < 36; ++q) acc[q] = 0.0;
+      for (int x = 0; x < 12; ++x) acc[x] += __shfl_xor_sync(kFull, acc[x], o);
+    }
+    if (active && ks == 0) {
+      const size_t at = (size_t)blk * 36 + 12 * pr;
+      if (kindL) {
+        double* __restrict__ dst = L2 + (size_t)j * kL + at;
+#pragma unroll
+        for (int x = 0; x < 12; ++x) dst[x] = -acc[x];
+      } else {
+        const double* __restrict__ src = D + (size_t)(2 * j) * kD + at;
+        double* __restrict__ dst = D2 + (size_t)j * kD + at;
+#pragma unroll
+        for (int x = 0; x < 12; ++x) dst[x] = src[x] - acc[x];
+      }
+    }
+  }
+  // rhs of the next level: the last D CTA (it has the fewest block tasks)
+  if (!kindL && part == P - 1) {
+    for (int o = tid; o < kV; o += nt) {
+      const int p = o / 6, r = o - 6 * p;
+      double a0 = 0.0, a1 = 0.0;
       for (int k = 0; k < kSB; ++k) {
-        const double* __restrict__ Pa = A + cell(rowbase + p, k);
-        const double* __restrict__ Pb = A + cell(colbase + q2, k);
-        double bj[36];
+        const double* __restrict__ Pa = Ea + (p * kSB + k) * kCS + 6 * r;
+        const double* __restrict__ Pb = Eb + (p * kSB + k) * kCS + 6 * r;
 #pragma unroll
-        for (int q = 0; q < 36; ++q) bj[q] = Pb[q];
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {
-          double a[6];
-#pragma unroll
-          for (int q = 0; q < 6; ++q) a[q] = Pa[6 * r + q];
-#pragma unroll
-          for (int c = 0; c < 6; ++c)
-#pragma unroll
-            for (int q = 0; q < 6; ++q) acc[6 * r + c] = fma(a[q], bj[6 * c + q], acc[6 * r + c]);
+        for (int q = 0; q < 6; ++q) {
+          if (hasL) a0 = fma(Pa[q], ya[6 * k + q], a0);
+          if (hasR) a1 = fma(Pb[q], yb[6 * k + q], a1);
         }
       }
-#pragma unroll
-      for (int q = 0; q < 36; ++q) atomicAdd(dst + q, -acc[q]);
-    } else {
-      // rhs: b_left -= E1 y, b_right -= E2 y   (one keyframe row block per task)
-      const int u = t - n_out;
-      const bool right = u >= kSB;
-      const int p = right ? u - kSB : u;
-      const int rowbase = right ? 2 * kSB : kSB;
-      double acc[6] = {0, 0, 0, 0, 0, 0};
-      for (int k = 0; k < kSB; ++k) {
-        const double* __restrict__ Pa = A + cell(rowbase + p, k);
-#pragma unroll
-        for (int r = 0; r < 6; ++r)
-#pragma unroll
-          for (int q = 0; q < 6; ++q) acc[r] = fma(Pa[6 * r + q], y[6 * k + q], acc[r]);
-      }
-      double* dst = b2 + (size_t)(right ? jr : jl) * kV + 6 * p;
-#pragma unroll
-      for (int r = 0; r < 6; ++r) atomicAdd(dst + r, -acc[r]);
+      b2[(size_t)j * kV + o] = b[(size_t)(2 * j) * kV + o] - (a0 + a1);
     }
   }
 }
@@ -395,13 +452,17 @@ k_bcr_elim(int N, const double* __restrict__ D, const double* __restrict__ L, co
 // ------------------------------------------------------------------------------------------
 // back substitution of one level:  x_i = C^-T (y - E1^T x_(i-1) - E2^T x_(i+1))
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1)
+constexpr int kBT = 512;
+constexpr int kBSlices = 5;                        // the 15 neighbour keyframes in 5 slices of 3
+
+__global__ void __launch_bounds__(kBT, 1)
 k_bcr_back(int N, int shift, const double* __restrict__ F, double* __restrict__ x, const int* fail) {
   extern __shared__ double sm[];
   double* __restrict__ C = sm;                      // kDB cells
   double* __restrict__ Linv = C + kDB * kCS;        // inverse diagonal factors
   double* __restrict__ v = Linv + kSB * 36;
   double* __restrict__ xs = v + kV;
+  double* __restrict__ ps = xs + kV;                // kBSlices x kV partial sums
   if (*fail) return;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
   const int e_idx = blockIdx.x;
@@ -412,32 +473,41 @@ k_bcr_back(int N, int shift, const double* __restrict__ F, double* __restrict__ 
   const double* __restrict__ E1 = Fe + kD + kV;
   const double* __restrict__ E2 = E1 + kL;
   const double* __restrict__ yv = E2 + kL;
-  const double* __restrict__ xl = has1 ? x + ((size_t)(i - 1) << shift) * kV : x;
-  const double* __restrict__ xr = has2 ? x + ((size_t)(i + 1) << shift) * kV : x;
-  for (int e = tid; e < kD; e += nt) C[(e / 36) * kCS + (e % 36)] = Fe[e];
-  // v_c = y_c - sum_a E1[a][c]^T x_left,a - sum_a E2[a][c]^T x_right,a     (one scalar per thread)
-  for (int t = tid; t < kV; t += nt) {
-    const int c = t / 6, cc = t - 6 * c;
-    double a0 = yv[t], a1 = 0.0;
+  const double* xl = has1 ? x + ((size_t)(i - 1) << shift) * kV : x;
+  const double* xr = has2 ? x + ((size_t)(i + 1) << shift) * kV : x;
+  // partial sums of  E1[a][c]^T x_left,a + E2[a][c]^T x_right,a  over a slice of a   (one scalar per thread)
+  if (tid < kBSlices * kV) {
+    const int sl = tid / kV, o = tid - sl * kV;
+    const int c = o / 6, cc = o - 6 * c;
+    double a0 = 0.0, a1 = 0.0;
     if (has1) {
-      for (int a = 0; a < kSB; ++a) {
+#pragma unroll
+      for (int a = 3 * sl; a < 3 * sl + 3; ++a) {
         const double* __restrict__ B = E1 + (a * kSB + c) * 36 + cc;
 #pragma unroll
-        for (int r = 0; r < 6; ++r) a0 = fma(-B[6 * r], xl[6 * a + r], a0);
+        for (int r = 0; r < 6; ++r) a0 = fma(B[6 * r], xl[6 * a + r], a0);
       }
     }
     if (has2) {
-      for (int a = 0; a < kSB; ++a) {
+#pragma unroll
+      for (int a = 3 * sl; a < 3 * sl + 3; ++a) {
         const double* __restrict__ B = E2 + (a * kSB + c) * 36 + cc;
 #pragma unroll
-        for (int r = 0; r < 6; ++r) a1 = fma(-B[6 * r], xr[6 * a + r], a1);
+        for (int r = 0; r < 6; ++r) a1 = fma(B[6 * r], xr[6 * a + r], a1);
       }
     }
-    v[t] = a0 + a1;
+    ps[tid] = a0 + a1;
   }
+  for (int e = tid; e < kD; e += nt) C[(e / 36) * kCS + (e % 36)] = Fe[e];
   __syncthreads();
-  for (int t = tid; t < 6 * kSB; t += nt) {
+  if (tid < kV) {
+    double a = yv[tid];
+#pragma unroll
+    for (int sl = 0; sl < kBSlices; ++sl) a -= ps[sl * kV + tid];
+    v[tid] = a;
+  } else if (tid >= 96 && tid < 96 + 6 * kSB) {
     // column j of the inverse of the lower-triangular diagonal factor of block K
+    const int t = tid - 96;
     const int K = t / 6, j = t - 6 * K;
     const double* __restrict__ Lk = C + (K * (K + 1) / 2 + K) * kCS;
     double col[6];
@@ -529,7 +599,8 @@ __global__ void k_bcr_flag(Work w, int* fail) {
 }
 
 size_t elim_smem() { return sizeof(double) * (kCells * kCS + 2 * kV + 8); }
-size_t back_smem() { return sizeof(double) * (kDB * kCS + kSB * 36 + 2 * kV + 8); }
+size_t update_smem() { return sizeof(double) * (2 * kLB * kCS + 2 * kV + 8); }
+size_t back_smem() { return sizeof(double) * (kDB * kCS + kSB * 36 + (2 + kBSlices) * kV + 8); }
 
 }  // namespace
 
@@ -540,31 +611,45 @@ size_t bcr_workspace_doubles(int n_cam) { return make_plan(n_cam).total; }
 int configure_bcr() {
   cudaError_t e = cudaFuncSetAttribute(k_bcr_elim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)elim_smem());
   if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_bcr_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem());
+  if (e == cudaSuccess)
     e = cudaFuncSetAttribute(k_bcr_back, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)back_smem());
   return e == cudaSuccess ? 0 : (int)e;
 }
 
-int launch_rcs_bcr(const Work& w, double* ws, cudaStream_t s) {
+// lanes that share one task of the update kernel: as many (1, 2 or 4) as keep one round of tasks inside the CTA
+static int pick_ks(int n_fine, int P) {
+  const int per = (n_fine + P - 1) / P;
+  return per * 4 <= kUT ? 4 : (per * 2 <= kUT ? 2 : 1);
+}
+
+int launch_rcs_bcr(const Work& w, double* ws, cudaStream_t s, int sm_count) {
   const BcrPlan p = make_plan(w.n_cam);
   int* fail = reinterpret_cast<int*>(ws + p.off_fail);
   double* x = ws + p.off_x;
   int launches = 0;
+  if (sm_count <= 0) sm_count = 148;
   k_bcr_assemble<<<p.N[0], 256, 0, s>>>(w, ws + p.off_D[0], ws + p.off_L[0], ws + p.off_b[0], fail);
   ++launches;
   for (int l = 0; l < p.n_levels; ++l) {
-    const int N = p.N[l];
-    double *D2 = nullptr, *L2 = nullptr, *b2 = nullptr;
+    const int N = p.N[l], ne = elim_count(N);
+    // CTAs per eliminated super-block: the SMs the level leaves idle, up to 8 (4 neighbour rows each)
+    const int R = N == 1 ? 1 : std::max(1, std::min(8, sm_count / ne));
+    k_bcr_elim<<<ne * R, kET, elim_smem(), s>>>(N, R, ws + p.off_D[l], ws + p.off_L[l], ws + p.off_b[l],
+                                                ws + p.off_F[l], fail);
+    ++launches;
     if (N > 1) {
-      D2 = ws + p.off_D[l + 1]; L2 = ws + p.off_L[l + 1]; b2 = ws + p.off_b[l + 1];
-      k_bcr_next<<<p.N[l + 1], 256, 0, s>>>(ws + p.off_D[l], ws + p.off_b[l], D2, L2, b2);
+      const int N2 = p.N[l + 1];
+      const int P = std::max(1, std::min(8, sm_count / (2 * N2)));
+      k_bcr_update<<<N2 * 2 * P, kUT, update_smem(), s>>>(N, P, pick_ks(3 * kDB, P), pick_ks(3 * kLB, P),
+                                                          ws + p.off_D[l], ws + p.off_b[l], ws + p.off_F[l],
+                                                          ws + p.off_D[l + 1], ws + p.off_L[l + 1], ws + p.off_b[l + 1],
+                                                          fail);
       ++launches;
     }
-    k_bcr_elim<<<elim_count(N), kET, elim_smem(), s>>>(N, ws + p.off_D[l], ws + p.off_L[l], ws + p.off_b[l],
-                                                      ws + p.off_F[l], D2, L2, b2, fail);
-    ++launches;
   }
   for (int l = p.n_levels - 1; l >= 0; --l) {
-    k_bcr_back<<<elim_count(p.N[l]), 256, back_smem(), s>>>(p.N[l], l, ws + p.off_F[l], x, fail);
+    k_bcr_back<<<elim_count(p.N[l]), kBT, back_smem(), s>>>(p.N[l], l, ws + p.off_F[l], x, fail);
     ++launches;
   }
   int blocks = (w.n_cam + 255) / 256;

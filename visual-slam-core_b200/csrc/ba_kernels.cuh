@@ -121,7 +121,7 @@ int launch_rcs_band(const Work& w, cudaStream_t s);
 bool bcr_supported(int n_cam, int band_w);
 size_t bcr_workspace_doubles(int n_cam);
 int configure_bcr();
-int launch_rcs_bcr(const Work& w, double* ws, cudaStream_t s);
+int launch_rcs_bcr(const Work& w, double* ws, cudaStream_t s, int sm_count = 0);
 int configure_band();
 int band_max_w();
 int launch_backsub(const Work& w, int sm_count, cudaStream_t s);
