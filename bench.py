@@ -463,15 +463,29 @@ def plugin_leg(p, device_index, max_iter, reps=5):
     R0 = [np.array(kf.R_w2c, dtype=np.float64) for kf in kfs]
     t0 = [np.array(kf.t_w2c, dtype=np.float64).reshape(3, 1) for kf in kfs]
     X0 = [np.array(mp.position, dtype=np.float64) for mp in mps]
-    total, ok = [], True
-    for _ in range(reps + 2):                               # the first calls create the solver and capture the graph
+    total, inner, site, ok = [], [], [], True
+
+    def reset():
         for kf, R, t in zip(kfs, R0, t0):
             kf.set_pose_Rt(R.copy(), t.copy())
         for mp, x in zip(mps, X0):
             mp.update_position(x.copy())
+
+    for _ in range(reps + 2):                               # the first calls create the solver and capture the graph
+        reset()
         t_a = time.perf_counter()
-        ok = bool(m.optimize_local(opt, kfs)) and ok
+        ok = bool(m.optimize_local(opt, kfs)) and ok        # the reference's own Map.optimize_local (its Python collection loop included)
         total.append(time.perf_counter() - t_a)
+    window_points = handlers.collect_window_points(kfs)
+    for _ in range(reps):
+        reset()
+        t_a = time.perf_counter()
+        ok = bool(opt.optimize_local(kfs, window_points)) and ok     # the plugin alone: pack + H2D + solve + D2H + write-back
+        inner.append(time.perf_counter() - t_a)
+        reset()
+        t_a = time.perf_counter()
+        ok = bool(handlers.local_optimize(opt, kfs)) and ok          # this repo's call site: C collection + the plugin + both mean errors
+        site.append(time.perf_counter() - t_a)
     res = opt.last_result
     t_a = time.perf_counter()
     pts = handlers.collect_window_points(kfs)
@@ -481,7 +495,8 @@ def plugin_leg(p, device_index, max_iter, reps=5):
     packing.write_back(kfs, pts, pw.R, pw.t, pw.X)
     t_d = time.perf_counter()
     timed = total[2:]
-    return {"seconds_per_call": statistics.median(timed), "ok": ok, "result": res,
+    return {"seconds_per_call": statistics.median(timed), "seconds_plugin_only": statistics.median(inner),
+            "seconds_call_site": statistics.median(site), "ok": ok, "result": res,
             "breakdown_ms": {"collect": 1e3 * (t_b - t_a), "pack": 1e3 * (t_c - t_b), "write_back": 1e3 * (t_d - t_c)},
             "packer": getattr(opt, "packer_name", "pack_window"),
             "h2d": int(pw.R.nbytes + pw.t.nbytes + pw.fixed.nbytes + pw.X.nbytes + pw.obs_cam.nbytes + pw.obs_uv.nbytes + pw.pt_offsets.nbytes),
@@ -530,8 +545,13 @@ def bench_window(ctx, cfg_name, args, with_cpu=True):
         out["e2e"] = {"value": max_iter / pl["seconds_per_call"], "unit": UNIT, "ms_per_call": 1e3 * pl["seconds_per_call"],
                       "h2d_bytes_per_step": pl["h2d"], "d2h_bytes_per_step": pl["d2h"], "ok": pl["ok"],
                       "breakdown_ms": pl["breakdown_ms"], "packer": pl["packer"],
-                      "api": "Map.optimize_local(B200Optimizer, keyframes): object graph in, objects mutated (collection + "
-                             "packing + H2D + solve + D2H + write-back, wall clock)"}
+                      "api": "Map.optimize_local(B200Optimizer, keyframes): object graph in, objects mutated (the reference's own "
+                             "Python collection loop, map/map.py:159-169, + packing + H2D + solve + D2H + write-back, wall clock)",
+                      "ms_plugin_only": 1e3 * pl["seconds_plugin_only"],
+                      "plugin_only_api": "B200Optimizer.optimize_local(keyframes, points): what the swapped-in class itself costs",
+                      "ms_call_site": 1e3 * pl["seconds_call_site"],
+                      "call_site_api": "handlers.local_optimize(optimizer, keyframes): collection in C + the plugin + mean "
+                                       "reprojection error before / after (LocalHandler.local_optimize restated)"}
     except Exception as e:                                  # never costs the bench line
         out["e2e"] = {"error": repr(e)}
     if with_cpu:

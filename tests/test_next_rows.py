@@ -445,3 +445,88 @@ def test_local_optimize_call_site_needs_more_than_two_keyframes():
     p = synth.make_problem("T0", seed=2)
     cam, kfs, mps = refgraph.graph_from_problem(p)
     assert handlers.local_optimize(B200Optimizer(log_dir=None), kfs[:2]) is False     # local_handler.py:37-40
+
+
+# ---------------------------------------------------------------------------------------------
+# C helpers of the host path: window collection, table selection, direct write-back
+# ---------------------------------------------------------------------------------------------
+def _python_collect(keyframes):
+    unique = {}
+    for kf in keyframes:
+        for mp in kf.get_all_mappoints().values():
+            unique[id(mp)] = mp
+    return list(unique.values())
+
+
+def test_collect_points_in_c_matches_the_reference_loop():
+    fp = packing._fastpack
+    if fp is None or not hasattr(fp, "collect_points"):
+        pytest.skip("C extension not built")
+    p = synth.make_problem("T2", seed=11)
+    cam, kfs, mps = refgraph.graph_from_problem(p)
+    got = fp.collect_points(kfs)
+    want = _python_collect(kfs)
+    assert len(got) == len(want) and all(a is b for a, b in zip(got, want))
+    assert fp.collect_points(tuple(kfs)) is None                  # not an exact list: the Python loop runs
+    assert handlers.collect_window_points(tuple(kfs))[0] is want[0]
+    assert fp.collect_points([]) == []
+
+
+def test_table_select_in_c_equals_the_numpy_selection():
+    fp = packing._fastpack
+    if fp is None or not hasattr(fp, "table_select"):
+        pytest.skip("C extension not built")
+    p = synth.make_problem("T2", seed=12)
+    table = packing.ObservationTable()
+    table.install(refgraph.MapPoint)
+    try:
+        cam, kfs, mps = refgraph.graph_from_problem(p)
+        # tombstones, an out-of-range keypoint index, a keyframe outside the window
+        kfs[1].remove_map_point(0, next(iter(kfs[1].map_points))[1])
+        mps[3].add_observation(kfs[2].keyframe_id + 1000, 0, 5)
+        win = kfs[1:]                                              # the first keyframe's observations drop out
+        pts = _python_collect(win)
+        ref = packing.pack_window(win, pts)
+        got = table.pack(win, pts)
+        saved, packing._fastpack = packing._fastpack, None         # the numpy path of the same method
+        try:
+            slow = table.pack(win, pts)
+        finally:
+            packing._fastpack = saved
+        for a in ("R", "t", "fixed", "X", "obs_cam", "obs_pt", "obs_uv", "obs_cam_id", "pt_offsets"):
+            np.testing.assert_array_equal(getattr(got, a), getattr(ref, a), err_msg=a)
+            np.testing.assert_array_equal(getattr(slow, a), getattr(ref, a), err_msg=a)
+        assert got.obs_cam.dtype == np.int32 and got.obs_uv.dtype == np.float32 and got.pt_offsets.dtype == np.int32
+    finally:
+        table.uninstall()
+
+
+def test_direct_write_back_only_for_the_plain_update_position():
+    class Plain:
+        def __init__(self):
+            import threading
+            self._lock = threading.RLock()
+            self.position = np.zeros(3)
+
+        def update_position(self, new_position):
+            with self._lock:
+                self.position = np.asarray(new_position, dtype=float)
+
+    class Recording(Plain):
+        def update_position(self, new_position):
+            super().update_position(new_position)
+            self.touched = True
+
+    assert packing._plain_update_position(Plain) and not packing._plain_update_position(Recording)
+    assert packing._plain_update_position(refgraph.MapPoint)
+    X = np.arange(12, dtype=np.float64).reshape(4, 3)
+    a, b = [Plain() for _ in range(4)], [Recording() for _ in range(4)]
+    packing.write_back_points(a, X)
+    packing.write_back_points(b, X)
+    mixed = [Plain(), Recording(), Plain(), Recording()]
+    packing.write_back_points(mixed, X)
+    for lst in (a, b, mixed):
+        for j, mp in enumerate(lst):
+            np.testing.assert_array_equal(mp.position, X[j])
+            assert mp.position.dtype == np.float64
+    assert all(getattr(mp, "touched", False) for mp in b) and mixed[1].touched and mixed[3].touched

@@ -36,6 +36,11 @@ def mean_reprojection_error(pw: packing.PackedWindow, R: Optional[np.ndarray] = 
 def collect_window_points(keyframes: List[Any]) -> List[Any]:
     """`Map.optimize_local`'s collection (`map/map.py:159-169`): points of every keyframe in order,
     deduplicated by identity, first occurrence kept."""
+    fp = packing._fastpack
+    if fp is not None and hasattr(fp, "collect_points") and isinstance(keyframes, list):
+        out = fp.collect_points(keyframes)               # the same walk in C (csrc/fastpack.c)
+        if out is not None:
+            return out
     unique = {}
     for kf in keyframes:
         for mp in kf.get_all_mappoints().values():
@@ -52,15 +57,16 @@ def local_optimize(optimizer, keyframes: List[Any], logger=None, cull: bool = Fa
     log = logger or optimizer.logger
     if len(keyframes) <= 2:
         return False
+    if table is not None and hasattr(optimizer, "table"):
+        optimizer.table = table                          # pack from this table instead of the process-wide one
     points = collect_window_points(keyframes)
-    pw = table.pack(keyframes, points) if table is not None else packing.pack_window(keyframes, points)
-    log.info(f"[Local Optimize] mean reprojection error before: {mean_reprojection_error(pw):.3f}px")
     ok = optimizer.optimize_local(keyframes, points)
     log.info(f"[Local Optimize] finished: success={ok}")
     if ok and optimizer.last_result is not None:
-        res = optimizer.last_result
-        log.info(f"[Local Optimize] mean reprojection error after: "
-                 f"{mean_reprojection_error(optimizer.last_packed, res.R, res.t, res.X):.3f}px")
+        # the window is packed once, by the optimizer; its snapshot holds the poses and points from before the solve
+        res, pw = optimizer.last_result, optimizer.last_packed
+        log.info(f"[Local Optimize] mean reprojection error before: {mean_reprojection_error(pw):.3f}px, "
+                 f"after: {mean_reprojection_error(pw, res.R, res.t, res.X):.3f}px")
         if cull:
             optimizer.cull_bad_points(keyframes, points)
     return ok

@@ -247,12 +247,43 @@ def gather_points(map_points: List[Any]):
     return X, keys
 
 
+def _update_position_template(self, new_position):
+    with self._lock:
+        self.position = np.asarray(new_position, dtype=float)
+
+
+_PLAIN_UPDATE = {}
+
+
+def _plain_update_position(cls) -> bool:
+    """True when `cls.update_position` is, instruction for instruction, the reference's
+    `with self._lock: self.position = np.asarray(new_position, dtype=float)` (`map/map_point.py:61-63`): the
+    write-back may then store the float64 row as `mp.position` directly (what `np.asarray` would return; a single
+    attribute store, atomic under the GIL, which is all the lock around it protects).  Any other implementation --
+    a subclass that records the change, another dtype -- keeps the per-point method call."""
+    hit = _PLAIN_UPDATE.get(cls)
+    if hit is None:
+        fn = getattr(cls, "update_position", None)
+        code, ref = getattr(fn, "__code__", None), _update_position_template.__code__
+        hit = bool(code is not None and code.co_code == ref.co_code and code.co_names == ref.co_names
+                   and code.co_consts == ref.co_consts and code.co_varnames == ref.co_varnames
+                   and getattr(getattr(fn, "__globals__", {}).get("np"), "__name__", "") == "numpy"
+                   and not hasattr(cls, "__slots__") and "position" not in vars(cls))
+        _PLAIN_UPDATE[cls] = hit
+    return hit
+
+
 def write_back_points(map_points: List[Any], X: np.ndarray) -> None:
     """`mp.update_position(X[j])` for every point (`torch_optimizer.py:201-203`), the loop in C when it can be."""
     X = np.ascontiguousarray(X, dtype=np.float64)
-    if _fastpack is not None and hasattr(_fastpack, "scatter_points") and isinstance(map_points, list):
-        if _fastpack.scatter_points(map_points, X):
-            return
+    if _fastpack is not None and hasattr(_fastpack, "scatter_points") and isinstance(map_points, list) and map_points:
+        cls = type(map_points[0])
+        try:
+            if _fastpack.scatter_points(map_points, X, cls if _plain_update_position(cls) else None):
+                return
+        except TypeError:                               # an older build of the extension: two arguments
+            if _fastpack.scatter_points(map_points, X):
+                return
     for mp, pos in zip(map_points, X):
         mp.update_position(pos)
 
@@ -545,14 +576,30 @@ class ObservationTable:
                     at += a.shape[0]
             Xd, mp_keys = gather_points(map_points)
             X = Xd.astype(np.float32).astype(np.float64)
+            if n_pt:
+                known = self._known
+                key_list = mp_keys.tolist()
+                if not known.issuperset(key_list):
+                    for j, k in enumerate(key_list):
+                        if k not in known:
+                            self.ingest(map_points[j])
+            uv_all = np.concatenate(uv_parts) if uv_parts else np.zeros((0, 2), dtype=np.float32)
+            n = self._n
+            if _fastpack is not None and hasattr(_fastpack, "table_select"):
+                # selection, skip rules and the counting sort by point in one C pass over the table's rows
+                sel = _fastpack.table_select(self._kf, self._mp, self._cam, self._kp, self._alive.view(np.uint8), self._grp, n,
+                                             kf_ids, np.ascontiguousarray(mp_keys), n_sens, base, count, base.shape[1],
+                                             np.ascontiguousarray(uv_all))
+                if sel is not None:
+                    pt_offsets = np.frombuffer(sel[3], dtype=np.int32)
+                    return PackedWindow(intr=intr, R=R, t=t, fixed=fixed, X=X,
+                                        obs_cam=np.frombuffer(sel[0], dtype=np.int32),
+                                        obs_pt=np.repeat(np.arange(n_pt, dtype=np.int32), np.diff(pt_offsets)),
+                                        obs_uv=np.frombuffer(sel[2], dtype=np.float32).reshape(-1, 2),
+                                        obs_cam_id=np.frombuffer(sel[1], dtype=np.int32), pt_offsets=pt_offsets)
             if n_pt and np.unique(mp_keys).shape[0] != n_pt:        # a point handed in twice: its rows would be needed twice
                 self.stats["fallbacks"] += 1
                 return None
-            if n_pt:
-                known = self._known
-                for j, k in enumerate(mp_keys.tolist()):
-                    if k not in known:
-                        self.ingest(map_points[j])
 
             n = self._n
             # key -> window row through a lookup table when the ids are small integers (the reference's global
@@ -579,7 +626,6 @@ class ObservationTable:
                 o = np.lexsort((rows, self._grp[rows], pt_row))
             cam_row, pt_row, cid = cam_row[o], pt_row[o], cid[o]
             src = (base[cam_row, cc[o]] + kpi[o])
-            uv_all = np.concatenate(uv_parts) if uv_parts else np.zeros((0, 2), dtype=np.float32)
             pt_offsets = np.zeros(n_pt + 1, dtype=np.int32)
             if n_pt:
                 np.cumsum(np.bincount(pt_row, minlength=n_pt), out=pt_offsets[1:])
