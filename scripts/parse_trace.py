@@ -8,11 +8,13 @@ for tok in line.split()[2:]:
     t += int(d)
     ev[int(tag)] = t
 names = {1: "group barrier", 2: "issue", 3: "mbar wait", 4: "empty wait", 5: "bookkeeping", 6: "obs loop"}
-for n in range(8, 16):
+for n in range(200, 208):
     st = [ev.get(10 * n + k) for k in range(1, 7)]
     mm = [ev.get(1000 + 10 * n + k) for k in range(1, 4)]
     steps = [tg - 5000 for tg in ev if 5000 <= tg < 6000 and ev[tg] > (mm[2] or 0) - 1 and ev[tg] < (mm[2] or 0) + 400]
     s = f"panel {n}: staging " + " ".join(f"{names[k + 1]} {st[k] - st[k - 1]}" for k in range(1, 6) if st[k] and st[k - 1])
+    if ev.get(10 * n + 7) and st[0]:
+        s += f" [issue: to expect_tx {ev[10 * n + 7] - st[0]}, expect_tx {ev[10 * n + 8] - ev[10 * n + 7]}, copies {st[1] - ev[10 * n + 8]}]"
     if all(mm):
         s += f" | mma: masks {mm[1] - mm[0]}, tile loop {mm[2] - mm[1]}" + (f" ({steps[0]} steps)" if steps else "")
     print(s)

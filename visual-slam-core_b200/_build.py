@@ -35,19 +35,25 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu under csrc/ and link libb200ba.so next to this file."""
+def build(force: bool = False, verbose: bool = False, out: str = "", extra: List[str] = ()) -> str:
+    """Compile every .cu under csrc/ and link libb200ba.so next to this file.  `out` / `extra` build a diagnostic
+    variant (e.g. extra=["-DBA_PANEL_TRACE"]) under another name; `BA_LIB_PATH` makes `_lib.load()` pick it up."""
+    if out:
+        return _build_to(out, os.path.join(HERE, "build", "variant_" + os.path.basename(out)), list(extra), verbose)
     if not force and not _stale():
         return LIB_PATH
+    return _build_to(LIB_PATH, os.path.join(HERE, "build"), list(extra), verbose)
+
+
+def _build_to(lib_path: str, objdir: str, extra: List[str], verbose: bool) -> str:
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     objs = []
     log = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("BA_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("BA_NVCC_EXTRA", "").split(), *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, cmd, p in procs:
@@ -55,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         log.append(f"$ {' '.join(cmd)}\n{out}")
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
-    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+    cmd = [nvcc, "-shared", "-o", lib_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
            "-Xcompiler", "-fPIC", "-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log.append(f"$ {' '.join(cmd)}\n{r.stdout}")
@@ -65,7 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    return LIB_PATH
+    return lib_path
 
 
 # ---------------------------------------------------------------------------------------------

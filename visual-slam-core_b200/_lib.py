@@ -57,7 +57,8 @@ class B200BAError(RuntimeError):
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    # BA_LIB_PATH: a diagnostic build of the same library (_build.build(out=..., extra=[...])), never a fallback
+    return os.environ.get("BA_LIB_PATH") or _build.LIB_PATH
 
 
 def load(build_if_missing: bool = True) -> C.CDLL:

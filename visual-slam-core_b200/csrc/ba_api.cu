@@ -77,7 +77,8 @@ struct ba_handle {
   std::string err;
   // workspace
   DevBuf camstate, X0, X1, red, ctl, cand, dbg, part;
-  DevBuf rec, cs_cnt, cs_blk_off, cs_blk_cam, cs_pt, cs_uv, cs_nblk;   // panel linearise path   // camstate = pose[0] | pose[1] | dp, contiguous (one broadcast)
+  DevBuf rec, cs_cnt, cs_blk_off, cs_blk_cam, cs_pt, cs_uv, cs_nblk;   // panel linearise path
+  DevBuf ro_cnt, ro_perm, ro_off, ro_cam, ro_pt, ro_uv;                // panel path: class order of the points   // camstate = pose[0] | pose[1] | dp, contiguous (one broadcast)
   // sparse path: structure + PCG workspace
   DevBuf bits, wpre, row_nnz, row_ptr, col_idx, tpos, pcg, bits_all;
   // banded path: factor columns, forward-substituted rhs, inverse pivots, bandwidth scalar
@@ -283,7 +284,8 @@ extern "C" int ba_destroy(ba_handle* h) {
                     &h->d_R, &h->d_t, &h->d_fixed, &h->d_X, &h->d_ocam, &h->d_opt, &h->d_ouv,
                     &h->d_off, &h->d_flags, &h->d_hist, &h->d_acc, &h->d_foff, &h->dbg, &h->part,
                     &h->bits, &h->wpre, &h->row_nnz, &h->row_ptr, &h->col_idx, &h->tpos, &h->pcg,
-                    &h->bits_all, &h->band_L, &h->band_y, &h->band_dinv, &h->band_wbuf, &h->bcr};
+                    &h->bits_all, &h->band_L, &h->band_y, &h->band_dinv, &h->band_wbuf, &h->bcr,
+                    &h->ro_cnt, &h->ro_perm, &h->ro_off, &h->ro_cam, &h->ro_pt, &h->ro_uv};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
@@ -475,7 +477,13 @@ static int make_work(ba_handle* h, int n_cam, int n_pt, int n_obs, const double 
   return BA_OK;
 }
 
-static int pick_schur(const ba_handle* h, const Work& w) {
+static bool panel_reorder_enabled() {           // diagnostics: BA_PANEL_REORDER=0 keeps the caller's point order
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BA_PANEL_REORDER"); v = (e && !atoi(e)) ? 0 : 1; }
+  return v != 0;
+}
+
+static int pick_schur(const ba_handle* h, const Work& w, bool ignore_alignment = false) {
   int kind = h->prm.schur_kind;
   if (kind == BA_SCHUR_AUTO) {
     // lane-per-keyframe staging needs the cameras of consecutive points inside a 20-keyframe window:
@@ -486,7 +494,7 @@ static int pick_schur(const ba_handle* h, const Work& w) {
     kind = (w.n_cam <= mma_window()) ? BA_SCHUR_MMA : (seq ? BA_SCHUR_PANEL : BA_SCHUR_STREAM);
   }
   // the panel path needs its workspace and 16-byte aligned observation arrays (bulk copies); the round-1 kernel takes anything
-  if (kind == BA_SCHUR_PANEL && !panel_supported(w)) kind = BA_SCHUR_MMA;
+  if (kind == BA_SCHUR_PANEL && !ignore_alignment && !panel_supported(w)) kind = BA_SCHUR_MMA;
   return kind;
 }
 
@@ -616,7 +624,7 @@ extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t
   h->last_solver = mode == MODE_DENSE ? BA_SOLVER_CHOLESKY : (mode == MODE_BAND ? BA_SOLVER_BAND : BA_SOLVER_PCG);
   h->last_band_w = bw;
   h->last_s_blocks = (int)(w.s_len / 36);
-  const int schur = pick_schur(h, w);
+  int schur = pick_schur(h, w, /*ignore_alignment=*/true);
   LmInit li{h->prm.lambda0, h->prm.huber_delta, h->prm.chi2_thr, h->prm.lambda_up,
             h->prm.lambda_down, h->prm.lambda_min, h->prm.lambda_max, h->prm.accept_rtol};
 
@@ -625,6 +633,23 @@ extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t
   if (w.dbg) cudaMemsetAsync(w.dbg, 0, sizeof(long long) * 4096, s);
   CK(cudaEventRecord(h->ev0, s));
   prof_mark(h, TAG_OTHER, s);
+  if (schur == BA_SCHUR_PANEL && h->prm.max_iter > 0 && n_pt > 0 && n_obs > 0 && panel_reorder_enabled()) {
+    // the panel path works in its own point order (class order, ba_panel.cu): a permuted copy of the observations
+    // and offsets, built on the device once per solve; k_init / k_finalize translate points and flags
+    if ((rc = ensure(h, h->ro_cnt, sizeof(unsigned long long) * (panel_classes(n_cam) + 2)))) return rc;
+    if ((rc = ensure(h, h->ro_perm, sizeof(int) * (size_t)(n_pt + 1)))) return rc;
+    if ((rc = ensure(h, h->ro_off, sizeof(int) * (size_t)(n_pt + 1)))) return rc;
+    if ((rc = ensure(h, h->ro_cam, sizeof(int) * (size_t)(n_obs + 4)))) return rc;
+    if ((rc = ensure(h, h->ro_pt, sizeof(int) * (size_t)(n_obs + 4)))) return rc;
+    if ((rc = ensure(h, h->ro_uv, sizeof(float) * 2 * (size_t)(n_obs + 4)))) return rc;
+    PanelOrder po{(unsigned long long*)h->ro_cnt.p, (int*)h->ro_perm.p, (int*)h->ro_off.p,
+                  (int*)h->ro_cam.p, (int*)h->ro_pt.p, (float*)h->ro_uv.p};
+    launches += launch_panel_reorder(w, po, s);
+    w.perm = po.perm;
+    w.pt_off_in = pt_offsets;
+    w.obs_cam = po.cam; w.obs_pt = po.pt; w.obs_uv = po.uv; w.pt_off = po.off;
+  }
+  if (schur == BA_SCHUR_PANEL && !panel_supported(w)) schur = BA_SCHUR_MMA;
   launches += launch_init(w, cam_R, cam_t, X, li, s);
   if (schur == BA_SCHUR_PANEL && h->prm.max_iter > 0) launches += launch_panel_setup(w, h->sm_count, s);
   if (h->prm.max_iter == 0) {
@@ -642,7 +667,7 @@ extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t
     ba_handle::GraphKey key;
     key.n_cam = n_cam; key.n_pt = n_pt; key.n_obs = n_obs; key.max_iter = h->prm.max_iter;
     key.schur = schur; key.world = h->world;
-    const void* ptrs[10] = {cam_fixed, obs_cam, obs_pt, obs_uv, pt_offsets, w.S, w.pose[0], w.X[0], w.ctl, w.dp};
+    const void* ptrs[10] = {cam_fixed, w.obs_cam, w.obs_pt, w.obs_uv, w.pt_off, w.S, w.pose[0], w.X[0], w.ctl, w.dp};
     memcpy(key.ptrs, ptrs, sizeof(ptrs));
     key.scal[0] = intr[0]; key.scal[1] = intr[1]; key.scal[2] = intr[2]; key.scal[3] = intr[3];
     if (!(h->graph && key == h->graph_key)) {

@@ -37,6 +37,11 @@ struct Work {
   float2* cs_uv;                      // [32 cs_nblk_max]
   int* cs_nblk;                       // [1] blocks in use
   int cs_nblk_max;
+  // class order of the panel path (ba_panel.cu, launch_panel_reorder): when perm != null, obs_* / pt_off / X / rec are
+  // in the solver's own point order (points sorted by first camera and camera span) and position p holds the caller's
+  // point perm[p]; k_init / k_finalize translate, nothing else knows
+  const int* perm;                    // [n_pt]
+  const int* pt_off_in;               // [n_pt + 1] the caller's offsets (flags go back to the caller's observation order)
   // block-sparse reduced camera matrix (large windows); all null / 0 for the dense packed layout
   const unsigned* bsr_bits;           // [n_cam * bsr_W] structure bitmap (symmetric, diagonal set)
   const int* bsr_wpre;                // [n_cam * bsr_W] set bits before each word of its row
@@ -105,6 +110,19 @@ int panel_window();
 size_t panel_rec_doubles(int n_pt);
 int panel_cs_blocks_max(int n_cam, int n_obs);
 bool panel_supported(const Work& w);
+// class order (once per solve, before launch_init): points sorted by (first camera, camera span), observations copied
+// along.  Buffers are the caller's workspace: cnt [panel_classes + 1] 64-bit, perm [n_pt], off [n_pt + 1],
+// cam / pt [n_obs], uv [2 n_obs].  `w` keeps the caller's arrays; the caller switches the pointers afterwards.
+struct PanelOrder {
+  unsigned long long* cnt;
+  int* perm;
+  int* off;
+  int* cam;
+  int* pt;
+  float* uv;
+};
+size_t panel_classes(int n_cam);
+int launch_panel_reorder(const Work& w, const PanelOrder& o, cudaStream_t s);
 int configure_mma();
 int mma_grid(int n_cam, int n_pt, int sm_count);   // CTAs launch_linearize_mma will use
 int mma_window();

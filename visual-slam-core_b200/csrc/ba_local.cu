@@ -32,7 +32,15 @@ __global__ void k_init(Work w, const double* __restrict__ R_in, const double* __
     w.pose[0][i] = v;
     w.pose[1][i] = v;
   }
-  for (int i = tid; i < 3 * w.n_pt; i += nth) w.X[0][i] = X_in[i];
+  if (w.perm == nullptr) {
+    for (int i = tid; i < 3 * w.n_pt; i += nth) w.X[0][i] = X_in[i];
+  } else {
+    // class order of the panel path: position p holds the caller's point perm[p]
+    for (int i = tid; i < 3 * w.n_pt; i += nth) {
+      const int p = i / 3, c = i - 3 * p;
+      w.X[0][i] = X_in[3 * (size_t)__ldg(w.perm + p) + c];
+    }
+  }
   long long nred = (long long)w.s_len + 2 * w.n + 1;   // S | b | diagU | cost_lin contiguous
   for (long long i = tid; i < nred; i += nth) w.S[i] = 0.0;
   for (int i = tid; i < w.n; i += nth) w.dp[i] = 0.0;
@@ -847,10 +855,19 @@ __global__ void k_finalize(Work w, double* __restrict__ R_out, double* __restric
       double ru, rv;
       residual_only(w.K, pose + 12 * in.cam, pose + 12 * in.cam + 9, X[3 * j], X[3 * j + 1],
                     X[3 * j + 2], in.u, in.v, ru, rv);
-      flags[o] = (ru * ru + rv * rv) > chi2 ? 1 : 0;
+      const unsigned char f = (ru * ru + rv * rv) > chi2 ? 1 : 0;
+      if (w.perm == nullptr) flags[o] = f;
+      else flags[__ldg(w.pt_off_in + __ldg(w.perm + j)) + (o - __ldg(w.pt_off + j))] = f;   // the caller's observation order
     }
   }
-  for (int i = tid; i < 3 * w.n_pt; i += nth) X_out[i] = X[i];
+  if (w.perm == nullptr) {
+    for (int i = tid; i < 3 * w.n_pt; i += nth) X_out[i] = X[i];
+  } else {
+    for (int i = tid; i < 3 * w.n_pt; i += nth) {
+      const int p = i / 3, c = i - 3 * p;
+      X_out[3 * (size_t)__ldg(w.perm + p) + c] = X[i];
+    }
+  }
   for (int i = tid; i < 12 * w.n_cam; i += nth) {
     int c = i / 12, k = i % 12;
     if (k < 9) R_out[9 * c + k] = pose[i];

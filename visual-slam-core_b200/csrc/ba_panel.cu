@@ -35,12 +35,11 @@ namespace {
 
 constexpr int kWin = 20;                  // keyframes per window
 constexpr int kCols = 6 * kWin;            // 120 window columns
-constexpr int kPCols = 128;               // panel columns: 8 super-tiles of 16 (columns 120..127 stay zero)
+constexpr int kPCols = 128;               // panel columns: 16 tiles of 8 (columns 120..127 stay zero)
 constexpr int kYS = kPCols + 4;            // panel row stride in doubles: 132 = 4 (mod 16).  A fragment load reads
                                           // (lane & 3) * kYS + (lane >> 2): 4 a + b, a, b = 0..3, are sixteen different
                                           // 8-byte banks.  (120 = 8 mod 16, the round-1 stride, folds a = 0, 2 and 1, 3
                                           // onto each other: ncu counted 2 wavefronts per half-warp on every fragment load.)
-constexpr int kNS = kPCols / 16;           // 8 super-tile columns of 16 (2 x 2 mma tiles)
 constexpr int kPP = 12;                   // points per panel (one mma k-step each)
 constexpr int kRows = 4 * kPP;            // panel rows
 constexpr int kGW = 4;                    // warps per staging group
@@ -49,11 +48,11 @@ constexpr int kNG = 2;                    // staging groups (each owns one panel
 constexpr int kXW = 8;                    // mma warps
 constexpr int kThreadsP = 32 * (kNG * kGW + kXW);   // 512
 constexpr int kOB = 512;                  // observation capacity of a panel's staging buffers
-constexpr int kOwn = 5;                   // super-tiles per mma warp (36 of the lower triangle / 8 warps = 4 or 5)
 constexpr int kBoundsCap = 2048;          // panel boundaries staged per super-chunk
 constexpr int kBarFull = 1, kBarEmpty = 3, kBarGroup = 5, kBarStageAll = 7;
 constexpr int kRecD = 10;                 // doubles per point record
 constexpr int kFlagFallback = 1, kFlagSkip = 2;
+constexpr int kTrace0 = 200;              // first of the eight panels of CTA 0 the clock64 trace covers (-DBA_PANEL_TRACE)
 
 static_assert(kYS % 16 == 12 || kYS % 16 == 4, "panel stride must be 4 or 12 mod 16 doubles for conflict-free fragment loads");
 static_assert(kYS % 2 == 0, "rows must stay 16-byte aligned");
@@ -286,6 +285,78 @@ __global__ void k_cs_fill(Work w) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// class order (once per solve): points sorted by (first camera, camera span), a counting sort over n_cam x 32 classes.
+// A panel of 12 consecutive points then holds one or two classes, i.e. one or two camera intervals, and every strip of
+// the mma warps sees its live points as one run (see strip_runs).  In the caller's order (points sorted by an anchor
+// camera, 2..16 keyframes each) the live points of a strip were a scattered half of the panel.
+// Counters are 64-bit (points << 32 | observations) so that one atomic hands out a consistent (position, first
+// observation) pair; the order inside a class is whatever the atomics make it, the observations of a point keep theirs.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kSpanClasses = 32;
+__device__ __forceinline__ int point_class(const Work& w, int j, int& k) {
+  const int o0 = __ldg(w.pt_off + j);
+  k = __ldg(w.pt_off + j + 1) - o0;
+  if (k <= 0) return w.n_cam * kSpanClasses;            // no observation: behind everything
+  int cmin = 0x7fffffff, cmax = -1;
+  for (int i = 0; i < k; ++i) {
+    const int c = __ldg(w.obs_cam + o0 + i);
+    cmin = min(cmin, c);
+    cmax = max(cmax, c);
+  }
+  return cmin * kSpanClasses + min(cmax - cmin, kSpanClasses - 1);
+}
+__global__ void k_ro_count(Work w, unsigned long long* __restrict__ cnt) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int j = tid; j < w.n_pt; j += nth) {
+    int k;
+    const int key = point_class(w, j, k);
+    atomicAdd(cnt + key, (1ull << 32) | (unsigned long long)max(k, 0));
+  }
+}
+// one block: exclusive scan of the class counters in place (they become the scatter cursors)
+__global__ void k_ro_scan(unsigned long long* __restrict__ cnt, int n_classes) {
+  __shared__ unsigned long long s_part[1024];
+  __shared__ unsigned long long s_carry;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_carry = 0ull;
+  __syncthreads();
+  for (int base = 0; base < n_classes; base += 1024) {
+    const int a = base + tid;
+    const unsigned long long v = (a < n_classes) ? cnt[a] : 0ull;
+    s_part[tid] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {                 // Hillis-Steele inclusive scan
+      const unsigned long long t = (tid >= o) ? s_part[tid - o] : 0ull;
+      __syncthreads();
+      s_part[tid] += t;
+      __syncthreads();
+    }
+    if (a < n_classes) cnt[a] = s_carry + s_part[tid] - v;
+    __syncthreads();
+    if (tid == 1023) s_carry += s_part[1023];
+    __syncthreads();
+  }
+}
+__global__ void k_ro_scatter(Work w, PanelOrder o) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  if (tid == 0) o.off[w.n_pt] = w.n_obs;
+  for (int j = tid; j < w.n_pt; j += nth) {
+    int k;
+    const int key = point_class(w, j, k);
+    const unsigned long long at = atomicAdd(o.cnt + key, (1ull << 32) | (unsigned long long)max(k, 0));
+    const int pos = (int)(at >> 32), ob = (int)(at & 0xffffffffull);
+    o.perm[pos] = j;
+    o.off[pos] = ob;
+    const int o0 = __ldg(w.pt_off + j);
+    for (int i = 0; i < k; ++i) {
+      o.cam[ob + i] = __ldg(w.obs_cam + o0 + i);
+      o.pt[ob + i] = pos;
+      reinterpret_cast<float2*>(o.uv)[ob + i] = __ldg(reinterpret_cast<const float2*>(w.obs_uv) + o0 + i);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // k_cam_blocks
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kCamBlocksPerWarp = 8;      // 256 observations between two flushes
@@ -385,7 +456,7 @@ struct __align__(16) PanelSmem {
   StageIn in[kNG][2];
   uint64_t bar[kNG][2];                 // mbarriers of the input stages
   int bounds[kBoundsCap + 1];           // pt_off at the panel boundaries of this CTA (one super-chunk)
-  unsigned char piv[kNG][16];           // per point slot: first | last << 4 super-tile of the point's camera interval (0xff: none)
+  unsigned char piv[kNG][16];           // per point slot: first | last << 4 tile (8 columns) of the point's camera interval (0xff: none)
   int pbase[kNG];                       // window base the panel was staged with
   int pnpts[kNG];
   int gbase[kNG];                       // the group's snapshot of cur_base for the panel it is staging
@@ -394,11 +465,13 @@ struct __align__(16) PanelSmem {
 };
 
 // Where a window should start so that it holds a point AND the widest point the co-visibility band allows around the same
-// place: the centre of the point's cameras minus half the band, minus one.  (Starting at the panel's first camera minus a
-// margin left the rare 16-keyframe point behind the window for a whole run of panels: ten such points made one CTA three
-// times slower than the rest, and the kernel with it.)
-__device__ __forceinline__ int window_start(int cmin, int cmax, int half_band) {
-  return ((cmin + cmax) >> 1) - half_band - 1;
+// place.  Caller's order (points follow an anchor camera): the centre of the point's cameras minus half the band, minus
+// one.  (Starting at the panel's first camera minus a margin left the rare 16-keyframe point behind the window for a
+// whole run of panels: ten such points made one CTA three times slower than the rest, and the kernel with it.)
+// Class order (first cameras never fall): the point's first camera -- centring sent the window back and forth between
+// the narrow and the wide classes of one first camera (9-12 moves and ~500 fallback observations per CTA).
+__device__ __forceinline__ int window_start(int cmin, int cmax, int half_band, bool class_order) {
+  return class_order ? cmin : ((cmin + cmax) >> 1) - half_band - 1;
 }
 
 // Y = W C of one observation: rows d = 0..2 of y[r][d], r = 0..5
@@ -481,111 +554,134 @@ __device__ __forceinline__ void pmark(const Work& w, bool who, int slot, int tag
 // ---- mma warps ----------------------------------------------------------------------------------------------------
 // S -= Yt^T Yt per panel with mma.sync.m8n8k4.f64.  What shaped this loop (all measured):
 //  * eight per-warp code specialisations starved the instruction fetch (stall_no_instruction on top): ONE code sequence,
-//    which super-tile an accumulator stands for is data (c_own);
-//  * a predicated-off DMMA still occupies the tensor pipe (117 M issued for 28 M useful at C4) and ptxas turns
-//    `if (inside) dmma` into exactly that: trip counts must be data, not predicates;
-//  * with single 8 x 8 tiles the scalar work around each DMMA (bit scan, address, two loads, loop) was ~125 clk per DMMA
-//    on an in-order warp, five times the DMMA itself: the unit of work is a 16 x 16 SUPER-TILE (four DMMAs, three on the
-//    diagonal, fed by four fragment loads), and the loads of the next step are issued before the DMMAs of this one.
-// Loop nest: TILE-major inside a panel.  For each of my (at most 5) super-tiles a ballot says which of the panel's points
-// have it inside their camera interval; a loop over the set bits does the work.  All accumulators stay in registers for
-// the life of a window.
-__host__ __device__ constexpr int stile_owner(int si, int sj) { return (si + 5 * sj) & 7; }
+//    which tiles an accumulator stands for is data (c_own);
+//  * a predicated-off DMMA still occupies the tensor pipe and ptxas turns `if (inside) dmma` into exactly that: trip
+//    counts must be data, not predicates;
+//  * the tensor pipe takes one DMMA per 16.2 clk and sub-partition and a dependent DMMA can follow after 26 clk
+//    (scripts/dmma_latency.cu): two mma warps per sub-partition with one or two accumulators in flight each keep it full,
+//    so the unit of work can be small.  Round 2 started with 16 x 16 super-tiles (four DMMAs per four fragment loads); the
+//    clock64 trace showed the mma warps, not the staging, setting the pace (3.3 k of 4.2 k clk per panel): a point seen by
+//    eight keyframes touches 48 of the 128 columns at a random offset, i.e. 10 super-tiles = 36 DMMAs, dealt to 8 warps in
+//    lumps of 3-4 (the busiest warp had 8 per point against a mean of 4.5).
+//  * Now the unit is a STRIP: tile row i (8 columns) x strip column sj (16 columns) = the 8 x 8 tiles (i, 2 sj) and
+//    (i, 2 sj + 1), one A fragment and two B fragments for two DMMAs; the strip on the diagonal of an even row is the
+//    single tile (i, i).  64 strips in the lower triangle of the 15 x 15 tiles; warp (i + 3 sj) mod 8 owns a pair strip,
+//    warp 5 sj mod 8 the single one: 7 + 1 strips = 30 accumulator doubles per lane, and for any place of a point's camera
+//    interval in the window the sub-partitions' shares stay within 1.15 of the mean (C4: 31.8 DMMAs per point instead of
+//    35.3, the busiest sub-partition 99 per panel instead of 126).
+// Loop nest: STRIP-major inside a panel.  For each of my 8 strips a ballot says which of the panel's points have it
+// inside their tile interval; a loop over the set bits does the work.  All accumulators stay in registers for the life
+// of a window.
+constexpr int kNT = kCols / 8;            // 15 tile rows / columns of 8 in the window
+constexpr int kSlots = 8;                 // strips per mma warp: slot 0 = the single diagonal tile, 1..7 = pair strips
+__host__ __device__ constexpr bool strip_single(int i, int sj) { return 2 * sj == i; }
+__host__ __device__ constexpr int strip_owner(int i, int sj) { return strip_single(i, sj) ? ((5 * sj) & 7) : ((i + 3 * sj) & 7); }
 
-struct OwnTable { unsigned char ij[kXW][8]; };        // si | sj << 4 of accumulator group s, 0xff = unused
+struct OwnTable { unsigned char ij[kXW][kSlots]; };   // i | sj << 4 of slot s
 constexpr OwnTable make_own() {
   OwnTable t{};
   for (int w = 0; w < kXW; ++w) {
-    int n = 0;
-    for (int i = 0; i < kNS; ++i)
-      for (int j = 0; j <= i; ++j)
-        if (stile_owner(i, j) == w) t.ij[w][n++] = (unsigned char)(i | (j << 4));
-    for (; n < 8; ++n) t.ij[w][n] = 0xff;
+    int n = 1;
+    for (int s = 0; s < kSlots; ++s) t.ij[w][s] = 0xff;
+    for (int i = 0; i < kNT; ++i)
+      for (int sj = 0; 2 * sj <= i; ++sj) {
+        if (strip_owner(i, sj) != w) continue;
+        if (strip_single(i, sj)) t.ij[w][0] = (unsigned char)(i | (sj << 4));
+        else if (n < kSlots) t.ij[w][n++] = (unsigned char)(i | (sj << 4));
+      }
   }
   return t;
 }
+constexpr bool own_complete() {           // every strip of the lower triangle has a slot
+  const OwnTable t = make_own();
+  int n = 0;
+  for (int w = 0; w < kXW; ++w)
+    for (int s = 0; s < kSlots; ++s)
+      if (t.ij[w][s] != 0xff) ++n;
+  int want = 0;
+  for (int i = 0; i < kNT; ++i) want += i / 2 + 1;
+  return n == want;
+}
+static_assert(own_complete(), "strip ownership must cover the lower triangle with 8 slots per warp");
 __constant__ OwnTable c_own = make_own();
 
 // one accumulator entry -> float64 RED (entries that are exactly zero belong to blocks nobody touched); out of line: rare
 __device__ __noinline__ void flush_entry(const Work& w, int base, int lane, int ti, int tj, int h, double v) {
   const int m = 8 * ti + (lane >> 2);
   const int n2 = 8 * tj + 2 * (lane & 3) + h;
-  if (m >= kCols || n2 >= kCols) return;               // pad columns of the last super-tile
+  if (m >= kCols || n2 >= kCols) return;
   const int a = m / 6, r = m - 6 * a, b = n2 / 6, cc = n2 - 6 * b;
   if (a > b || (a == b && cc <= r)) atomicAdd(s_block_ptr(w, base + a, base + b) + 6 * r + cc, -v);
 }
 
-// one step: super-tile (rows 16 si.., columns 16 sj..) x one point.  acc[0] = (2si, 2sj), [1] = (2si, 2sj+1) (upper
-// on the diagonal: skipped), [2] = (2si+1, 2sj), [3] = (2si+1, 2sj+1)
-template <bool kDiag>
-__device__ __forceinline__ void stile_loop(const double* __restrict__ Yg, unsigned pm, int oi, int oj, double (&acc)[4][2]) {
-  if (pm == 0) return;
-  int p = __ffs(pm) - 1;
-  pm &= pm - 1;
-  const double* Yp = Yg + p * (4 * kYS);
-  double a0 = Yp[oi], a1 = Yp[oi + 8], b0 = 0.0, b1 = 0.0;
-  if (!kDiag) { b0 = Yp[oj]; b1 = Yp[oj + 8]; }
+// one strip x the points of `pm`: Ya = panel + 8 i (A fragment), Yb = panel + 16 sj (B fragments at +0, +8), both with
+// the lane's fragment offset.  A point that is not in `pm` costs no DMMA.  How this loop got here (clock64 trace + ncu source page of the mma warps, C4):
+//  * `while (pm) { p = ffs(pm); ... }` with the next point's fragments loaded before this point's DMMAs: ptxas renamed
+//    the prefetched fragments through MOVs at the loop end, i.e. waited for the loads inside the iteration that issued
+//    them (BREV -> FLO -> IMAD -> IMAD -> LDS -> MOV in front of every DMMA pair); half of the mma warps' samples were
+//    fixed-latency `wait` stalls, 3 % math-pipe throttle: the warps were bound by their own instruction stream (640
+//    instructions per panel and warp for 50 DMMAs), not by the tensor pipe.
+//  * `if (bit) { loads; dmma; }` per point is if-converted by ptxas (also from a PTX `bra.uni`) into predicated DMMAs,
+//    and a predicated-off DMMA holds the tensor pipe as long as a real one (scripts/dmma_pred.cu: 771 vs 802 clk per
+//    24 DMMAs with none / all of them on).  A loop of opaque trip count 0 / 1 is kept as a branch but adds a counter.
+//  * a switch over pairs of mask bits (compare tree over unpredicated straight-line bodies) halved the instruction
+//    count and was slower still (3.8-5.3 k clk per panel against 3.2-4.4 k): taken branches and one exposed LDS latency
+//    per pair.
+//  * what the tensor pipe wants from a warp is a long unpredicated run of DMMAs with the fragment loads batched in
+//    front: the live points of a strip are walked as RUNS of consecutive points (dense loops with data trip counts,
+//    unrolled by four).  In class order (k_ro_*) a panel holds one or two camera intervals and a strip has one run.
+template <bool kPair>
+__device__ __forceinline__ void strip_runs(const double* __restrict__ Ya, const double* __restrict__ Yb, unsigned pm,
+                                           double (&acc)[2][2]) {
 #pragma unroll 1
   while (pm) {
-    // the next point's fragments are on their way before this point's DMMAs are issued
-    p = __ffs(pm) - 1;
-    pm &= pm - 1;
-    Yp = Yg + p * (4 * kYS);
-    const double na0 = Yp[oi], na1 = Yp[oi + 8];
-    double nb0 = 0.0, nb1 = 0.0;
-    if (!kDiag) { nb0 = Yp[oj]; nb1 = Yp[oj + 8]; }
-    if (kDiag) {
-      dmma(acc[0][0], acc[0][1], a0, a0);
-      dmma(acc[2][0], acc[2][1], a1, a0);
-      dmma(acc[3][0], acc[3][1], a1, a1);
-    } else {
-      dmma(acc[0][0], acc[0][1], a0, b0);
-      dmma(acc[1][0], acc[1][1], a0, b1);
-      dmma(acc[2][0], acc[2][1], a1, b0);
-      dmma(acc[3][0], acc[3][1], a1, b1);
+    const int p0 = __ffs(pm) - 1;
+    const int len = __ffs(~(pm >> p0)) - 1;                // pm has at most kPP bits: the complement has a set bit
+    pm &= ~(((1u << len) - 1u) << p0);
+    const double* __restrict__ ya = Ya + p0 * (4 * kYS);
+    const double* __restrict__ yb = Yb + p0 * (4 * kYS);
+#pragma unroll 4
+    for (int t = 0; t < len; ++t) {
+      const double a_ = ya[t * (4 * kYS)];
+      if (kPair) {
+        const double b0_ = yb[t * (4 * kYS)], b1_ = yb[t * (4 * kYS) + 8];
+        dmma(acc[0][0], acc[0][1], a_, b0_);
+        dmma(acc[1][0], acc[1][1], a_, b1_);
+      } else {
+        dmma(acc[0][0], acc[0][1], a_, a_);
+      }
     }
-    a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
-  }
-  if (kDiag) {
-    dmma(acc[0][0], acc[0][1], a0, a0);
-    dmma(acc[2][0], acc[2][1], a1, a0);
-    dmma(acc[3][0], acc[3][1], a1, a1);
-  } else {
-    dmma(acc[0][0], acc[0][1], a0, b0);
-    dmma(acc[1][0], acc[1][1], a0, b1);
-    dmma(acc[2][0], acc[2][1], a1, b0);
-    dmma(acc[3][0], acc[3][1], a1, b1);
   }
 }
 
 __device__ __forceinline__ void mma_warp(const Work& w, PanelSmem& sm, int mw, int lane, int n_panels) {
-  double acc[kOwn][4][2];
+  double acc[kSlots][2][2];
 #pragma unroll
-  for (int s = 0; s < kOwn; ++s)
+  for (int s = 0; s < kSlots; ++s)
 #pragma unroll
-    for (int t = 0; t < 4; ++t) { acc[s][t][0] = 0.0; acc[s][t][1] = 0.0; }
-  // my super-tiles: si, sj per accumulator group (8 = none), kept in registers (opaque: the compiler otherwise re-derives
-  // them from constant memory inside the panel loop)
-  int ssi[kOwn], ssj[kOwn];
+    for (int t = 0; t < 2; ++t) { acc[s][t][0] = 0.0; acc[s][t][1] = 0.0; }
+  // my strips: tile row i and strip column sj per slot (15 | 15: none), kept in registers (opaque: the compiler otherwise
+  // re-derives them from constant memory inside the panel loop)
+  int si[kSlots], sj[kSlots];
 #pragma unroll
-  for (int s = 0; s < kOwn; ++s) {
+  for (int s = 0; s < kSlots; ++s) {
     const unsigned ij = c_own.ij[mw][s];
-    int a = (ij == 0xff) ? 8 : (int)(ij & 15u), b = (ij == 0xff) ? 0 : (int)(ij >> 4);
+    int a = (int)(ij & 15u), b = (int)(ij >> 4);
     asm volatile("mov.s32 %0, %0;" : "+r"(a));
     asm volatile("mov.s32 %0, %0;" : "+r"(b));
-    ssi[s] = a;
-    ssj[s] = b;
+    si[s] = a;
+    sj[s] = b;
   }
   auto flush = [&](int base) {
 #pragma unroll
-    for (int s = 0; s < kOwn; ++s)
+    for (int s = 0; s < kSlots; ++s)
 #pragma unroll
-      for (int t = 0; t < 4; ++t)
+      for (int t = 0; t < 2; ++t)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const double v = acc[s][t][h];
           acc[s][t][h] = 0.0;
-          if (v != 0.0) flush_entry(w, base, lane, 2 * ssi[s] + (t >> 1), 2 * ssj[s] + (t & 1), h, v);
+          if (v != 0.0) flush_entry(w, base, lane, si[s], 2 * sj[s] + t, h, v);
         }
   };
   const int foff = (lane & 3) * kYS + (lane >> 2);
@@ -593,28 +689,32 @@ __device__ __forceinline__ void mma_warp(const Work& w, PanelSmem& sm, int mw, i
   for (int n = 0; n < n_panels; ++n) {
     const int g = n & 1;
     bar_sync<kGL + 32 * kXW>(kBarFull + g);
-    pmark(w, mw == 0 && lane == 0 && n >= 8 && n < 16, 100 + 4 * (n - 8), 1000 + 10 * n + 1);
+    pmark(w, mw == 0 && lane == 0 && n >= kTrace0 && n < kTrace0 + 8, 100 + 4 * (n - kTrace0), 1000 + 10 * n + 1);
     const int base_n = sm.pbase[g];
     if (base_n != acc_base) {
       if (acc_base >= 0) flush(acc_base);
       acc_base = base_n;
     }
     const int npts = sm.pnpts[g];
-    // lane p speaks for point p: its super-tile interval [lo, hi] (lo > hi: the point is not in the panel product)
-    int lo = 1, hi = 0;
+    // lane p speaks for point p: its tile interval [lo, hi] (lo > hi: the point is not in the panel product)
+    int lo = 15, hi = -1;
     if (lane < npts) {
       const int iv = sm.piv[g][lane];
       if (iv != 0xff) { lo = iv & 15; hi = iv >> 4; }
     }
+    const int lo2 = lo >> 1;
     const double* Yg = sm.Yt[g] + foff;
-    pmark(w, mw == 0 && lane == 0 && n >= 8 && n < 16, 101 + 4 * (n - 8), 1000 + 10 * n + 2);
-#pragma unroll
-    for (int s = 0; s < kOwn; ++s) {
-      const unsigned pm = __ballot_sync(kFull, ssj[s] >= lo && ssi[s] <= hi);
-      if (ssi[s] == ssj[s]) stile_loop<true>(Yg, pm, 16 * ssi[s], 16 * ssj[s], acc[s]);
-      else stile_loop<false>(Yg, pm, 16 * ssi[s], 16 * ssj[s], acc[s]);
+    pmark(w, mw == 0 && lane == 0 && n >= kTrace0 && n < kTrace0 + 8, 101 + 4 * (n - kTrace0), 1000 + 10 * n + 2);
+    {
+      const unsigned pm = __ballot_sync(kFull, si[0] >= lo && si[0] <= hi);
+      strip_runs<false>(Yg + 8 * si[0], Yg, pm, acc[0]);
     }
-    pmark(w, mw == 0 && lane == 0 && n >= 8 && n < 16, 102 + 4 * (n - 8), 1000 + 10 * n + 3);
+#pragma unroll
+    for (int s = 1; s < kSlots; ++s) {
+      const unsigned pm = __ballot_sync(kFull, si[s] >= lo && si[s] <= hi && sj[s] >= lo2);
+      strip_runs<true>(Yg + 8 * si[s], Yg + 16 * sj[s], pm, acc[s]);
+    }
+    pmark(w, mw == 0 && lane == 0 && n >= kTrace0 && n < kTrace0 + 8, 102 + 4 * (n - kTrace0), 1000 + 10 * n + 3);
     if (n + kNG < n_panels) bar_arrive<kGL + 32 * kXW>(kBarEmpty + g);
   }
   if (acc_base >= 0) flush(acc_base);
@@ -632,6 +732,7 @@ k_schur_panel(const __grid_constant__ Work w) {
   const double* __restrict__ X = w.X[cur];
   const double* __restrict__ rec = w.rec;
   const bool sliding = w.n_cam > kWin;
+  const bool class_order = w.perm != nullptr;
   const int half_band = (min(w.band_w >= 0 ? w.band_w : kWin - 1, kWin - 3) + 1) >> 1;   // half the widest camera span a point can have
 
   const int p_lo = __ldg(w.part + blockIdx.x), p_hi = __ldg(w.part + blockIdx.x + 1);
@@ -653,7 +754,7 @@ k_schur_panel(const __grid_constant__ Work w) {
     int c = 0x7fffffff;
     if (p_lo + tid < p_hi) {
       const Rec& r = reinterpret_cast<const Rec*>(rec)[p_lo + tid];
-      if (!((((unsigned)r.cmaxf) >> 28) & kFlagSkip)) c = window_start(r.cmin, r.cmaxf & 0x0fffffff, half_band);
+      if (!((((unsigned)r.cmaxf) >> 28) & kFlagSkip)) c = window_start(r.cmin, r.cmaxf & 0x0fffffff, half_band, class_order);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c = min(c, __shfl_xor_sync(kFull, c, o));
@@ -672,7 +773,7 @@ k_schur_panel(const __grid_constant__ Work w) {
   const int g = wid / kGW;                       // staging group = panel buffer
   const int gt = tid - g * kGL;                  // thread index inside the group
   // service warp of the group = its LAST warp (lanes 96..127 carry an observation least often): it issues the bulk
-  // copies of the next panel (five lanes, one copy each) and keeps the panel's books, off the other warps' critical path
+  // points / records copies of the next panel and keeps the panel's books, off the other warps' critical path
   const int sl = gt - (kGL - 32);                // lane inside the service warp (negative: not in it)
   const bool producer = sl == 0;
   double* __restrict__ Yb = sm.Yt[g];
@@ -688,7 +789,7 @@ k_schur_panel(const __grid_constant__ Work w) {
     bar_sync<kNG * kGL>(kBarStageAll);
 
     // issue the bulk copies of panel `n` (this group's) into input stage `st`
-    auto issue = [&](int n, int st) {
+    auto issue = [&](int n, int st, bool trm) {
       StageIn& si = sm.in[g][st];
       const int j0 = p_lo + n * kPP;
       const int npts = min(kPP, p_hi - j0);
@@ -719,20 +820,26 @@ k_schur_panel(const __grid_constant__ Work w) {
       }
       if (a_hi > a_lo) bytes += 16u * (unsigned)(a_hi - a_lo);
       bytes += xb + rb;
-      // one arrival (lane 0, with the byte count) + five copies, one per lane; a copy that completes before the count is
-      // posted only drives the transaction count negative for a moment, the phase still needs the arrival
+      // one arrival (service lane 0, with the byte count) + five copies: lane 0 of the group's warps 0..2 sends the
+      // observation arrays, two lanes of the service warp the points and records.  (Five lanes of the service warp cost
+      // it 1.1-1.5 k clk per panel -- divergent, one UBLKCP after the other -- and the whole group waits for that warp at
+      // the panel buffer's barrier.)  A copy that completes before the count is posted only drives the transaction count
+      // negative for a moment, the phase still needs the arrival.
       const unsigned nb4 = (a_hi > a_lo) ? 4u * (unsigned)(a_hi - a_lo) : 0u;
+      pmark(w, trm, 8 * (n - kNG - kTrace0) + 6, 10 * (n - kNG) + 7);
       if (sl == 0) mbar_expect_tx(&sm.bar[g][st], bytes);
-      if (sl == 0 && nb4) bulk_g2s(&si.cam[a_lo - a0], w.obs_cam + a_lo, nb4, &sm.bar[g][st]);
-      if (sl == 1 && nb4) bulk_g2s(&si.pt[a_lo - a0], w.obs_pt + a_lo, nb4, &sm.bar[g][st]);
-      if (sl == 2 && nb4) bulk_g2s(&si.uv[a_lo - a0], reinterpret_cast<const float2*>(w.obs_uv) + a_lo, 2 * nb4, &sm.bar[g][st]);
-      if (sl == 3 && xb) bulk_g2s(si.X, X + 3 * (size_t)j0, xb, &sm.bar[g][st]);
-      if (sl == 4) bulk_g2s(si.rec, rec + kRecD * (size_t)j0, rb, &sm.bar[g][st]);
+      pmark(w, trm, 8 * (n - kNG - kTrace0) + 7, 10 * (n - kNG) + 8);
+      if (gt == 0 && nb4) bulk_g2s(&si.cam[a_lo - a0], w.obs_cam + a_lo, nb4, &sm.bar[g][st]);
+      if (gt == 32 && nb4) bulk_g2s(&si.pt[a_lo - a0], w.obs_pt + a_lo, nb4, &sm.bar[g][st]);
+      if (gt == 64 && nb4) bulk_g2s(&si.uv[a_lo - a0], reinterpret_cast<const float2*>(w.obs_uv) + a_lo, 2 * nb4, &sm.bar[g][st]);
+      if (sl == 0 && xb) bulk_g2s(si.X, X + 3 * (size_t)j0, xb, &sm.bar[g][st]);
+      if (sl == 1) bulk_g2s(si.rec, rec + kRecD * (size_t)j0, rb, &sm.bar[g][st]);
     };
+    const bool issuer = (lane == 0) || sl == 1;           // the lanes that take part in issue()
 
     const int n_first = sc0 + g;                          // this group's panels: sc0 + g, + kNG, ...
     const int sc_end = sc0 + sc_n;
-    if (sl >= 0 && sl < 5 && n_first < sc_end) issue(n_first, (n_first / kNG) & 1);
+    if (issuer && n_first < sc_end) issue(n_first, (n_first / kNG) & 1, false);
 
     for (int n = n_first; n < sc_end; n += kNG) {
       const int it = n / kNG;                             // this group's it-th panel overall
@@ -741,12 +848,12 @@ k_schur_panel(const __grid_constant__ Work w) {
       if (producer) sm.gbase[g] = sm.cur_base;
       // everyone is done with the other stage (panel n - kNG): its buffers may be refilled
       bar_sync<kGL>(kBarGroup + g);
-      const bool tr = sl == 0 && n >= 8 && n < 16;
-      pmark(w, tr, 8 * (n - 8), 10 * n + 1);
-      if (sl >= 0 && sl < 5 && n + kNG < sc_end) issue(n + kNG, st ^ 1);
-      pmark(w, tr, 8 * (n - 8) + 1, 10 * n + 2);
+      const bool tr = sl == 0 && n >= kTrace0 && n < kTrace0 + 8;
+      pmark(w, tr, 8 * (n - kTrace0), 10 * n + 1);
+      if (issuer && n + kNG < sc_end) issue(n + kNG, st ^ 1, tr);
+      pmark(w, tr, 8 * (n - kTrace0) + 1, 10 * n + 2);
       mbar_wait(&sm.bar[g][st], (it >> 1) & 1);
-      pmark(w, tr, 8 * (n - 8) + 2, 10 * n + 3);
+      pmark(w, tr, 8 * (n - kTrace0) + 2, 10 * n + 3);
       const StageIn& si = sm.in[g][st];
       const int j0 = p_lo + n * kPP;
       const int npts = min(kPP, p_hi - j0);
@@ -772,7 +879,7 @@ k_schur_panel(const __grid_constant__ Work w) {
         const bool ahead = live && my_cmax >= base + kWin;
         const bool fits = live && myrec.cmin >= base && my_cmax < base + kWin;
         if (__any_sync(kFull, ahead) || !__any_sync(kFull, fits)) {
-          int ws = live ? window_start(myrec.cmin, my_cmax, half_band) : 0x7fffffff;
+          int ws = live ? window_start(myrec.cmin, my_cmax, half_band, class_order) : 0x7fffffff;
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) ws = min(ws, __shfl_xor_sync(kFull, ws, o));
           if (ws != 0x7fffffff && max(0, ws) != base) { base = max(0, ws); moved = true; }
@@ -781,7 +888,7 @@ k_schur_panel(const __grid_constant__ Work w) {
 
       // the panel buffer is free again once the mma warps have consumed this group's previous panel
       if (it >= 1) bar_sync<kGL + 32 * kXW>(kBarEmpty + g);
-      pmark(w, tr, 8 * (n - 8) + 3, 10 * n + 4);
+      pmark(w, tr, 8 * (n - kTrace0) + 3, 10 * n + 4);
 
       // slot intervals + the books, by the group's service warp
       if (sl >= 0) {
@@ -790,7 +897,7 @@ k_schur_panel(const __grid_constant__ Work w) {
           if (!(my_flags & kFlagSkip)) {
             const bool fits = myrec.cmin >= base && my_cmax < base + kWin;
             if (fits && !(my_flags & kFlagFallback) && !overflow) {
-              const int lo = (6 * (myrec.cmin - base)) >> 4, hi = (6 * (my_cmax - base) + 5) >> 4;   // super-tiles of 16 columns
+              const int lo = (6 * (myrec.cmin - base)) >> 3, hi = (6 * (my_cmax - base) + 5) >> 3;   // tiles of 8 columns
               iv = lo | (hi << 4);
             }
           }
@@ -802,7 +909,7 @@ k_schur_panel(const __grid_constant__ Work w) {
         }
       }
 
-      pmark(w, tr, 8 * (n - 8) + 4, 10 * n + 5);
+      pmark(w, tr, 8 * (n - kTrace0) + 4, 10 * n + 5);
       // ---- lane <-> observation ---------------------------------------------------------------------------
       if (!overflow) {
         for (int i = gt; i < nob; i += kGL) {
@@ -828,7 +935,7 @@ k_schur_panel(const __grid_constant__ Work w) {
           const int rel = cam - base;
           const bool first = (i == 0) || (si.pt[e - 1] - j0 != slot);
           const bool last = (i == nob - 1) || (si.pt[e + 1] - j0 != slot);
-          // the mma warps read whole super-tiles: zeros out to the 16-column boundaries around the point's cameras
+          // the mma warps read whole strips (16 columns): zeros out to the 16-column boundaries around the point's cameras
           const int lo_col = 16 * ((6 * (r.cmin - base)) >> 4);
           const int hi_col = 16 * (((6 * (cmax - base) + 5) >> 4) + 1);
           const int next_col = last ? hi_col : 6 * (si.cam[e + 1] - base);
@@ -894,7 +1001,7 @@ k_schur_panel(const __grid_constant__ Work w) {
           }
         }
       }
-      pmark(w, tr, 8 * (n - 8) + 5, 10 * n + 6);
+      pmark(w, tr, 8 * (n - kTrace0) + 5, 10 * n + 6);
       __threadfence_block();
       bar_arrive<kGL + 32 * kXW>(kBarFull + g);
     }
@@ -931,6 +1038,20 @@ bool panel_supported(const Work& w) {
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   return w.part != nullptr && w.rec != nullptr && w.cs_pt != nullptr && al(w.obs_cam) && al(w.obs_pt) && al(w.obs_uv) &&
          al(w.X[0]) && al(w.X[1]) && al(w.rec);
+}
+
+size_t panel_classes(int n_cam) { return (size_t)n_cam * kSpanClasses + 1; }
+
+int launch_panel_reorder(const Work& w, const PanelOrder& o, cudaStream_t s) {
+  const int ncls = (int)panel_classes(w.n_cam);
+  cudaMemsetAsync(o.cnt, 0, sizeof(unsigned long long) * (size_t)(ncls + 1), s);
+  int blocks = (w.n_pt + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_ro_count<<<blocks, 256, 0, s>>>(w, o.cnt);
+  k_ro_scan<<<1, 1024, 0, s>>>(o.cnt, ncls);
+  k_ro_scatter<<<blocks, 256, 0, s>>>(w, o);
+  return 3;
 }
 
 // once per solve: camera-sorted copy of the observations for k_cam_blocks
