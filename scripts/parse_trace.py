@@ -18,3 +18,14 @@ for n in range(200, 208):
     if all(mm):
         s += f" | mma: masks {mm[1] - mm[0]}, tile loop {mm[2] - mm[1]}" + (f" ({steps[0]} steps)" if steps else "")
     print(s)
+
+# all eight mma warps: start (after the full barrier) and end of the strip loop, relative to warp 0's start
+for k in range(8):
+    row = []
+    t0 = ev.get(20000 + 10 * k + 1)
+    for mw in range(8):
+        a, b = ev.get(20000 + 1000 * mw + 10 * k + 1), ev.get(20000 + 1000 * mw + 10 * k + 3)
+        if a and b and t0:
+            row.append(f"w{mw} {a - t0:+d}..{b - t0}")
+    if row:
+        print(f"panel {200 + k}: mma warps " + "  ".join(row))

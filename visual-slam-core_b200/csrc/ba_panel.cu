@@ -44,12 +44,15 @@ constexpr int kPP = 12;                   // points per panel (one mma k-step ea
 constexpr int kRows = 4 * kPP;            // panel rows
 constexpr int kGW = 4;                    // warps per staging group
 constexpr int kGL = 32 * kGW;             // lanes per staging group
-constexpr int kNG = 2;                    // staging groups (each owns one panel buffer)
+constexpr int kNG = 2;                    // staging groups (take the CTA's panels in turn)
+constexpr int kNB = 3;                    // panel buffers (panel n lives in buffer n mod 3): a group starts its next panel while
+                                          // the mma warps still read its last one
 constexpr int kXW = 8;                    // mma warps
 constexpr int kThreadsP = 32 * (kNG * kGW + kXW);   // 512
 constexpr int kOB = 512;                  // observation capacity of a panel's staging buffers
 constexpr int kBoundsCap = 2048;          // panel boundaries staged per super-chunk
-constexpr int kBarFull = 1, kBarEmpty = 3, kBarGroup = 5, kBarStageAll = 7;
+constexpr int kBarFull = 1, kBarEmpty = 1 + kNB, kBarGroup = 1 + 2 * kNB, kBarStageAll = 1 + 2 * kNB + kNG;
+static_assert(kBarStageAll < 16, "named barriers");
 constexpr int kRecD = 10;                 // doubles per point record
 constexpr int kFlagFallback = 1, kFlagSkip = 2;
 constexpr int kTrace0 = 200;              // first of the eight panels of CTA 0 the clock64 trace covers (-DBA_PANEL_TRACE)
@@ -452,13 +455,13 @@ struct __align__(16) StageIn {          // one panel's inputs, landed by bulk co
 };
 
 struct __align__(16) PanelSmem {
-  double Yt[kNG][kRows * kYS];
+  double Yt[kNB][kRows * kYS];
   StageIn in[kNG][2];
   uint64_t bar[kNG][2];                 // mbarriers of the input stages
   int bounds[kBoundsCap + 1];           // pt_off at the panel boundaries of this CTA (one super-chunk)
-  unsigned char piv[kNG][16];           // per point slot: first | last << 4 tile (8 columns) of the point's camera interval (0xff: none)
-  int pbase[kNG];                       // window base the panel was staged with
-  int pnpts[kNG];
+  unsigned char piv[kNB][16];           // per point slot: first | last << 4 tile (8 columns) of the point's camera interval (0xff: none)
+  int pbase[kNB];                       // window base the panel was staged with
+  int pnpts[kNB];
   int gbase[kNG];                       // the group's snapshot of cur_base for the panel it is staging
   int cur_base;                         // window base for the panels that start from now on
   int n_rebase, n_fallback;             // diagnostics (-DBA_PANEL_TRACE)
@@ -686,10 +689,10 @@ __device__ __forceinline__ void mma_warp(const Work& w, PanelSmem& sm, int mw, i
   };
   const int foff = (lane & 3) * kYS + (lane >> 2);
   int acc_base = -1;
-  for (int n = 0; n < n_panels; ++n) {
-    const int g = n & 1;
+  for (int n = 0, g = 0; n < n_panels; ++n, g = (g + 1 == kNB) ? 0 : g + 1) {      // g: the panel's buffer
     bar_sync<kGL + 32 * kXW>(kBarFull + g);
     pmark(w, mw == 0 && lane == 0 && n >= kTrace0 && n < kTrace0 + 8, 100 + 4 * (n - kTrace0), 1000 + 10 * n + 1);
+    pmark(w, lane == 0 && n >= kTrace0 && n < kTrace0 + 8, 400 + 16 * (n - kTrace0) + 2 * mw, 20000 + 1000 * mw + 10 * (n - kTrace0) + 1);
     const int base_n = sm.pbase[g];
     if (base_n != acc_base) {
       if (acc_base >= 0) flush(acc_base);
@@ -715,7 +718,8 @@ __device__ __forceinline__ void mma_warp(const Work& w, PanelSmem& sm, int mw, i
       strip_runs<true>(Yg + 8 * si[s], Yg + 16 * sj[s], pm, acc[s]);
     }
     pmark(w, mw == 0 && lane == 0 && n >= kTrace0 && n < kTrace0 + 8, 102 + 4 * (n - kTrace0), 1000 + 10 * n + 3);
-    if (n + kNG < n_panels) bar_arrive<kGL + 32 * kXW>(kBarEmpty + g);
+    pmark(w, lane == 0 && n >= kTrace0 && n < kTrace0 + 8, 400 + 16 * (n - kTrace0) + 2 * mw + 1, 20000 + 1000 * mw + 10 * (n - kTrace0) + 3);
+    if (n + kNB < n_panels) bar_arrive<kGL + 32 * kXW>(kBarEmpty + g);
   }
   if (acc_base >= 0) flush(acc_base);
 }
@@ -742,7 +746,8 @@ k_schur_panel(const __grid_constant__ Work w) {
 #endif
 
   if (tid == 0) {
-    for (int g = 0; g < kNG; ++g) { mbar_init(&sm.bar[g][0], 1); mbar_init(&sm.bar[g][1], 1); sm.pbase[g] = 0; sm.pnpts[g] = 0; }
+    for (int g = 0; g < kNG; ++g) { mbar_init(&sm.bar[g][0], 1); mbar_init(&sm.bar[g][1], 1); }
+    for (int b = 0; b < kNB; ++b) { sm.pbase[b] = 0; sm.pnpts[b] = 0; }
     sm.cur_base = 0;
     sm.n_rebase = 0; sm.n_fallback = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -776,7 +781,6 @@ k_schur_panel(const __grid_constant__ Work w) {
   // points / records copies of the next panel and keeps the panel's books, off the other warps' critical path
   const int sl = gt - (kGL - 32);                // lane inside the service warp (negative: not in it)
   const bool producer = sl == 0;
-  double* __restrict__ Yb = sm.Yt[g];
 
   for (int sc0 = 0; sc0 < n_panels; sc0 += kBoundsCap) {
     // panel boundaries of this super-chunk (all staging threads), then the groups run their panels
@@ -844,6 +848,8 @@ k_schur_panel(const __grid_constant__ Work w) {
     for (int n = n_first; n < sc_end; n += kNG) {
       const int it = n / kNG;                             // this group's it-th panel overall
       const int st = it & 1;
+      const int pb = n % kNB;                             // the panel's buffer
+      double* __restrict__ Yb = sm.Yt[pb];
       // the group's view of the window base for this panel (the other group may move cur_base at any time)
       if (producer) sm.gbase[g] = sm.cur_base;
       // everyone is done with the other stage (panel n - kNG): its buffers may be refilled
@@ -886,8 +892,10 @@ k_schur_panel(const __grid_constant__ Work w) {
         }
       }
 
-      // the panel buffer is free again once the mma warps have consumed this group's previous panel
-      if (it >= 1) bar_sync<kGL + 32 * kXW>(kBarEmpty + g);
+      // the panel buffer is free again once the mma warps have consumed the panel that was in it.  (Letting the three
+      // observation warps pass without the service warp -- late, it has just sent the next panel's copies, ~1.5 k clk of
+      // MIO queue -- changed nothing: the mma warps, 3.2 k clk per panel all eight alike, release the buffer later still.)
+      if (n >= kNB) bar_sync<kGL + 32 * kXW>(kBarEmpty + pb);
       pmark(w, tr, 8 * (n - kTrace0) + 3, 10 * n + 4);
 
       // slot intervals + the books, by the group's service warp
@@ -901,10 +909,10 @@ k_schur_panel(const __grid_constant__ Work w) {
               iv = lo | (hi << 4);
             }
           }
-          sm.piv[g][sl] = (unsigned char)iv;
+          sm.piv[pb][sl] = (unsigned char)iv;
         }
         if (sl == 0) {
-          sm.pbase[g] = base; sm.pnpts[g] = npts;
+          sm.pbase[pb] = base; sm.pnpts[pb] = npts;
           if (moved) { sm.cur_base = base; sm.n_rebase++; }
         }
       }
@@ -1003,7 +1011,7 @@ k_schur_panel(const __grid_constant__ Work w) {
       }
       pmark(w, tr, 8 * (n - kTrace0) + 5, 10 * n + 6);
       __threadfence_block();
-      bar_arrive<kGL + 32 * kXW>(kBarFull + g);
+      bar_arrive<kGL + 32 * kXW>(kBarFull + pb);
     }
   }
 #ifdef BA_PANEL_TRACE
