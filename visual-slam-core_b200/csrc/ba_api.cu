@@ -78,7 +78,7 @@ struct ba_handle {
   // workspace
   DevBuf camstate, X0, X1, red, ctl, cand, dbg, part;
   DevBuf rec, cs_cnt, cs_blk_off, cs_blk_cam, cs_pt, cs_uv, cs_nblk;   // panel linearise path
-  DevBuf ro_cnt, ro_perm, ro_off, ro_cam, ro_pt, ro_uv;                // panel path: class order of the points   // camstate = pose[0] | pose[1] | dp, contiguous (one broadcast)
+  DevBuf ro_cnt, ro_perm, ro_off, ro_cam, ro_pt, ro_uv, ro_range;      // panel path: class order of the points, the shard's camera range   // camstate = pose[0] | pose[1] | dp, contiguous (one broadcast)
   // sparse path: structure + PCG workspace
   DevBuf bits, wpre, row_nnz, row_ptr, col_idx, tpos, pcg, bits_all;
   // banded path: factor columns, forward-substituted rhs, inverse pivots, bandwidth scalar
@@ -105,6 +105,15 @@ struct ba_handle {
   // multi-GPU
   nccl_comm comm = nullptr;
   int rank = 0, world = 1;
+  // peer-memory exchange of the reduction buffer (banded path): CUDA IPC mappings of every rank's `red` and flag array
+  struct Peer {
+    bool open = false, off = false;
+    void* red_exported = nullptr;            // the `red` pointer the peers have mapped
+    void* red[8] = {nullptr};                // every rank's reduction buffer (own at [rank])
+    void* flags[8] = {nullptr};              // every rank's flag array: flags[q][r] = last epoch rank r posted to rank q
+    DevBuf flagbuf, xbuf;                    // own flag array; scratch for the handle exchange
+    unsigned long long solves = 0;           // epoch base = 64 * solves (all ranks call in lock step)
+  } peer;
   // profile mode: events between kernels, tag of the kernel that follows each event
   std::vector<cudaEvent_t> prof_ev;
   std::vector<int> prof_tag;
@@ -175,6 +184,106 @@ static int ensure(ba_handle* h, DevBuf& b, size_t bytes) {
   b.cap = cap;
   if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; h->graph_key = ba_handle::GraphKey(); }
   return BA_OK;
+}
+
+// ---- peer-memory exchange (sharded banded path) --------------------------------------------------------------
+static bool peer_wanted(const ba_handle* h) {
+  static int v = -1;                 // diagnostics: BA_PEER_REDUCE=0 keeps the NCCL all-reduce in front of the solver
+  if (v < 0) { const char* e = getenv("BA_PEER_REDUCE"); v = (e && !atoi(e)) ? 0 : 1; }
+  return v != 0 && h->world > 1 && h->world <= kMaxPeers && !h->peer.off;
+}
+
+// unmap the peers' buffers; every rank gets here in the same call (the buffer sizes depend on the window only), and the
+// collective makes sure nobody frees a buffer a peer still has mapped
+static int peer_close(ba_handle* h, cudaStream_t s) {
+  if (!h->peer.open) return BA_OK;
+  for (int q = 0; q < h->world; ++q) {
+    if (q == h->rank) continue;
+    if (h->peer.red[q]) cudaIpcCloseMemHandle(h->peer.red[q]);
+    if (h->peer.flags[q]) cudaIpcCloseMemHandle(h->peer.flags[q]);
+    h->peer.red[q] = h->peer.flags[q] = nullptr;
+  }
+  h->peer.open = false;
+  h->peer.red_exported = nullptr;
+  if (h->comm) {
+    if (ensure(h, h->peer.xbuf, 4096)) return BA_ERR_CUDA;
+    int r = g_nccl.allreduce(h->peer.xbuf.p, h->peer.xbuf.p, 1, kNcclInt32, kNcclSum, h->comm, s);
+    if (r != 0) { h->err = "ncclAllReduce(peer close)"; return BA_ERR_NCCL; }
+    CK(cudaStreamSynchronize(s));
+  }
+  return BA_OK;
+}
+
+// map every rank's reduction buffer and flag array (IPC handles travel through an NCCL all-gather); the ranks agree
+// on the outcome, a failure anywhere switches the peer path off everywhere (NCCL all-reduce instead)
+static int peer_open(ba_handle* h, cudaStream_t s) {
+  const int W = h->world;
+  int rc;
+  if ((rc = ensure(h, h->peer.xbuf, 4096))) return rc;
+  if (!h->peer.flagbuf.p) {
+    if ((rc = ensure(h, h->peer.flagbuf, sizeof(long long) * 64))) return rc;
+    CK(cudaMemset(h->peer.flagbuf.p, 0, sizeof(long long) * 64));
+  }
+  struct Pair { cudaIpcMemHandle_t red, flags; };
+  static_assert(sizeof(Pair) == 128, "IPC handle size");
+  std::vector<Pair> all(W);
+  Pair mine;
+  int ok = 1;
+  if (cudaIpcGetMemHandle(&mine.red, h->red.p) != cudaSuccess) ok = 0;
+  if (cudaIpcGetMemHandle(&mine.flags, h->peer.flagbuf.p) != cudaSuccess) ok = 0;
+  cudaGetLastError();
+  char* xb = (char*)h->peer.xbuf.p;                      // [0, 128): mine; [256, 256 + 128 W): everyone's
+  CK(cudaMemcpyAsync(xb, &mine, sizeof(Pair), cudaMemcpyHostToDevice, s));
+  int r = g_nccl.allgather(xb, xb + 256, sizeof(Pair), /*ncclChar*/ 0, h->comm, s);
+  if (r != 0) { h->err = "ncclAllGather(IPC handles)"; return BA_ERR_NCCL; }
+  CK(cudaMemcpyAsync(all.data(), xb + 256, sizeof(Pair) * W, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  for (int q = 0; q < W && ok; ++q) {
+    if (q == h->rank) { h->peer.red[q] = h->red.p; h->peer.flags[q] = h->peer.flagbuf.p; continue; }
+    if (cudaIpcOpenMemHandle(&h->peer.red[q], all[q].red, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = 0;
+    else if (cudaIpcOpenMemHandle(&h->peer.flags[q], all[q].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = 0;
+  }
+  cudaGetLastError();
+  // agreement: min over the ranks
+  int* d_ok = (int*)(xb + 2048);
+  CK(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, s));
+  r = g_nccl.allreduce(d_ok, d_ok, 1, kNcclInt32, /*ncclMin*/ 3, h->comm, s);
+  if (r != 0) { h->err = "ncclAllReduce(peer agreement)"; return BA_ERR_NCCL; }
+  int all_ok = 0;
+  CK(cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  h->peer.open = true;                                   // so that peer_close unmaps whatever was mapped
+  h->peer.red_exported = h->red.p;
+  if (!all_ok) {
+    h->peer.off = true;
+    return peer_close(h, s);
+  }
+  return BA_OK;
+}
+
+// unmap without a collective (tear-down: the ranks do not arrive together)
+static void peer_unmap(ba_handle* h) {
+  for (int q = 0; q < kMaxPeers; ++q) {
+    if (q == h->rank || !h->peer.open) continue;
+    if (h->peer.red[q]) cudaIpcCloseMemHandle(h->peer.red[q]);
+    if (h->peer.flags[q]) cudaIpcCloseMemHandle(h->peer.flags[q]);
+  }
+  for (int q = 0; q < kMaxPeers; ++q) h->peer.red[q] = h->peer.flags[q] = nullptr;
+  h->peer.open = false;
+  h->peer.red_exported = nullptr;
+}
+
+static PeerView peer_view(const ba_handle* h) {
+  PeerView pv;
+  memset(&pv, 0, sizeof(pv));
+  pv.world = h->world; pv.rank = h->rank;
+  for (int q = 0; q < h->world; ++q) {
+    pv.red[q] = (const double*)h->peer.red[q];
+    pv.flag_remote[q] = (long long*)h->peer.flags[q] + 4 * h->rank;
+  }
+  pv.flag_local = (const long long*)h->peer.flagbuf.p;
+  pv.cam_range = (const int*)h->ro_range.p;
+  return pv;
 }
 
 namespace ba { int mma_max_active_clusters(int cluster); }
@@ -285,7 +394,9 @@ extern "C" int ba_destroy(ba_handle* h) {
                     &h->d_off, &h->d_flags, &h->d_hist, &h->d_acc, &h->d_foff, &h->dbg, &h->part,
                     &h->bits, &h->wpre, &h->row_nnz, &h->row_ptr, &h->col_idx, &h->tpos, &h->pcg,
                     &h->bits_all, &h->band_L, &h->band_y, &h->band_dinv, &h->band_wbuf, &h->bcr,
-                    &h->ro_cnt, &h->ro_perm, &h->ro_off, &h->ro_cam, &h->ro_pt, &h->ro_uv};
+                    &h->ro_cnt, &h->ro_perm, &h->ro_off, &h->ro_cam, &h->ro_pt, &h->ro_uv,
+                    &h->peer.flagbuf, &h->peer.xbuf, &h->ro_range};
+  peer_unmap(h);
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
@@ -469,7 +580,12 @@ static int make_work(ba_handle* h, int n_cam, int n_pt, int n_obs, const double 
     w.pcg_Minv = q; q += 36 * (size_t)n_cam;
     w.pcg_acc = q;
   }
-  if ((rc = ensure(h, h->red, sizeof(double) * (w.s_len + 2 * (size_t)n + 1)))) return rc;
+  {
+    const size_t need = sizeof(double) * (w.s_len + 2 * (size_t)n + 1);
+    // peers have this buffer mapped: they let go before it is reallocated (same call on every rank)
+    if (h->peer.open && !(need <= h->red.cap && h->red.p) && (rc = peer_close(h, s))) return rc;
+    if ((rc = ensure(h, h->red, need))) return rc;
+  }
   w.S = (double*)h->red.p;
   w.b = w.S + w.s_len;
   w.diagU = w.b + n;
@@ -510,6 +626,9 @@ static int launch_linearize(const Work& w, int schur, int sm_count, cudaStream_t
 static int enqueue_lm_loop(ba_handle* h, const Work& w, int schur, cudaStream_t s) {
   int launches = 0;
   const size_t nred = w.s_len + 2 * (size_t)w.n + 1;
+  // sharded banded path: the solver's first kernel sums the ranks' reduction buffers over peer memory itself
+  const bool peers = h->world > 1 && h->peer.open && w.band_w >= 0 && w.bcr_ws != nullptr;
+  const PeerView pv = peers ? peer_view(h) : PeerView();
   const bool sparse = w.bsr_bits != nullptr;
   const int pcg_grid = sparse ? pcg_grid_size(w.n_cam, h->sm_count) : 0;
   for (int it = 0; it < h->prm.max_iter; ++it) {
@@ -523,14 +642,14 @@ static int enqueue_lm_loop(ba_handle* h, const Work& w, int schur, cudaStream_t 
       if (nl < 0) { h->err = std::string("linearise launch: ") + cudaGetErrorString(cudaGetLastError()); return BA_ERR_CUDA; }
       launches += nl;
     }
-    if (h->world > 1) {
+    if (h->world > 1 && !peers) {
       prof_mark(h, TAG_COMM, s);
       int r = g_nccl.allreduce(w.S, w.S, nred, kNcclDouble, kNcclSum, h->comm, s);
       if (r != 0) { h->err = std::string("ncclAllReduce(S): ") + (g_nccl.errstr ? g_nccl.errstr(r) : "?"); return BA_ERR_NCCL; }
     }
     prof_mark(h, TAG_SOLVE, s);
     if (w.band_w >= 0) {
-      launches += w.bcr_ws ? launch_rcs_bcr(w, w.bcr_ws, s, h->sm_count) : launch_rcs_band(w, s);
+      launches += w.bcr_ws ? launch_rcs_bcr(w, w.bcr_ws, s, h->sm_count, peers ? &pv : nullptr, it) : launch_rcs_band(w, s);
     } else if (sparse) {
       if (launch_rcs_pcg(w, pcg_grid, s) < 0) { h->err = std::string("cooperative PCG launch: ") + cudaGetErrorString(cudaGetLastError()); return BA_ERR_CUDA; }
       launches += 1;
@@ -539,7 +658,9 @@ static int enqueue_lm_loop(ba_handle* h, const Work& w, int schur, cudaStream_t 
     }
     static int no_bcast = -1;       // diagnostics only (BA_NO_BCAST=1): how much of the iteration is the broadcast
     if (no_bcast < 0) { const char* e = getenv("BA_NO_BCAST"); no_bcast = (e && atoi(e)) ? 1 : 0; }
-    if (h->world > 1 && !no_bcast) {
+    // (the cyclic-reduction solver is deterministic -- gathered updates, no REDs -- and its inputs are identical bits on
+    // every rank: no broadcast there)
+    if (h->world > 1 && !no_bcast && !(w.band_w >= 0 && w.bcr_ws != nullptr)) {
       // the replicated solve ends in float64 REDs whose order differs from rank to rank: rank 0's camera step
       // and candidate poses go to everyone, so the replicated state stays bit-identical across ranks
       prof_mark(h, TAG_COMM, s);
@@ -553,6 +674,8 @@ static int enqueue_lm_loop(ba_handle* h, const Work& w, int schur, cudaStream_t 
       int r = g_nccl.allreduce(w.cost_cand, w.cost_cand, 2, kNcclDouble, kNcclSum, h->comm, s);
       if (r != 0) { h->err = std::string("ncclAllReduce(cost): ") + (g_nccl.errstr ? g_nccl.errstr(r) : "?"); return BA_ERR_NCCL; }
       launches += launch_accept(w, s);
+      // every rank has passed its assembly by now (it fed the all-reduce after it): nobody reads this buffer any more
+      if (peers) CK(cudaMemsetAsync(w.S, 0, sizeof(double) * nred, s));
     }
   }
   return launches;
@@ -624,15 +747,29 @@ extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t
   h->last_solver = mode == MODE_DENSE ? BA_SOLVER_CHOLESKY : (mode == MODE_BAND ? BA_SOLVER_BAND : BA_SOLVER_PCG);
   h->last_band_w = bw;
   h->last_s_blocks = (int)(w.s_len / 36);
+  if (h->world > 1) {
+    // peer-memory exchange for the cyclic-reduction band solver; (re)mapped whenever the reduction buffer moved
+    const bool want = peer_wanted(h) && mode == MODE_BAND && w.bcr_ws != nullptr;
+    if (h->peer.open && (!want || h->peer.red_exported != h->red.p) && (rc = peer_close(h, s))) return rc;
+    if (want && !h->peer.open && (rc = peer_open(h, s))) return rc;
+    h->peer.solves++;
+  }
   int schur = pick_schur(h, w, /*ignore_alignment=*/true);
   LmInit li{h->prm.lambda0, h->prm.huber_delta, h->prm.chi2_thr, h->prm.lambda_up,
-            h->prm.lambda_down, h->prm.lambda_min, h->prm.lambda_max, h->prm.accept_rtol};
+            h->prm.lambda_down, h->prm.lambda_min, h->prm.lambda_max, h->prm.accept_rtol, 0};
+  li.epoch_base = (long long)(64ull * h->peer.solves);
 
   int launches = 0;
   h->prof_n = 0;
   if (w.dbg) cudaMemsetAsync(w.dbg, 0, sizeof(long long) * 4096, s);
   CK(cudaEventRecord(h->ev0, s));
   prof_mark(h, TAG_OTHER, s);
+  {
+    // the shard's camera range: everything, unless the class-order pass below measures it
+    if ((rc = ensure(h, h->ro_range, 64))) return rc;
+    const int full_range[2] = {0, n_cam - 1};
+    CK(cudaMemcpyAsync(h->ro_range.p, full_range, sizeof(full_range), cudaMemcpyHostToDevice, s));
+  }
   if (schur == BA_SCHUR_PANEL && h->prm.max_iter > 0 && n_pt > 0 && n_obs > 0 && panel_reorder_enabled()) {
     // the panel path works in its own point order (class order, ba_panel.cu): a permuted copy of the observations
     // and offsets, built on the device once per solve; k_init / k_finalize translate points and flags
@@ -642,7 +779,7 @@ extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t
     if ((rc = ensure(h, h->ro_cam, sizeof(int) * (size_t)(n_obs + 4)))) return rc;
     if ((rc = ensure(h, h->ro_pt, sizeof(int) * (size_t)(n_obs + 4)))) return rc;
     if ((rc = ensure(h, h->ro_uv, sizeof(float) * 2 * (size_t)(n_obs + 4)))) return rc;
-    PanelOrder po{(unsigned long long*)h->ro_cnt.p, (int*)h->ro_perm.p, (int*)h->ro_off.p,
+    PanelOrder po{(int*)h->ro_range.p, (unsigned long long*)h->ro_cnt.p, (int*)h->ro_perm.p, (int*)h->ro_off.p,
                   (int*)h->ro_cam.p, (int*)h->ro_pt.p, (float*)h->ro_uv.p};
     launches += launch_panel_reorder(w, po, s);
     w.perm = po.perm;
@@ -666,7 +803,7 @@ extern "C" int ba_solve_local(ba_handle* h, int32_t n_cam, int32_t n_pt, int32_t
   if (use_graph) {
     ba_handle::GraphKey key;
     key.n_cam = n_cam; key.n_pt = n_pt; key.n_obs = n_obs; key.max_iter = h->prm.max_iter;
-    key.schur = schur; key.world = h->world;
+    key.schur = schur; key.world = 2 * h->world + (h->peer.open ? 1 : 0);
     const void* ptrs[10] = {cam_fixed, w.obs_cam, w.obs_pt, w.obs_uv, w.pt_off, w.S, w.pose[0], w.X[0], w.ctl, w.dp};
     memcpy(key.ptrs, ptrs, sizeof(ptrs));
     key.scal[0] = intr[0]; key.scal[1] = intr[1]; key.scal[2] = intr[2]; key.scal[3] = intr[3];
@@ -973,6 +1110,7 @@ extern "C" int ba_dist_init(ba_handle* h, const void* id, int32_t rank, int32_t 
 
 extern "C" int ba_dist_shutdown(ba_handle* h) {
   if (!h) return BA_ERR_INVALID;
+  peer_unmap(h);
   if (h->comm && g_nccl.destroy) { g_nccl.destroy(h->comm); h->comm = nullptr; }
   h->world = 1; h->rank = 0;
   if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }

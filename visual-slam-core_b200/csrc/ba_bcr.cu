@@ -17,6 +17,8 @@
 // left.  Back substitution runs the levels in reverse:  x_i = C^-T (y - E1^T x_(i-1) - E2^T x_(i+1)).
 // Every level is one launch whose CTAs are independent, so all SMs work; the results equal the
 // sequential factorisation's up to rounding (both are exact direct solves of the same SPD system).
+#include <string.h>
+
 #include "ba_kernels.cuh"
 
 namespace ba {
@@ -83,17 +85,95 @@ __device__ __forceinline__ int cell(int I, int J) {
 // ------------------------------------------------------------------------------------------
 // level 0 from the banded accumulation buffers (damping, gauge rows, clearing behind the read)
 // ------------------------------------------------------------------------------------------
+// Level 0 from the banded accumulation buffers.  Sharded runs (kPeers): the exchange of the reduced camera system IS
+// this kernel -- a CTA stages its super-block's 15 band rows of S and its rows of b / diagU in shared memory as the SUM
+// over the ranks' reduction buffers, read over NVLink peer memory (16-byte loads, four in flight per thread; a peer whose
+// shard does not touch the super-block's cameras -- every rank posts its camera range with its flag -- is skipped: with
+// contiguous point shards of a trajectory that leaves one or two ranks per row), then assembles from there.
+constexpr int kFlagStride = 4;                // 64-bit words per (owner, poster) flag slot: epoch | first camera | last camera | -
+constexpr int kAsmRowMax = (kSB + 1) * 36;    // doubles of one band row at the widest band
+inline size_t assemble_smem() { return sizeof(double) * ((size_t)kSB * kAsmRowMax + 2 * kV + 2); }
+
+template <bool kPeers>
 __global__ void __launch_bounds__(256)
-k_bcr_assemble(Work w, double* __restrict__ D, double* __restrict__ L, double* __restrict__ b, int* fail) {
+k_bcr_assemble(Work w, double* __restrict__ D, double* __restrict__ L, double* __restrict__ b, int* fail, PeerView pv, int it) {
+  extern __shared__ __align__(16) double s_asm[];
   const int i = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const int bw = w.band_w, rowlen = (bw + 1) * 36;
   LmCtl* ctl = w.ctl;
   const double lambda = ctl->lambda;
+  const size_t off_b = w.s_len, off_dU = w.s_len + (size_t)w.n, off_cost = w.s_len + 2 * (size_t)w.n;
+  double* s_S = s_asm;                                   // [15][rowlen]
+  double* s_b = s_asm + (size_t)kSB * kAsmRowMax;        // [90]
+  double* s_dU = s_b + kV;                               // [90]
+  __shared__ int s_late;
+  __shared__ int s_use[kMaxPeers];
+  __shared__ double s_cost;
+  const int I0 = kSB * i;
+  const int n_rows = max(0, min(kSB, w.n_cam - I0));
+  if (kPeers) {
+    // this rank's linearisation is complete (stream order): tell every peer (epoch + my camera range), then wait for
+    // theirs.  The wait is bounded: a peer that never arrives fails the step instead of hanging the GPU.
+    const long long epoch = ctl->epoch_base + it + 1;
+    if (tid == 0) { s_late = 0; s_cost = 0.0; }
+    __syncthreads();
+    if (tid < pv.world) {
+      int use = 1;
+      if (tid != pv.rank) {
+        if (i == 0) {
+          volatile long long* out = reinterpret_cast<volatile long long*>(pv.flag_remote[tid]);
+          out[1] = pv.cam_range[0];
+          out[2] = pv.cam_range[1];
+          __threadfence_system();
+          out[0] = epoch;
+        }
+        const volatile long long* f = reinterpret_cast<const volatile long long*>(pv.flag_local + kFlagStride * tid);
+        const long long t0 = clock64();
+        while (f[0] < epoch) {
+          if (clock64() - t0 > 6000000000ll) { s_late = 1; break; }
+        }
+        __threadfence_system();
+        const long long clo = f[1], chi = f[2];
+        use = (chi >= I0 && clo <= I0 + kSB - 1) ? 1 : 0;
+      }
+      s_use[tid] = use;
+    }
+    __syncthreads();
+    // the sum over the ranks, in rank order on every rank: the replicated solves then start from identical bits
+    const int n2 = (n_rows * rowlen) >> 1;               // double2 entries (rowlen is a multiple of 36)
+    bool first = true;
+    for (int q = 0; q < pv.world; ++q) {
+      if (!s_use[q]) continue;
+      const double2* __restrict__ src = reinterpret_cast<const double2*>(pv.red[q] + (size_t)I0 * rowlen);
+      double2* dst = reinterpret_cast<double2*>(s_S);
+#pragma unroll 4
+      for (int e = tid; e < n2; e += nt) {
+        const double2 v = __ldcg(src + e);
+        if (first) dst[e] = v;
+        else { double2 o = dst[e]; o.x += v.x; o.y += v.y; dst[e] = o; }
+      }
+      if (tid < 6 * n_rows) {
+        const double vb = __ldcg(pv.red[q] + off_b + 6 * (size_t)I0 + tid);
+        const double vu = __ldcg(pv.red[q] + off_dU + 6 * (size_t)I0 + tid);
+        if (first) { s_b[tid] = vb; s_dU[tid] = vu; } else { s_b[tid] += vb; s_dU[tid] += vu; }
+      }
+      first = false;
+    }
+    if (i == 0 && tid == 0) {
+      double c = 0.0;
+      for (int q = 0; q < pv.world; ++q) c += __ldcg(pv.red[q] + off_cost);
+      s_cost = c;
+    }
+    __syncthreads();
+  }
+  auto S_at = [&](int I, int dq) -> double {             // entry dq of band row I of this super-block
+    return kPeers ? s_S[(size_t)(I - I0) * rowlen + dq] : w.S[(size_t)I * rowlen + dq];
+  };
   if (i == 0 && tid == 0) {
-    fail[0] = (ctl->solve_fail != 0) ? 1 : 0;
+    fail[0] = (ctl->solve_fail != 0 || (kPeers && s_late)) ? 1 : 0;
     fail[1] = 0;
     if (ctl->iter == 0) {
-      const double c0 = *w.cost_lin;
+      const double c0 = kPeers ? s_cost : *w.cost_lin;
       ctl->cost_cur = c0;
       ctl->cost_hist[0] = c0;
     }
@@ -107,14 +187,14 @@ k_bcr_assemble(Work w, double* __restrict__ D, double* __restrict__ L, double* _
     while (a * (a + 1) / 2 > blk) --a;
     while ((a + 1) * (a + 2) / 2 <= blk) ++a;
     const int c = blk - a * (a + 1) / 2;
-    const int I = kSB * i + a, J = kSB * i + c, d = I - J;
+    const int I = I0 + a, J = I0 + c, d = I - J;
     const int r = q / 6, cc = q - 6 * r;
     double v = 0.0;
     if (I < w.n_cam) {
-      if (d <= bw) v = w.S[(size_t)I * rowlen + d * 36 + q];
+      if (d <= bw) v = S_at(I, d * 36 + q);
       if (d == 0) {
         if (w.fixed[I] != 0) v = (r == cc) ? 1.0 : 0.0;
-        else if (r == cc) v += damp(w.diagU[6 * (size_t)I + r], lambda);
+        else if (r == cc) v += damp(kPeers ? s_dU[6 * a + r] : w.diagU[6 * (size_t)I + r], lambda);
       }
     } else if (d == 0) {
       v = (r == cc) ? 1.0 : 0.0;               // padding keyframes: identity
@@ -125,19 +205,21 @@ k_bcr_assemble(Work w, double* __restrict__ D, double* __restrict__ L, double* _
   for (int e = tid; e < kL; e += nt) {
     const int blk = e / 36, q = e - 36 * blk;
     const int a = blk / kSB, c = blk - kSB * a;
-    const int I = kSB * i + a, J = kSB * (i - 1) + c, d = I - J;
+    const int I = I0 + a, J = kSB * (i - 1) + c, d = I - J;
     double v = 0.0;
-    if (i > 0 && I < w.n_cam && d <= bw) v = w.S[(size_t)I * rowlen + d * 36 + q];
+    if (i > 0 && I < w.n_cam && d <= bw) v = S_at(I, d * 36 + q);
     Li[e] = v;
   }
   for (int e = tid; e < kV; e += nt) {
-    const int I = kSB * i + e / 6;
-    b[(size_t)i * kV + e] = (I < w.n_cam && w.fixed[I] == 0) ? w.b[6 * (size_t)kSB * i + e] : 0.0;
+    const int I = I0 + e / 6;
+    b[(size_t)i * kV + e] = (I < w.n_cam && w.fixed[I] == 0) ? (kPeers ? s_b[e] : w.b[6 * (size_t)I0 + e]) : 0.0;
   }
   __syncthreads();
-  // clear this super-block's rows of the accumulation buffers for the next LM iteration
+  // clear this super-block's rows of the accumulation buffers for the next LM iteration (with peers reading them the
+  // clearing waits for the candidate-cost all-reduce, which every rank reaches after this kernel: ba_api.cu)
+  if (kPeers) return;
   for (int a = 0; a < kSB; ++a) {
-    const int I = kSB * i + a;
+    const int I = I0 + a;
     if (I >= w.n_cam) break;
     for (int e = tid; e < rowlen; e += nt) w.S[(size_t)I * rowlen + e] = 0.0;
     if (tid < 6) { w.b[6 * (size_t)I + tid] = 0.0; w.diagU[6 * (size_t)I + tid] = 0.0; }
@@ -611,6 +693,8 @@ size_t bcr_workspace_doubles(int n_cam) { return make_plan(n_cam).total; }
 int configure_bcr() {
   cudaError_t e = cudaFuncSetAttribute(k_bcr_elim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)elim_smem());
   if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_bcr_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)assemble_smem());
+  if (e == cudaSuccess)
     e = cudaFuncSetAttribute(k_bcr_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem());
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(k_bcr_back, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)back_smem());
@@ -623,13 +707,19 @@ static int pick_ks(int n_fine, int P) {
   return per * 4 <= kUT ? 4 : (per * 2 <= kUT ? 2 : 1);
 }
 
-int launch_rcs_bcr(const Work& w, double* ws, cudaStream_t s, int sm_count) {
+int launch_rcs_bcr(const Work& w, double* ws, cudaStream_t s, int sm_count, const PeerView* pv, int it) {
   const BcrPlan p = make_plan(w.n_cam);
   int* fail = reinterpret_cast<int*>(ws + p.off_fail);
   double* x = ws + p.off_x;
   int launches = 0;
   if (sm_count <= 0) sm_count = 148;
-  k_bcr_assemble<<<p.N[0], 256, 0, s>>>(w, ws + p.off_D[0], ws + p.off_L[0], ws + p.off_b[0], fail);
+  if (pv != nullptr && pv->world > 1) {
+    k_bcr_assemble<true><<<p.N[0], 256, assemble_smem(), s>>>(w, ws + p.off_D[0], ws + p.off_L[0], ws + p.off_b[0], fail, *pv, it);
+  } else {
+    PeerView none;
+    memset(&none, 0, sizeof(none));
+    k_bcr_assemble<false><<<p.N[0], 256, 0, s>>>(w, ws + p.off_D[0], ws + p.off_L[0], ws + p.off_b[0], fail, none, it);
+  }
   ++launches;
   for (int l = 0; l < p.n_levels; ++l) {
     const int N = p.N[l], ne = elim_count(N);

@@ -39,6 +39,7 @@ struct LmCtl {
   int solve_fail_hist[64];
   int pcg_iters_hist[64];
   unsigned char accepted[64];
+  long long epoch_base;   // sharded runs with the peer-memory exchange: 64 * (solves so far), set by k_init
 };
 
 __device__ __forceinline__ double huber_rho(double r, double delta) {

@@ -95,6 +95,7 @@ __device__ __forceinline__ double* s_block_ptr(const Work& w, int a, int b) {
 // launch wrappers; every one returns the number of kernels it launched
 struct LmInit {
   double lambda0, huber_delta, chi2_thr, lambda_up, lambda_down, lambda_min, lambda_max, accept_rtol;
+  long long epoch_base;   // 0 unless the peer-memory exchange is on
 };
 int launch_init(const Work& w, const double* R_in, const double* t_in, const double* X_in,
                 const LmInit& p, cudaStream_t s);
@@ -114,6 +115,7 @@ bool panel_supported(const Work& w);
 // along.  Buffers are the caller's workspace: cnt [panel_classes + 1] 64-bit, perm [n_pt], off [n_pt + 1],
 // cam / pt [n_obs], uv [2 n_obs].  `w` keeps the caller's arrays; the caller switches the pointers afterwards.
 struct PanelOrder {
+  int* range;                               // [2] first / last camera of the shard (min / max over the points)
   unsigned long long* cnt;
   int* perm;
   int* off;
@@ -139,7 +141,21 @@ int launch_rcs_band(const Work& w, cudaStream_t s);
 bool bcr_supported(int n_cam, int band_w);
 size_t bcr_workspace_doubles(int n_cam);
 int configure_bcr();
-int launch_rcs_bcr(const Work& w, double* ws, cudaStream_t s, int sm_count = 0);
+// Sharded runs, banded path: instead of an NCCL all-reduce of S | b | diagU | cost in front of the solver, the solver's
+// first kernel (k_bcr_assemble) sums the ranks' reduction buffers itself over NVLink peer memory (CUDA IPC mappings)
+// while it builds level 0 -- one kernel for the exchange and the assembly.  red[q] = rank q's reduction buffer (own
+// at [rank]); flags: one 64-bit epoch per (owner, poster); a rank posts "my linearisation of epoch e is complete" into
+// every peer's flag array and waits until every peer has posted e into its own (e = LmCtl::epoch_base + LM iteration + 1,
+// from device memory: the LM loop is a replayed CUDA graph).  world <= 1: no exchange.
+constexpr int kMaxPeers = 8;
+struct PeerView {
+  int world, rank;
+  const double* red[kMaxPeers];
+  long long* flag_remote[kMaxPeers];        // this rank's slot in rank q's flag array (4 words: epoch | first camera | last camera | -)
+  const long long* flag_local;              // this rank's flag array, one slot per poster
+  const int* cam_range;                     // [2] first / last camera this rank's shard observes
+};
+int launch_rcs_bcr(const Work& w, double* ws, cudaStream_t s, int sm_count = 0, const PeerView* pv = nullptr, int it = 0);
 int configure_band();
 int band_max_w();
 int launch_backsub(const Work& w, int sm_count, cudaStream_t s);

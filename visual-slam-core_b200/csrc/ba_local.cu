@@ -73,6 +73,7 @@ __global__ void k_init(Work w, const double* __restrict__ R_in, const double* __
     c->lambda_min = p.lambda_min;
     c->lambda_max = p.lambda_max;
     c->accept_rtol = p.accept_rtol;
+    c->epoch_base = p.epoch_base;
     c->cost_cur = 0.0;
     c->cost_cand = 0.0;
     c->cost_lin = 0.0;

@@ -296,11 +296,11 @@ __global__ void k_cs_fill(Work w) {
 // observation) pair; the order inside a class is whatever the atomics make it, the observations of a point keep theirs.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kSpanClasses = 32;
-__device__ __forceinline__ int point_class(const Work& w, int j, int& k) {
+__device__ __forceinline__ int point_class(const Work& w, int j, int& k, int& cmin, int& cmax) {
   const int o0 = __ldg(w.pt_off + j);
   k = __ldg(w.pt_off + j + 1) - o0;
+  cmin = 0x7fffffff; cmax = -1;
   if (k <= 0) return w.n_cam * kSpanClasses;            // no observation: behind everything
-  int cmin = 0x7fffffff, cmax = -1;
   for (int i = 0; i < k; ++i) {
     const int c = __ldg(w.obs_cam + o0 + i);
     cmin = min(cmin, c);
@@ -308,12 +308,22 @@ __device__ __forceinline__ int point_class(const Work& w, int j, int& k) {
   }
   return cmin * kSpanClasses + min(cmax - cmin, kSpanClasses - 1);
 }
-__global__ void k_ro_count(Work w, unsigned long long* __restrict__ cnt) {
+__global__ void k_ro_count(Work w, unsigned long long* __restrict__ cnt, int* __restrict__ range) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  int lo = 0x7fffffff, hi = -1;
   for (int j = tid; j < w.n_pt; j += nth) {
-    int k;
-    const int key = point_class(w, j, k);
+    int k, cmin, cmax;
+    const int key = point_class(w, j, k, cmin, cmax);
     atomicAdd(cnt + key, (1ull << 32) | (unsigned long long)max(k, 0));
+    lo = min(lo, cmin);
+    hi = max(hi, cmax);
+  }
+  // the shard's camera range (the sharded solver skips peers whose range misses a row of the reduced camera system)
+  lo = __reduce_min_sync(kFull, lo);
+  hi = __reduce_max_sync(kFull, hi);
+  if ((threadIdx.x & 31) == 0) {
+    if (lo != 0x7fffffff) atomicMin(range, lo);
+    if (hi >= 0) atomicMax(range + 1, hi);
   }
 }
 // one block: exclusive scan of the class counters in place (they become the scatter cursors)
@@ -344,8 +354,8 @@ __global__ void k_ro_scatter(Work w, PanelOrder o) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   if (tid == 0) o.off[w.n_pt] = w.n_obs;
   for (int j = tid; j < w.n_pt; j += nth) {
-    int k;
-    const int key = point_class(w, j, k);
+    int k, cmin, cmax;
+    const int key = point_class(w, j, k, cmin, cmax);
     const unsigned long long at = atomicAdd(o.cnt + key, (1ull << 32) | (unsigned long long)max(k, 0));
     const int pos = (int)(at >> 32), ob = (int)(at & 0xffffffffull);
     o.perm[pos] = j;
@@ -1053,10 +1063,12 @@ size_t panel_classes(int n_cam) { return (size_t)n_cam * kSpanClasses + 1; }
 int launch_panel_reorder(const Work& w, const PanelOrder& o, cudaStream_t s) {
   const int ncls = (int)panel_classes(w.n_cam);
   cudaMemsetAsync(o.cnt, 0, sizeof(unsigned long long) * (size_t)(ncls + 1), s);
+  static const int kEmptyRange[2] = {0x7fffffff, -1};
+  cudaMemcpyAsync(o.range, kEmptyRange, sizeof(kEmptyRange), cudaMemcpyHostToDevice, s);
   int blocks = (w.n_pt + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  k_ro_count<<<blocks, 256, 0, s>>>(w, o.cnt);
+  k_ro_count<<<blocks, 256, 0, s>>>(w, o.cnt, o.range);
   k_ro_scan<<<1, 1024, 0, s>>>(o.cnt, ncls);
   k_ro_scatter<<<blocks, 256, 0, s>>>(w, o);
   return 3;
