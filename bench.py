@@ -858,7 +858,10 @@ def run_b200(args, rank, local_rank, world):
         "config": {"workload": workload_name(args.config, full.n_cam, full.n_pt, full.n_obs),
                    "lm_iterations_per_step": max_iter,
                    "parallelism": "single GPU" if world == 1 else
-                                  f"points sharded over {world} GPUs (cameras replicated), NCCL all-reduce of the reduced camera system and the costs every LM iteration",
+                                  (f"points sharded over {world} GPUs (cameras replicated); every LM iteration the reduced camera system is summed over "
+                                   "NVLink peer memory inside the solver's first kernel (CUDA IPC mappings, flag handshake; its time is in rcs_solve) and the "
+                                   "candidate cost goes through an NCCL all-reduce (nccl_allreduce)" if int(getattr(r_prof, "peer_exchange", 0)) else
+                                   f"points sharded over {world} GPUs (cameras replicated), NCCL all-reduce of the reduced camera system and the costs every LM iteration"),
                    "solver": {"used": {1: "cholesky", 2: "pcg", 3: "band"}.get(int(r_prof.solver_used), "?"),
                               "band_width": int(r_prof.band_width), "s_blocks": int(r_prof.s_blocks)},
                    "l2": "flushed between steps (256 MiB write); the window itself is larger than L2",

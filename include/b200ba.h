@@ -108,9 +108,12 @@ typedef struct ba_report {
   float ms_other;                       /* init + finalize */
   int32_t band_width;                   /* BA_SOLVER_BAND: co-visibility bandwidth in keyframes, else -1 */
   int32_t s_blocks;                     /* 6x6 blocks of the reduced camera matrix that are stored / all-reduced */
-  float ms_comm;                        /* profile=1, sharded: NCCL all-reduces (reduced camera system, candidate cost + accept) */
+  float ms_comm;                        /* profile=1, sharded: NCCL collectives (candidate cost + solve-failed flag; the reduced camera
+                                           system and the camera-state broadcast where the peer exchange is off) */
   float ms_point_blocks;                /* profile=1, panel path: the point-block pass inside ms_linearize */
   float ms_cam_blocks;                  /* profile=1, panel path: the camera-major pass inside ms_linearize */
+  int32_t peer_exchange;                /* sharded: 1 = the solver's first kernel summed the ranks' reduced camera systems over
+                                           NVLink peer memory (its time is inside ms_solve), 0 = ncclAllReduce in front of it */
 } ba_report;
 
 typedef struct ba_handle ba_handle;

@@ -39,6 +39,7 @@ class BAReport(C.Structure):
         ("ms_linearize", C.c_float), ("ms_solve", C.c_float), ("ms_backsub", C.c_float),
         ("ms_other", C.c_float), ("band_width", C.c_int32), ("s_blocks", C.c_int32),
         ("ms_comm", C.c_float), ("ms_point_blocks", C.c_float), ("ms_cam_blocks", C.c_float),
+        ("peer_exchange", C.c_int32),
     ]
 
 

@@ -720,6 +720,7 @@ static void fill_report(const ba_handle* h, const LmCtl* c, ba_report* rep, int 
   rep->ms_linearize = h->prof_ms[TAG_LIN] + h->prof_ms[TAG_LIN_PB] + h->prof_ms[TAG_LIN_CAM];
   rep->ms_point_blocks = h->prof_ms[TAG_LIN_PB];
   rep->ms_cam_blocks = h->prof_ms[TAG_LIN_CAM];
+  rep->peer_exchange = (h->world > 1 && h->peer.open && h->last_solver == BA_SOLVER_BAND) ? 1 : 0;
   rep->ms_solve = h->prof_ms[TAG_SOLVE];
   rep->ms_backsub = h->prof_ms[TAG_BACK];
   rep->ms_other = h->prof_ms[TAG_OTHER];

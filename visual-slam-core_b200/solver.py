@@ -176,7 +176,8 @@ class LocalBASolver:
                        ms_backsub=float(rep.ms_backsub), ms_other=float(rep.ms_other), ms_comm=float(rep.ms_comm),
                        ms_point_blocks=float(rep.ms_point_blocks), ms_cam_blocks=float(rep.ms_cam_blocks),
                        solver_used={1: "cholesky", 2: "pcg", 3: "band"}.get(int(rep.solver_used), "?"),
-                       band_width=int(rep.band_width), s_blocks=int(rep.s_blocks)))
+                       band_width=int(rep.band_width), s_blocks=int(rep.s_blocks),
+                       peer_exchange=int(rep.peer_exchange)))
 
     # ------------------------------------------------------------------ local BA, torch CUDA tensors
     def solve_local_device(self, intr, R, t, fixed, X, obs_cam, obs_pt, obs_uv, pt_offsets,
