@@ -773,14 +773,17 @@ static int backsub_group(const Work& w) {
   if (forced < 0) {
     const char* e = getenv("BA_BACKSUB_GROUP");
     const int v = e ? atoi(e) : 0;
-    forced = (v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ? v : 0;
+    forced = (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ? v : 0;
   }
   if (forced) return forced;
   if (w.n_pt <= 0) return 32;
-  // measured on B200 (C1 / C2 / C4, 10 / 14.6 / 8 observations per point): 4 lanes per point beat 8, 16 and 32
-  // everywhere -- the kernel is bound by the latency of a point's chain, so more points in flight win
+  // measured on B200 (C1 / C2 / C4, 10 / 14.6 / 8 observations per point): the kernel is bound by the latency of a
+  // point's chain, so more points in flight win -- 4 lanes per point beat 8, 16 and 32 everywhere, and where the points
+  // alone fill the machine fewer still: C4 (1 M points) 0.190 / 0.203 / 0.255 ms with 1 / 2 / 4 lanes, C2 (10 k points)
+  // 24.9 / 18.8 / 14.8 us, C1 (2 k) 15.9 / 13.5 / 12.1 us
   const double mean = (double)w.n_obs / (double)w.n_pt;
-  return mean <= 24.0 ? 4 : (mean <= 48.0 ? 8 : (mean <= 96.0 ? 16 : 32));
+  if (mean <= 24.0) return w.n_pt >= 100000 ? 1 : (w.n_pt >= 40000 ? 2 : 4);
+  return mean <= 48.0 ? 8 : (mean <= 96.0 ? 16 : 32);
 }
 
 template <bool kStaged>
@@ -790,7 +793,8 @@ static void launch_backsub_g(const Work& w, int g, int sm_count, cudaStream_t s)
   const int cap = sm_count * BA_BACKSUB_MIN_CTAS;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  if (g == 2) k_backsub<kStaged, 2><<<blocks, kThreads, 0, s>>>(w);
+  if (g == 1) k_backsub<kStaged, 1><<<blocks, kThreads, 0, s>>>(w);
+  else if (g == 2) k_backsub<kStaged, 2><<<blocks, kThreads, 0, s>>>(w);
   else if (g == 4) k_backsub<kStaged, 4><<<blocks, kThreads, 0, s>>>(w);
   else if (g == 8) k_backsub<kStaged, 8><<<blocks, kThreads, 0, s>>>(w);
   else if (g == 16) k_backsub<kStaged, 16><<<blocks, kThreads, 0, s>>>(w);

@@ -25,6 +25,7 @@
 //   camera (accumulators flushed by REDs, entries that are exactly zero skipped).
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "ba_kernels.cuh"
 #include "ba_scatter.cuh"
@@ -1090,11 +1091,27 @@ int launch_panel_setup(const Work& w, int sm_count, cudaStream_t s) {
 int launch_linearize_panel(const Work& w, int sm_count, cudaStream_t s, cudaEvent_t* marks) {
   // marks (profile mode, else null): events after the point-block pass and after the camera pass
   // lanes per point of the point-block pass: the mean observation count picks it
+  // lanes per point of the point-block pass.  The pass is bound by the latency of a point's chain (offsets -> observation
+  // -> pose gather -> 3x3 factor by one lane of the group), so what counts is points in flight: with enough points to
+  // fill the machine ONE lane per point wins (C4, 1 M points, 8 observations each: 0.128 ms against 0.132 / 0.174 /
+  // 0.276 / 0.489 ms with 2 / 4 / 8 / 16 lanes); small windows need the lanes for parallelism.  BA_PB_GROUP overrides.
   const double mean_k = w.n_pt > 0 ? (double)w.n_obs / (double)w.n_pt : 0.0;
-  if (mean_k <= 6.0) launch_pb<4>(w, sm_count, s);
-  else if (mean_k <= 12.0) launch_pb<8>(w, sm_count, s);
-  else if (mean_k <= 24.0) launch_pb<16>(w, sm_count, s);
-  else launch_pb<32>(w, sm_count, s);
+  static int force_g = -1;
+  if (force_g < 0) { const char* e = getenv("BA_PB_GROUP"); force_g = e ? atoi(e) : 0; }
+  int g = force_g;
+  if (g != 1 && g != 2 && g != 4 && g != 8 && g != 16 && g != 32) {
+    if (mean_k <= 16.0 && w.n_pt >= 100000) g = 1;
+    else if (mean_k <= 16.0 && w.n_pt >= 40000) g = 2;
+    else g = mean_k <= 6.0 ? 4 : (mean_k <= 12.0 ? 8 : (mean_k <= 24.0 ? 16 : 32));
+  }
+  switch (g) {
+    case 1: launch_pb<1>(w, sm_count, s); break;
+    case 2: launch_pb<2>(w, sm_count, s); break;
+    case 4: launch_pb<4>(w, sm_count, s); break;
+    case 8: launch_pb<8>(w, sm_count, s); break;
+    case 16: launch_pb<16>(w, sm_count, s); break;
+    default: launch_pb<32>(w, sm_count, s); break;
+  }
   if (marks) cudaEventRecord(marks[0], s);
   {
     const int warps = (w.cs_nblk_max + kCamBlocksPerWarp - 1) / kCamBlocksPerWarp;
