@@ -264,7 +264,6 @@ __global__ void k_cs_scan(Work w) {
     if (a < w.n_cam) {
       w.cs_blk_off[a] = excl;
       w.cs_cnt[a] = 0;                                   // becomes the fill cursor
-      for (int b = 0; b < nb; ++b) w.cs_blk_cam[excl + b] = a;
     }
     __syncthreads();
     if (tid == 1023) s_carry += s_part[1023];
@@ -275,6 +274,17 @@ __global__ void k_cs_scan(Work w) {
 __global__ void k_cs_fill(Work w) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
+  // block -> camera table: a binary search over the cameras' first blocks per block (the scan kernel used to write it,
+  // one thread per camera and 250 entries each at C4: 133 us on one SM)
+  const int nblk = __ldg(w.cs_blk_off + w.n_cam);
+  for (int b = tid; b < nblk; b += nth) {
+    int lo = 0, hi = w.n_cam - 1;                        // last camera whose first block is <= b
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(w.cs_blk_off + mid) <= b) lo = mid; else hi = mid - 1;
+    }
+    w.cs_blk_cam[b] = lo;
+  }
   for (int o = tid; o < w.n_obs; o += nth) {
     const int c = __ldg(w.obs_cam + o);
     const unsigned peers = __match_any_sync(__activemask(), c);
@@ -373,7 +383,7 @@ __global__ void k_ro_scatter(Work w, PanelOrder o) {
 // ------------------------------------------------------------------------------------------------------------
 // k_cam_blocks
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kCamBlocksPerWarp = 8;      // 256 observations between two flushes
+constexpr int kCamBlocksPerWarp = 16;     // 512 observations between two flushes (C4: 0.277 / 0.246 / 0.233 / 0.240 ms with 4 / 8 / 16 / 32)
 
 __device__ __forceinline__ void cam_flush(const Work& w, int cam, int lane, double (&acc)[27]) {
   // butterfly over the lanes, 27 sums side by side; lane q then owns entry q
@@ -403,7 +413,7 @@ __device__ __forceinline__ void cam_flush(const Work& w, int cam, int lane, doub
 }
 
 __global__ void __launch_bounds__(256, 2)
-k_cam_blocks(const __grid_constant__ Work w) {
+k_cam_blocks(const __grid_constant__ Work w, const int per_warp) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nblk = *w.cs_nblk;
@@ -413,9 +423,9 @@ k_cam_blocks(const __grid_constant__ Work w) {
   const double* __restrict__ pose = w.pose[cur];
   const double* __restrict__ X = w.X[cur];
   const Rec* __restrict__ rec = reinterpret_cast<const Rec*>(w.rec);
-  const int b0 = warp * kCamBlocksPerWarp;
+  const int b0 = warp * per_warp;
   if (b0 >= nblk) return;
-  const int b1 = min(nblk, b0 + kCamBlocksPerWarp);
+  const int b1 = min(nblk, b0 + per_warp);
   double acc[27];
 #pragma unroll
   for (int q = 0; q < 27; ++q) acc[q] = 0.0;
@@ -1114,9 +1124,11 @@ int launch_linearize_panel(const Work& w, int sm_count, cudaStream_t s, cudaEven
   }
   if (marks) cudaEventRecord(marks[0], s);
   {
-    const int warps = (w.cs_nblk_max + kCamBlocksPerWarp - 1) / kCamBlocksPerWarp;
+    static int per_warp = -1;          // diagnostics: BA_CAM_BLOCKS = 32-observation blocks between two flushes of a warp
+    if (per_warp < 0) { const char* e = getenv("BA_CAM_BLOCKS"); per_warp = (e && atoi(e) > 0) ? atoi(e) : kCamBlocksPerWarp; }
+    const int warps = (w.cs_nblk_max + per_warp - 1) / per_warp;
     const int blocks = (warps + 7) / 8;
-    k_cam_blocks<<<blocks < 1 ? 1 : blocks, 256, 0, s>>>(w);
+    k_cam_blocks<<<blocks < 1 ? 1 : blocks, 256, 0, s>>>(w, per_warp);
   }
   if (marks) cudaEventRecord(marks[1], s);
   k_schur_panel<<<w.part_n, kThreadsP, sizeof(PanelSmem), s>>>(w);
