@@ -92,7 +92,8 @@ struct ba_handle {
   size_t h_small_cap = 0;         // bytes
   DevBuf d_small;
   cudaStream_t stream = nullptr;  // used by the host API
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_val = nullptr;
+  DevBuf d_bad;                   // verdict of k_validate
   // CUDA graph cache of the LM loop
   cudaGraphExec_t graph = nullptr;
   struct GraphKey {
@@ -362,6 +363,7 @@ extern "C" int ba_create(const ba_params* params, int device, ba_handle** out) {
   }
   if ((ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (ce = cudaEventCreate(&h->ev0)) != cudaSuccess || (ce = cudaEventCreate(&h->ev1)) != cudaSuccess ||
+      (ce = cudaEventCreateWithFlags(&h->ev_val, cudaEventDisableTiming)) != cudaSuccess ||
       (ce = cudaMallocHost((void**)&h->h_ctl, sizeof(LmCtl))) != cudaSuccess ||
       (ce = cudaMallocHost((void**)&h->h_nnzb, sizeof(int))) != cudaSuccess) {
     g_create_err = std::string("handle resources: ") + cudaGetErrorString(ce);
@@ -395,7 +397,7 @@ extern "C" int ba_destroy(ba_handle* h) {
                     &h->bits, &h->wpre, &h->row_nnz, &h->row_ptr, &h->col_idx, &h->tpos, &h->pcg,
                     &h->bits_all, &h->band_L, &h->band_y, &h->band_dinv, &h->band_wbuf, &h->bcr,
                     &h->ro_cnt, &h->ro_perm, &h->ro_off, &h->ro_cam, &h->ro_pt, &h->ro_uv,
-                    &h->peer.flagbuf, &h->peer.xbuf, &h->ro_range};
+                    &h->peer.flagbuf, &h->peer.xbuf, &h->ro_range, &h->d_bad};
   peer_unmap(h);
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
@@ -406,6 +408,7 @@ extern "C" int ba_destroy(ba_handle* h) {
   if (h->h_nnzb) cudaFreeHost(h->h_nnzb);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_val) cudaEventDestroy(h->ev_val);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return BA_OK;
@@ -857,17 +860,14 @@ extern "C" int ba_solve_local_host(ba_handle* h, int32_t n_cam, int32_t n_pt, in
   if (n_cam <= 0 || n_pt < 0 || n_obs < 0 || !intr || !cam_R || !cam_t || !cam_fixed ||
       (n_pt > 0 && (!X || !pt_offsets)) || (n_obs > 0 && (!obs_cam || !obs_uv)))
     return BA_ERR_INVALID;
-  // host arrays are cheap to check and the kernels index with them unchecked
+  // the kernels index with the offsets and camera indices unchecked: the ends are looked at here, everything in between
+  // by a kernel once the arrays are on the device (k_validate; the host loops cost 2-3 ms of a C4 call)
   if (n_pt > 0) {
     if (pt_offsets[0] != 0 || pt_offsets[n_pt] != n_obs) { h->err = "pt_offsets must start at 0 and end at n_obs"; return BA_ERR_INVALID; }
-    for (int32_t j = 0; j < n_pt; ++j)
-      if (pt_offsets[j + 1] < pt_offsets[j]) { h->err = "pt_offsets must be non-decreasing"; return BA_ERR_INVALID; }
   } else if (n_obs != 0) {
     h->err = "observations without points";
     return BA_ERR_INVALID;
   }
-  for (int32_t o = 0; o < n_obs; ++o)
-    if ((uint32_t)obs_cam[o] >= (uint32_t)n_cam) { h->err = "obs_cam out of range"; return BA_ERR_INVALID; }
   DeviceGuard dev_guard(h->device);
   cudaStream_t s = h->stream;
   int rc;
@@ -894,15 +894,22 @@ extern "C" int ba_solve_local_host(ba_handle* h, int32_t n_cam, int32_t n_pt, in
   double* d_t = d_R + nR;
   const uint8_t* d_fixed = (const uint8_t*)(d_t + nT);
   CK(cudaMemcpyAsync(h->d_small.p, h->h_small, small_bytes, cudaMemcpyHostToDevice, s));
-  if (n_pt > 0) {
-    CK(cudaMemcpyAsync(h->d_off.p, pt_offsets, sizeof(int32_t) * (size_t)(n_pt + 1), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_X.p, X, sizeof(double) * 3 * (size_t)n_pt, cudaMemcpyHostToDevice, s));
-    if (n_obs > 0) launch_expand_obs_pt((const int*)h->d_off.p, n_pt, (int*)h->d_opt.p, s);
+  // indices first, their check behind them; the host looks at its verdict while the big arrays are still on their way
+  if ((rc = ensure(h, h->d_bad, 64))) return rc;
+  if (n_pt > 0) CK(cudaMemcpyAsync(h->d_off.p, pt_offsets, sizeof(int32_t) * (size_t)(n_pt + 1), cudaMemcpyHostToDevice, s));
+  if (n_obs > 0) CK(cudaMemcpyAsync(h->d_ocam.p, obs_cam, sizeof(int32_t) * (size_t)n_obs, cudaMemcpyHostToDevice, s));
+  launch_validate(n_cam, n_pt, n_obs, (const int*)h->d_ocam.p, (const int*)h->d_off.p, (int*)h->d_bad.p, s);
+  CK(cudaMemcpyAsync(h->h_nnzb, h->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(h->ev_val, s));
+  if (n_pt > 0) CK(cudaMemcpyAsync(h->d_X.p, X, sizeof(double) * 3 * (size_t)n_pt, cudaMemcpyHostToDevice, s));
+  if (n_obs > 0) CK(cudaMemcpyAsync(h->d_ouv.p, obs_uv, sizeof(float) * 2 * (size_t)n_obs, cudaMemcpyHostToDevice, s));
+  CK(cudaEventSynchronize(h->ev_val));
+  if (*h->h_nnzb != 0) {
+    cudaStreamSynchronize(s);
+    h->err = (*h->h_nnzb & 1) ? "pt_offsets must be non-decreasing" : "obs_cam out of range";
+    return BA_ERR_INVALID;
   }
-  if (n_obs > 0) {
-    CK(cudaMemcpyAsync(h->d_ocam.p, obs_cam, sizeof(int32_t) * (size_t)n_obs, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_ouv.p, obs_uv, sizeof(float) * 2 * (size_t)n_obs, cudaMemcpyHostToDevice, s));
-  }
+  if (n_pt > 0 && n_obs > 0) launch_expand_obs_pt((const int*)h->d_off.p, n_pt, (int*)h->d_opt.p, s);
   rc = ba_solve_local(h, n_cam, n_pt, n_obs, intr, d_R, d_t, d_fixed, (double*)h->d_X.p,
                       (const int32_t*)h->d_ocam.p, (const int32_t*)h->d_opt.p, (const float*)h->d_ouv.p,
                       (const int32_t*)h->d_off.p, flags ? (uint8_t*)h->d_flags.p : nullptr, s, nullptr);

@@ -163,6 +163,7 @@ int launch_accept(const Work& w, cudaStream_t s);
 int launch_cost0(const Work& w, cudaStream_t s);   // max_iter == 0: cost_cand -> cost_hist[0]
 int launch_finalize(const Work& w, double* R_out, double* t_out, double* X_out,
                     unsigned char* flags, cudaStream_t s);
+int launch_validate(int n_cam, int n_pt, int n_obs, const int* obs_cam, const int* pt_off, int* bad, cudaStream_t s);
 int launch_expand_obs_pt(const int* pt_off, int n_pt, int* obs_pt, cudaStream_t s);   // CSR offsets -> point of every observation
 int launch_eval_cost(const Work& w, const double* pose, const double* X, double* out,
                      double delta, cudaStream_t s);
