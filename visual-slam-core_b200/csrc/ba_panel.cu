@@ -432,8 +432,19 @@ k_cam_blocks(const __grid_constant__ Work w, const int per_warp) {
   int cam = -1;
   bool free_cam = false;
   double P[12];
+  // the block's camera, point and pixel are fetched one block ahead: what is left of the chain table -> point -> gather
+  // inside a trip is the gather of X_j and q_j
+  int c_n = __ldg(w.cs_blk_cam + b0);
+  int j_n = __ldg(w.cs_pt + 32 * (size_t)b0 + lane);
+  float2 uv_n = __ldg(w.cs_uv + 32 * (size_t)b0 + lane);
   for (int b = b0; b < b1; ++b) {
-    const int c = __ldg(w.cs_blk_cam + b);
+    const int c = c_n, j = j_n;
+    const float2 uv = uv_n;
+    if (b + 1 < b1) {
+      c_n = __ldg(w.cs_blk_cam + b + 1);
+      j_n = __ldg(w.cs_pt + 32 * (size_t)(b + 1) + lane);
+      uv_n = __ldg(w.cs_uv + 32 * (size_t)(b + 1) + lane);
+    }
     if (c != cam) {
       if (cam >= 0 && free_cam) cam_flush(w, cam, lane, acc);
       cam = c;
@@ -442,9 +453,7 @@ k_cam_blocks(const __grid_constant__ Work w, const int per_warp) {
       for (int q = 0; q < 12; ++q) P[q] = __ldg(pose + 12 * (size_t)c + q);
     }
     if (!free_cam) continue;
-    const int j = __ldg(w.cs_pt + 32 * (size_t)b + lane);
     if (j < 0) continue;
-    const float2 uv = __ldg(w.cs_uv + 32 * (size_t)b + lane);
     const double X0 = X[3 * (size_t)j], X1 = X[3 * (size_t)j + 1], X2 = X[3 * (size_t)j + 2];
     const double q0 = rec[j].q[0], q1 = rec[j].q[1], q2 = rec[j].q[2];
     ObsLin ol;
