@@ -490,6 +490,7 @@ struct __align__(16) PanelSmem {
   uint64_t bar[kNG][2];                 // mbarriers of the input stages
   int bounds[kBoundsCap + 1];           // pt_off at the panel boundaries of this CTA (one super-chunk)
   unsigned char piv[kNB][16];           // per point slot: first | last << 4 tile (8 columns) of the point's camera interval (0xff: none)
+  unsigned char puni[kNB][4];           // [0]: the one tile interval (first | last << 4) all twelve points of the panel share, 0xff: none
   int pbase[kNB];                       // window base the panel was staged with
   int pnpts[kNB];
   int gbase[kNG];                       // the group's snapshot of cur_base for the panel it is staging
@@ -687,6 +688,23 @@ __device__ __forceinline__ void strip_runs(const double* __restrict__ Ya, const 
   }
 }
 
+// a strip x ALL twelve points of a panel (class order: most panels hold one camera interval): straight-line code, no
+// masks, no trip counts
+template <bool kPair>
+__device__ __forceinline__ void strip_full(const double* __restrict__ Ya, const double* __restrict__ Yb, double (&acc)[2][2]) {
+#pragma unroll
+  for (int t = 0; t < kPP; ++t) {
+    const double a_ = Ya[t * (4 * kYS)];
+    if (kPair) {
+      const double b0_ = Yb[t * (4 * kYS)], b1_ = Yb[t * (4 * kYS) + 8];
+      dmma(acc[0][0], acc[0][1], a_, b0_);
+      dmma(acc[1][0], acc[1][1], a_, b1_);
+    } else {
+      dmma(acc[0][0], acc[0][1], a_, a_);
+    }
+  }
+}
+
 __device__ __forceinline__ void mma_warp(const Work& w, PanelSmem& sm, int mw, int lane, int n_panels) {
   double acc[kSlots][2][2];
 #pragma unroll
@@ -729,6 +747,17 @@ __device__ __forceinline__ void mma_warp(const Work& w, PanelSmem& sm, int mw, i
       acc_base = base_n;
     }
     const int npts = sm.pnpts[g];
+    const double* Yg = sm.Yt[g] + foff;
+    const int pu = sm.puni[g][0];
+    if (pu != 0xff) {
+      // one interval for the whole panel: a strip is in or out as a whole
+      const int lo = pu & 15, hi = pu >> 4, lo2 = lo >> 1;
+      pmark(w, mw == 0 && lane == 0 && n >= kTrace0 && n < kTrace0 + 8, 101 + 4 * (n - kTrace0), 1000 + 10 * n + 2);
+      if (si[0] >= lo && si[0] <= hi) strip_full<false>(Yg + 8 * si[0], Yg, acc[0]);
+#pragma unroll
+      for (int s = 1; s < kSlots; ++s)
+        if (si[s] >= lo && si[s] <= hi && sj[s] >= lo2) strip_full<true>(Yg + 8 * si[s], Yg + 16 * sj[s], acc[s]);
+    } else {
     // lane p speaks for point p: its tile interval [lo, hi] (lo > hi: the point is not in the panel product)
     int lo = 15, hi = -1;
     if (lane < npts) {
@@ -736,7 +765,6 @@ __device__ __forceinline__ void mma_warp(const Work& w, PanelSmem& sm, int mw, i
       if (iv != 0xff) { lo = iv & 15; hi = iv >> 4; }
     }
     const int lo2 = lo >> 1;
-    const double* Yg = sm.Yt[g] + foff;
     pmark(w, mw == 0 && lane == 0 && n >= kTrace0 && n < kTrace0 + 8, 101 + 4 * (n - kTrace0), 1000 + 10 * n + 2);
     {
       const unsigned pm = __ballot_sync(kFull, si[0] >= lo && si[0] <= hi);
@@ -746,6 +774,7 @@ __device__ __forceinline__ void mma_warp(const Work& w, PanelSmem& sm, int mw, i
     for (int s = 1; s < kSlots; ++s) {
       const unsigned pm = __ballot_sync(kFull, si[s] >= lo && si[s] <= hi && sj[s] >= lo2);
       strip_runs<true>(Yg + 8 * si[s], Yg + 16 * sj[s], pm, acc[s]);
+    }
     }
     pmark(w, mw == 0 && lane == 0 && n >= kTrace0 && n < kTrace0 + 8, 102 + 4 * (n - kTrace0), 1000 + 10 * n + 3);
     pmark(w, lane == 0 && n >= kTrace0 && n < kTrace0 + 8, 400 + 16 * (n - kTrace0) + 2 * mw + 1, 20000 + 1000 * mw + 10 * (n - kTrace0) + 3);
@@ -930,18 +959,20 @@ k_schur_panel(const __grid_constant__ Work w) {
 
       // slot intervals + the books, by the group's service warp
       if (sl >= 0) {
-        if (sl < npts) {
-          int iv = 0xff;                                  // no interval: skipped by the mma warps
-          if (!(my_flags & kFlagSkip)) {
-            const bool fits = myrec.cmin >= base && my_cmax < base + kWin;
-            if (fits && !(my_flags & kFlagFallback) && !overflow) {
-              const int lo = (6 * (myrec.cmin - base)) >> 3, hi = (6 * (my_cmax - base) + 5) >> 3;   // tiles of 8 columns
-              iv = lo | (hi << 4);
-            }
+        int iv = 0xff;                                    // no interval: skipped by the mma warps
+        if (sl < npts && !(my_flags & kFlagSkip)) {
+          const bool fits = myrec.cmin >= base && my_cmax < base + kWin;
+          if (fits && !(my_flags & kFlagFallback) && !overflow) {
+            const int lo = (6 * (myrec.cmin - base)) >> 3, hi = (6 * (my_cmax - base) + 5) >> 3;   // tiles of 8 columns
+            iv = lo | (hi << 4);
           }
-          sm.piv[pb][sl] = (unsigned char)iv;
         }
+        if (sl < npts) sm.piv[pb][sl] = (unsigned char)iv;
+        // all twelve points in one interval (class order): the mma warps take their strips whole
+        const int iv0 = __shfl_sync(kFull, iv, 0);
+        const bool uni = __all_sync(kFull, sl >= npts || iv == iv0) && iv0 != 0xff && npts == kPP;
         if (sl == 0) {
+          sm.puni[pb][0] = (unsigned char)(uni ? iv0 : 0xff);
           sm.pbase[pb] = base; sm.pnpts[pb] = npts;
           if (moved) { sm.cur_base = base; sm.n_rebase++; }
         }
