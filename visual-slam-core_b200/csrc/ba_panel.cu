@@ -15,11 +15,14 @@
 //                    Y_aj = W_aj C_j (6 x 3) and stores it into the panel  Yt[4 p + d][6 a + r]  (4th row of a
 //                    point = zero pad, so that one mma k-step = one point).  No cross-lane reduction, no
 //                    private sums, no slot tables: the chain per lane is projection -> Y.
-//                    MMA warps (8): S -= Yt^T Yt with mma.sync.m8n8k4.f64 per 8 x 8 tile.  The 120 tiles of the
-//                    lower triangle of the 20-keyframe window are distributed over the warps (owner = (i + 2 j)
-//                    mod 8), ALL accumulators stay in registers for the life of a window, and a k-step only
+//                    MMA warps (8): S -= Yt^T Yt with mma.sync.m8n8k4.f64 per 8 x 8 tile.  The tiles of the lower
+//                    triangle of the 20-keyframe window are owned in strips (tile row x 16 columns, see the mma
+//                    warps below), ALL accumulators stay in registers for the life of a window, and a k-step only
 //                    touches the tiles inside the point's camera interval [cmin, cmax]: a point seen by 8
-//                    keyframes costs 28 DMMAs instead of the 120 of the dense window.
+//                    keyframes costs ~30 DMMAs instead of the 120 of the dense window.
+//                    (Tried and dropped: leaving the zero pads of a panel buffer in place when it is refilled with
+//                    the camera interval it held before -- correct, 0.957 -> 0.950 ms: the staging warps are bound
+//                    by their instruction stream per observation, not by those stores.)
 //   Points whose cameras do not fit the window, or that see a keyframe twice / out of order, take a per-lane
 //   fallback (every observation pair of the point -> float64 REDs); the window then moves to the panel's first
 //   camera (accumulators flushed by REDs, entries that are exactly zero skipped).
