@@ -551,6 +551,43 @@ __device__ __forceinline__ void obs_Y(const Intr& K, const double* __restrict__ 
   }
 }
 
+// the same, written straight into the panel: rows d = 0..2 of the point at `dst` (row stride kYS), two pose parameters at
+// a time, so that at most six results are alive together (the staging warps sit at the 128-register cap: with all 18
+// entries of Y alive the loop spilled, 17 local loads per observation)
+__device__ __forceinline__ void obs_Y_store(const Intr& K, const double* __restrict__ P, double X0, double X1, double X2,
+                                            float2 uv, double delta, const double* __restrict__ c, double* __restrict__ dst) {
+  const double2* P2 = reinterpret_cast<const double2*>(P);
+  const double2 q0 = __ldg(P2), q1 = __ldg(P2 + 1), q2 = __ldg(P2 + 2), q3 = __ldg(P2 + 3), q4 = __ldg(P2 + 4), q5 = __ldg(P2 + 5);
+  const double R0 = q0.x, R1 = q0.y, R2 = q1.x, R3 = q1.y, R4 = q2.x, R5 = q2.y, R6 = q3.x, R7 = q3.y, R8 = q4.x;
+  const double T0 = q4.y, T1 = q5.x, T2 = q5.y;
+  const double Y0 = R0 * X0 + R1 * X1 + R2 * X2;
+  const double Y1 = R3 * X0 + R4 * X1 + R5 * X2;
+  const double Y2 = R6 * X0 + R7 * X1 + R8 * X2;
+  const double xc = Y0 + T0, yc = Y1 + T1, zc = Y2 + T2;
+  const double iz = 1.0 / (zc + kDepthEps);
+  const double xz = xc * iz, yz = yc * iz;
+  const double ru = K.fx * xz + K.cx - (double)uv.x;
+  const double rv = K.fy * yz + K.cy - (double)uv.y;
+  const double wu = huber_w(ru, delta), wv = huber_w(rv, delta);
+  const double ja = K.fx * iz, jc = -K.fx * xz * iz;
+  const double jb = K.fy * iz, jd = -K.fy * yz * iz;
+  const double lu0 = ja * R0 + jc * R6, lu1 = ja * R1 + jc * R7, lu2 = ja * R2 + jc * R8;
+  const double lv0 = jb * R3 + jd * R6, lv1 = jb * R4 + jd * R7, lv2 = jb * R5 + jd * R8;
+  const double c00 = c[0], c01 = c[1], c02 = c[2], c11 = c[3], c12 = c[4], c22 = c[5];
+  const double luC0 = lu0 * c00, luC1 = lu0 * c01 + lu1 * c11, luC2 = lu0 * c02 + lu1 * c12 + lu2 * c22;
+  const double lvC0 = lv0 * c00, lvC1 = lv0 * c01 + lv1 * c11, lvC2 = lv0 * c02 + lv1 * c12 + lv2 * c22;
+  const double wja = wu * ja, wjc = wu * jc, wjb = wv * jb, wjd = wv * jd;
+  auto put = [&](int pair, double pa0, double pb0, double pa1, double pb1) {   // weighted pose Jacobian entries of two parameters
+    *reinterpret_cast<double2*>(dst + 0 * kYS + 2 * pair) = make_double2(pa0 * luC0 + pb0 * lvC0, pa1 * luC0 + pb1 * lvC0);
+    *reinterpret_cast<double2*>(dst + 1 * kYS + 2 * pair) = make_double2(pa0 * luC1 + pb0 * lvC1, pa1 * luC1 + pb1 * lvC1);
+    *reinterpret_cast<double2*>(dst + 2 * kYS + 2 * pair) = make_double2(pa0 * luC2 + pb0 * lvC2, pa1 * luC2 + pb1 * lvC2);
+  };
+  // pu = (jc Y1, ja Y2 - jc Y0, -ja Y1, ja, 0, jc), pv = (-jb Y2 + jd Y1, -jd Y0, jb Y0, 0, jb, jd), times the weights
+  put(0, wjc * Y1, wjd * Y1 - wjb * Y2, wja * Y2 - wjc * Y0, -wjd * Y0);
+  put(1, -wja * Y1, wjb * Y0, wja, 0.0);
+  put(2, 0.0, wjb, wjc, wjd);
+}
+
 // fallback for one observation of a point that cannot go through the panel: its Y against the Y of EVERY
 // observation of the point (pairs in both orders are visited by the two lanes involved, each adds the lower part)
 __device__ __noinline__ void pair_fallback(const Work& w, const double* __restrict__ pose, const StageIn& in, int i_self,
@@ -1014,15 +1051,7 @@ k_schur_panel(const __grid_constant__ Work w) {
           double* row0 = Yb + (size_t)(4 * slot) * kYS;
           // my six columns: Y (rows 0..2) and the zero pad row
           if (w.fixed[cam] == 0) {
-            YObs yo;
-            obs_Y(w.K, pose + 12 * (size_t)cam, X0, X1, X2, si.uv[e], delta, r.c, yo);
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-              double2* dst = reinterpret_cast<double2*>(row0 + d * kYS + 6 * rel);
-              dst[0] = make_double2(yo.y[0][d], yo.y[1][d]);
-              dst[1] = make_double2(yo.y[2][d], yo.y[3][d]);
-              dst[2] = make_double2(yo.y[4][d], yo.y[5][d]);
-            }
+            obs_Y_store(w.K, pose + 12 * (size_t)cam, X0, X1, X2, si.uv[e], delta, r.c, row0 + 6 * rel);
           } else {
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
