@@ -46,9 +46,24 @@ __device__ __forceinline__ double huber_rho(double r, double delta) {
   double a = fabs(r);
   return a < delta ? 0.5 * r * r : delta * (a - 0.5 * delta);
 }
+// Reciprocal without the division routine (25 instructions, a slow-path call and its convergence barriers per
+// division; every observation costs three -- depth and two Huber weights -- in each of the four passes that linearise
+// it): rcp.approx + two Newton steps, within an ulp of the quotient for the normal numbers met here.  The panel kernel's
+// staging loop went from 0.951 to 0.923 ms with it; S, b, diag U of a linearisation agree with the oracle as before
+// (3e-15 .. 1e-14 relative).
+__device__ __forceinline__ double fast_rcp(double a) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+  }
+  return r;
+}
 __device__ __forceinline__ double huber_w(double r, double delta) {
   double a = fabs(r);
-  return a < delta ? 1.0 : delta / a;
+  return a < delta ? 1.0 : delta * fast_rcp(a);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -152,7 +167,7 @@ __device__ __forceinline__ void residual_only(const Intr& K, const double* __res
   double Y1 = R[3] * X0 + R[4] * X1 + R[5] * X2;
   double Y2 = R[6] * X0 + R[7] * X1 + R[8] * X2;
   double xc = Y0 + t[0], yc = Y1 + t[1], zc = Y2 + t[2];
-  double iz = 1.0 / (zc + kDepthEps);
+  double iz = fast_rcp(zc + kDepthEps);
   ru = K.fx * (xc * iz) + K.cx - u;
   rv = K.fy * (yc * iz) + K.cy - v;
 }
@@ -166,7 +181,7 @@ __device__ __forceinline__ void linearize_obs(const Intr& K, const double* __res
   double Y1 = R[3] * X0 + R[4] * X1 + R[5] * X2;
   double Y2 = R[6] * X0 + R[7] * X1 + R[8] * X2;
   double xc = Y0 + t[0], yc = Y1 + t[1], zc = Y2 + t[2];
-  double iz = 1.0 / (zc + kDepthEps);
+  double iz = fast_rcp(zc + kDepthEps);
   double xz = xc * iz, yz = yc * iz;
   o.ru = K.fx * xz + K.cx - u;
   o.rv = K.fy * yz + K.cy - v;

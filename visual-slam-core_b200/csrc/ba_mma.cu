@@ -534,7 +534,7 @@ k_linearize_mma(const __grid_constant__ Work w) {
         Y1 = R3 * X0 + R4 * X1 + R5 * X2;
         Y2 = R6 * X0 + R7 * X1 + R8 * X2;
         const double xc = Y0 + P[9], yc = Y1 + P[10], zc = Y2 + P[11];
-        const double iz = 1.0 / (zc + kDepthEps);
+        const double iz = fast_rcp(zc + kDepthEps);
         const double xz = xc * iz, yz = yc * iz;
         ru = w.K.fx * xz + w.K.cx - (double)uv.x;
         rv = w.K.fy * yz + w.K.cy - (double)uv.y;

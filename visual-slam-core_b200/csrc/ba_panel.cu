@@ -525,7 +525,7 @@ __device__ __forceinline__ void obs_Y(const Intr& K, const double* __restrict__ 
   const double Y1 = R3 * X0 + R4 * X1 + R5 * X2;
   const double Y2 = R6 * X0 + R7 * X1 + R8 * X2;
   const double xc = Y0 + T0, yc = Y1 + T1, zc = Y2 + T2;
-  const double iz = 1.0 / (zc + kDepthEps);
+  const double iz = fast_rcp(zc + kDepthEps);
   const double xz = xc * iz, yz = yc * iz;
   const double ru = K.fx * xz + K.cx - (double)uv.x;
   const double rv = K.fy * yz + K.cy - (double)uv.y;
@@ -564,7 +564,7 @@ __device__ __forceinline__ void obs_Y_store(const Intr& K, const double* __restr
   const double Y1 = R3 * X0 + R4 * X1 + R5 * X2;
   const double Y2 = R6 * X0 + R7 * X1 + R8 * X2;
   const double xc = Y0 + T0, yc = Y1 + T1, zc = Y2 + T2;
-  const double iz = 1.0 / (zc + kDepthEps);
+  const double iz = fast_rcp(zc + kDepthEps);
   const double xz = xc * iz, yz = yc * iz;
   const double ru = K.fx * xz + K.cx - (double)uv.x;
   const double rv = K.fy * yz + K.cy - (double)uv.y;
