@@ -124,14 +124,14 @@ __device__ __forceinline__ void so3_exp_mul(const double w[3], const double R[9]
 // Same operation order as oracle/lm_oracle.py:sym3_inverse.  Non-positive pivot -> zero, false.
 __device__ __forceinline__ bool sym3_inverse(const double V[6], double inv[6]) {
   double a = V[0], b = V[1], c = V[2], d = V[3], e = V[4], f = V[5];
-  double i0 = 1.0 / a;
+  double i0 = fast_rcp(a);
   double l10 = b * i0, l20 = c * i0;
   double d1 = d - l10 * b;
   double e1 = e - l20 * b;
-  double i1 = 1.0 / d1;
+  double i1 = fast_rcp(d1);
   double l21 = e1 * i1;
   double d2 = f - l20 * c - l21 * e1;
-  double i2 = 1.0 / d2;
+  double i2 = fast_rcp(d2);
   double m10 = -l10, m20 = l10 * l21 - l20, m21 = -l21;
   inv[0] = i0 + m10 * m10 * i1 + m20 * m20 * i2;
   inv[1] = m10 * i1 + m20 * m21 * i2;
