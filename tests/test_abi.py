@@ -62,3 +62,25 @@ def test_sass_is_sm100a():
         pytest.skip("cuobjdump not present")
     out = subprocess.run([cu, "-lelf", _build.build()], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_diagnostic_library_override(monkeypatch, tmp_path):
+    """`BA_LIB_PATH` points `_lib` at a diagnostic build of the same library (`_build.build(out=..., extra=[...])`);
+    without it the in-tree `libb200ba.so` is the only library the product loads."""
+    from visual_slam_core_b200 import _build, _lib
+    monkeypatch.delenv("BA_LIB_PATH", raising=False)
+    assert _lib.lib_path() == _build.LIB_PATH
+    other = str(tmp_path / "libb200ba_trace.so")
+    monkeypatch.setenv("BA_LIB_PATH", other)
+    assert _lib.lib_path() == other
+
+
+def test_report_mirror_matches_the_header():
+    """Every field of `ba_report` in include/b200ba.h has its ctypes twin, in order (a mismatch would shift the report)."""
+    import re
+    from visual_slam_core_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "b200ba.h")).read()
+    body = src[src.index("typedef struct ba_report"):src.index("} ba_report;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"\b(?:int32_t|uint8_t|float|double)\s+(\w+)\s*(?:\[[^\]]*\])?\s*;", body)
+    assert names == [f[0] for f in _lib.BAReport._fields_]
